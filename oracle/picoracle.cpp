@@ -1,0 +1,1484 @@
+// picoracle — CPU restatement of PIConGPU's core PIC step (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+//
+// This file is the parity oracle for picongpu_b200.  It restates, in plain C++17 (fp32, no FMA
+// contraction: build with -ffp-contract=off), the arithmetic of the reference's hot path so that the
+// CUDA kernels can be compared against it on identical inputs.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load this library.
+//
+// Parity status: PINNED by the reference's own known-answer tests (tests/test_oracle_golden.py):
+//   * share/picongpu/unit/MoveParticle.cpp:98-202   (7 cell/supercell crossing scenarios)
+//   * share/picongpu/unit/shape.cpp:176-207         (partition of unity, mt19937(42), on/off support)
+//   * include/pmacc/test/particles/memory/SuperCell.hpp:69-98 (last-frame arithmetic)
+//   * share/picongpu/tests/CurrentDeposition (Python Esirkepov reference imported from the reference
+//     tree to generate tests/golden/current_deposition.npz)
+//   * share/picongpu/tests/Pusher/README.rst        (gyro radius / phase drift bounds)
+// The reference binary itself cannot be built in this image (needs Boost + MPI), see DESIGN.md.
+//
+// All paths cited below are relative to /root/reference/include/ unless stated otherwise
+// (P/ = picongpu/, M/ = pmacc/).
+//
+// Data conventions (shared with the CUDA library):
+//   * local domain n[3] cells, guard g[3] cells per side (GuardSize * SuperCellSize), padded N = n + 2g
+//   * fields are SoA: F[c][z][y][x], x fastest, index ((z*Ny + y)*Nx + x), local cell (0,0,0) at (g0,g1,g2)
+//   * particles: pos[3][np] in-cell [0,1), mom[3][np], w[np], cell[np] = cx + n0*(cy + n1*cz)
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <random>
+#include <vector>
+#ifdef _OPENMP
+#    include <omp.h>
+#endif
+
+extern "C"
+{
+    struct OrcParams
+    {
+        int n[3]; // local cells (no guard)
+        int sc[3]; // SuperCellSize (P/param/memory.param:51)
+        int g[3]; // guard cells per side
+        float cell[3]; // sim.pic.getCellSize()
+        float dt; // sim.pic.getDt()
+        float c; // sim.pic.getSpeedOfLight()
+        float eps0; // sim.pic.getEps0()
+        float mue0; // sim.pic.getMue0()
+        float base_mass; // sim.pic.getBaseMass()
+        float base_charge; // sim.pic.getBaseCharge()
+        int shape; // 0 NGP, 1 CIC, 2 TSC, 3 PQS, 4 PCS
+        int pusher; // 0 Boris, 1 Vay
+        int current; // 0 Esirkepov, 1 EmZ
+        int solver; // 0 Yee, 1 Lehe
+        int lehe_dir; // Cherenkov-free direction for Lehe
+        int wrap[3]; // 1: periodic wrap inside this domain; 0: leaving particles get cell coordinate -1 / n
+    };
+}
+
+namespace
+{
+    using f32 = float;
+
+    // ---------------------------------------------------------------------------------------------
+    // Shapes: P/particles/shapes/{NGP,CIC,TSC,PQS,PCS}.hpp
+    // ---------------------------------------------------------------------------------------------
+    constexpr int MAXS = 6; // support+1 of PCS
+
+    inline int shapeSupport(int shape)
+    {
+        return shape + 1;
+    }
+
+    // TSC.hpp:47-64
+    inline f32 tsc_r1(f32 x)
+    {
+        f32 const sq = x * x;
+        return 0.75f - sq;
+    }
+    inline f32 tsc_r2(f32 x)
+    {
+        f32 const tmp = 3.0f / 2.0f - x;
+        f32 const sq = tmp * tmp;
+        return 0.5f * sq;
+    }
+    // PQS.hpp:47-66
+    inline f32 pqs_r1(f32 x)
+    {
+        f32 const sq = x * x;
+        f32 const tr = sq * x;
+        return 1.0f / 6.0f * (4.0f - 6.0f * sq + 3.0f * tr);
+    }
+    inline f32 pqs_r2(f32 x)
+    {
+        f32 const tmp = 2.0f - x;
+        f32 const tr = tmp * tmp * tmp;
+        return 1.0f / 6.0f * tr;
+    }
+    // PCS.hpp:47-77
+    inline f32 pcs_r1(f32 x)
+    {
+        f32 const sq = x * x;
+        return 115.f / 192.f + sq * (-5.f / 8.f + 1.0f / 4.0f * sq);
+    }
+    inline f32 pcs_r2(f32 x)
+    {
+        return 1.f / 96.f * (55.f + 4.f * x * (5.f - 2.f * x * (15.f + 2.f * x * (-5.f + x))));
+    }
+    inline f32 pcs_r3(f32 x)
+    {
+        f32 const tmp = 5.f - 2.f * x;
+        f32 const sq = tmp * tmp;
+        f32 const bi = sq * sq;
+        return 1.f / 384.f * bi;
+    }
+
+    /** detail::<Shape>::shapeArray — values on the support points, particle on support.
+     * NGP.hpp:58-65, CIC.hpp:58-69, TSC.hpp:76-88, PQS.hpp:77-90, PCS.hpp:88-102 */
+    inline void shapeArrayOnSupport(int shape, f32 x, f32* v)
+    {
+        switch(shape)
+        {
+        case 0:
+            v[0] = 1.0f;
+            break;
+        case 1:
+            v[0] = 1.0f - x;
+            v[1] = x;
+            break;
+        case 2:
+            v[0] = tsc_r2(std::fabs(-1.f - x));
+            v[1] = tsc_r1(std::fabs(x));
+            v[2] = 1.0f - (v[0] + v[1]);
+            break;
+        case 3:
+            v[0] = pqs_r2(std::fabs(-1.f - x));
+            v[1] = pqs_r1(x);
+            v[3] = pqs_r2(2.f - x);
+            v[2] = 1.0f - (v[0] + v[1] + v[3]);
+            break;
+        default:
+            v[0] = pcs_r3(std::fabs(-2.f - x));
+            v[1] = pcs_r2(std::fabs(-1.f - x));
+            v[2] = pcs_r1(std::fabs(x));
+            v[4] = pcs_r3(2.f - x);
+            v[3] = 1.0f - (v[0] + v[1] + v[2] + v[4]);
+            break;
+        }
+    }
+
+    /** ChargeAssignment::shapeArray(x, isOutOfRange) — support+1 values, shifted by one slot if the
+     * particle sits in the neighbouring assignment cell (e.g. TSC.hpp:140-153). */
+    inline void shapeArrayOffSupport(int shape, f32 xx, bool isOutOfRange, f32* v)
+    {
+        int const supp = shapeSupport(shape);
+        f32 const x = isOutOfRange ? xx - 1.0f : xx;
+        f32 t[MAXS];
+        shapeArrayOnSupport(shape, x, t);
+        // identical select chain as the reference, written as a loop from the top slot downwards
+        v[supp] = isOutOfRange ? t[supp - 1] : 0.0f;
+        for(int i = supp - 1; i >= 1; --i)
+            v[i] = isOutOfRange ? t[i - 1] : t[i];
+        v[0] = isOutOfRange ? 0.0f : t[0];
+    }
+
+    /** ChargeAssignmentOnSupport::operator()(x): NGP.hpp:127-133, CIC.hpp:141-147, TSC.hpp:161-185,
+     * PQS.hpp:163-186, PCS.hpp:190-214 */
+    inline f32 shapeEvalOnSupport(int shape, f32 x)
+    {
+        f32 const a = std::fabs(x);
+        switch(shape)
+        {
+        case 0:
+            return 1.0f;
+        case 1:
+            return 1.0f - a;
+        case 2:
+        {
+            f32 const r1 = tsc_r1(a), r2 = tsc_r2(a);
+            return a < 0.5f ? r1 : r2;
+        }
+        case 3:
+        {
+            f32 const r1 = pqs_r1(a), r2 = pqs_r2(a);
+            return a < 1.0f ? r1 : r2;
+        }
+        default:
+        {
+            f32 const r1 = pcs_r1(a), r2 = pcs_r2(a), r3 = pcs_r3(a);
+            f32 r = r3;
+            if(a < 0.5f)
+                r = r1;
+            else if(a < 1.5f)
+                r = r2;
+            return r;
+        }
+        }
+    }
+
+    /** ChargeAssignment::operator()(x): NGP.hpp:80-95, CIC.hpp:88-106, TSC.hpp:108-131, PQS.hpp:110-133,
+     * PCS.hpp:123-148 */
+    inline f32 shapeEval(int shape, f32 x)
+    {
+        f32 const a = std::fabs(x);
+        switch(shape)
+        {
+        case 0:
+            return f32(-0.5f <= x && x < 0.5f);
+        case 1:
+            return a < 1.0f ? 1.0f - a : 0.0f;
+        case 2:
+        {
+            f32 const r1 = tsc_r1(a), r2 = tsc_r2(a);
+            f32 r = 0.0f;
+            if(a < 0.5f)
+                r = r1;
+            else if(a < 1.5f)
+                r = r2;
+            return r;
+        }
+        case 3:
+        {
+            f32 const r1 = pqs_r1(a), r2 = pqs_r2(a);
+            f32 r = 0.0f;
+            if(a < 1.0f)
+                r = r1;
+            else if(a < 2.0f)
+                r = r2;
+            return r;
+        }
+        default:
+        {
+            f32 const on = shapeEvalOnSupport(4, a);
+            return a < 2.5f ? on : 0.0f;
+        }
+        }
+    }
+
+    // begin offsets: ChargeAssignment(OnSupport)::begin
+    inline int shapeBegin(int shape)
+    {
+        static int const b[5] = {0, 0, -1, -1, -2};
+        return b[shape];
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Domain helpers
+    // ---------------------------------------------------------------------------------------------
+    struct Dom
+    {
+        int n[3], g[3], N[3], sc[3], nsc[3];
+        int64_t vol;
+        explicit Dom(OrcParams const& p)
+        {
+            for(int d = 0; d < 3; ++d)
+            {
+                n[d] = p.n[d];
+                g[d] = p.g[d];
+                N[d] = n[d] + 2 * g[d];
+                sc[d] = p.sc[d];
+                nsc[d] = n[d] / sc[d];
+            }
+            vol = int64_t(N[0]) * N[1] * N[2];
+        }
+        inline int64_t idx(int x, int y, int z) const
+        {
+            return (int64_t(z) * N[1] + y) * N[0] + x;
+        }
+    };
+
+    struct Field3
+    {
+        f32* c[3];
+        Field3(f32* base, int64_t vol)
+        {
+            c[0] = base;
+            c[1] = base + vol;
+            c[2] = base + 2 * vol;
+        }
+    };
+
+    // ---------------------------------------------------------------------------------------------
+    // Field -> particle interpolation
+    // P/algorithms/FieldToParticleInterpolation.hpp:97-124, AssignedTrilinearInterpolation.hpp:54-86,
+    // ShiftCoordinateSystem.hpp:54-79, P/fields/YeeCell.hpp:70-130
+    // ---------------------------------------------------------------------------------------------
+    f32 const fieldPosE[3][3] = {{0.5f, 0.f, 0.f}, {0.f, 0.5f, 0.f}, {0.f, 0.f, 0.5f}};
+    f32 const fieldPosB[3][3] = {{0.f, 0.5f, 0.5f}, {0.5f, 0.f, 0.5f}, {0.5f, 0.5f, 0.f}};
+
+    inline f32 interpolateComponent(
+        Dom const& D,
+        f32 const* F,
+        int shape,
+        int const cellG[3], // particle cell incl. guard offset
+        f32 const pos[3],
+        f32 const fpos[3])
+    {
+        int const supp = shapeSupport(shape);
+        bool const isEven = (supp % 2) == 0;
+        int const begin = -supp / 2 + (supp + 1) % 2;
+        int const end = begin + supp - 1;
+        f32 S[3][MAXS];
+        int base[3];
+        for(int d = 0; d < 3; ++d)
+        {
+            f32 const v_pos = pos[d] - fpos[d] - 0.5f;
+            int shift;
+            if(isEven)
+                shift = v_pos >= -0.5f ? 0 : -1;
+            else
+                shift = v_pos >= 0.0f ? 1 : 0;
+            f32 const p = v_pos - f32(shift) + 0.5f;
+            base[d] = cellG[d] + shift;
+            // shapes::Cached<ChargeAssignmentOnSupport>(pos, true) -> shapeArray(pos, false)
+            shapeArrayOnSupport(shape, p, S[d]);
+        }
+        f32 result_z = 0.0f;
+        for(int z = begin; z <= end; ++z)
+        {
+            f32 result_y = 0.0f;
+            for(int y = begin; y <= end; ++y)
+            {
+                f32 result_x = 0.0f;
+                for(int x = begin; x <= end; ++x)
+                    result_x += F[D.idx(base[0] + x, base[1] + y, base[2] + z)] * S[0][x - begin];
+                result_y += result_x * S[1][y - begin];
+            }
+            result_z += result_y * S[2][z - begin];
+        }
+        return result_z;
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Pushers.  P/particles/pusher/particlePusherBoris.hpp:42-91, particlePusherVay.hpp:43-112,
+    // P/algorithms/Gamma.hpp:30-38, Velocity.hpp:28-38 (CPU backend: rsqrt == 1/sqrt)
+    // ---------------------------------------------------------------------------------------------
+    inline f32 l2norm2(f32 const v[3])
+    {
+        f32 tmp = v[0] * v[0];
+        tmp += v[1] * v[1];
+        tmp += v[2] * v[2];
+        return tmp;
+    }
+    inline void cross(f32 const a[3], f32 const b[3], f32 r[3])
+    {
+        r[0] = a[1] * b[2] - a[2] * b[1];
+        r[1] = a[2] * b[0] - a[0] * b[2];
+        r[2] = a[0] * b[1] - a[1] * b[0];
+    }
+    inline f32 gammaF(OrcParams const& P, f32 const mom[3], f32 mass)
+    {
+        f32 const fMom2 = l2norm2(mom);
+        f32 const c2 = P.c * P.c;
+        f32 const m2_c2_reci = 1.0f / (mass * mass * c2);
+        return std::sqrt(1.0f + fMom2 * m2_c2_reci);
+    }
+    inline void velocityF(OrcParams const& P, f32 const mom[3], f32 mass0, f32 vel[3])
+    {
+        f32 const rc2 = f32(1. / double(P.c) / double(P.c)); // getMue0Eps0()
+        f32 const m0_2 = mass0 * mass0;
+        f32 const fMom2 = l2norm2(mom);
+        f32 const t = 1.0f / std::sqrt(m0_2 + fMom2 * rc2);
+        for(int d = 0; d < 3; ++d)
+            vel[d] = t * mom[d];
+    }
+
+    inline void pushBoris(OrcParams const& P, f32 mass, f32 charge, f32 const E[3], f32 const B[3], f32 mom[3], f32 pos[3])
+    {
+        f32 const QoM = charge / mass;
+        f32 const dt = P.dt;
+        f32 mom_minus[3], t[3], s[3], tmp[3], mom_prime[3], mom_plus[3], vel[3];
+        for(int d = 0; d < 3; ++d)
+            mom_minus[d] = mom[d] + 0.5f * charge * E[d] * dt;
+        f32 const gamma_reci = 1.0f / gammaF(P, mom_minus, mass);
+        for(int d = 0; d < 3; ++d)
+            t[d] = 0.5f * QoM * B[d] * gamma_reci * dt;
+        f32 const sfac = 1.0f / (1.0f + l2norm2(t));
+        for(int d = 0; d < 3; ++d)
+            s[d] = 2.0f * t[d] * sfac;
+        cross(mom_minus, t, tmp);
+        for(int d = 0; d < 3; ++d)
+            mom_prime[d] = mom_minus[d] + tmp[d];
+        cross(mom_prime, s, tmp);
+        for(int d = 0; d < 3; ++d)
+            mom_plus[d] = mom_minus[d] + tmp[d];
+        for(int d = 0; d < 3; ++d)
+            mom[d] = mom_plus[d] + 0.5f * charge * E[d] * dt;
+        velocityF(P, mom, mass, vel);
+        for(int d = 0; d < 3; ++d)
+            pos[d] += (vel[d] * dt) / P.cell[d];
+    }
+
+    inline void pushVay(OrcParams const& P, f32 mass, f32 charge, f32 const E[3], f32 const B[3], f32 mom[3], f32 pos[3])
+    {
+        f32 const dt = P.dt;
+        f32 const factor = f32(0.5 * double(charge) * double(dt)); // `0.5 * charge * deltaT` promotes to double
+        f32 vel0[3], cr[3], mom0[3], momp[3];
+        velocityF(P, mom, mass, vel0);
+        cross(vel0, B, cr);
+        for(int d = 0; d < 3; ++d)
+            mom0[d] = mom[d] + factor * (E[d] + cr[d]);
+        for(int d = 0; d < 3; ++d)
+            momp[d] = mom0[d] + factor * E[d];
+        f32 const gamma_prime = gammaF(P, momp, mass);
+        // sqrt_Vay = precision64Bit (P/param/pusher.param:62)
+        double tau[3];
+        for(int d = 0; d < 3; ++d)
+            tau[d] = double(factor / mass * B[d]);
+        double dotpt = double(momp[0]) * tau[0];
+        dotpt += double(momp[1]) * tau[1];
+        dotpt += double(momp[2]) * tau[2];
+        double const u_star = dotpt / double(P.c * mass);
+        double tau2 = tau[0] * tau[0];
+        tau2 += tau[1] * tau[1];
+        tau2 += tau[2] * tau[2];
+        double const sigma = double(gamma_prime * gamma_prime) - tau2;
+        double const gamma_plus = std::sqrt(0.5 * (sigma + std::sqrt(sigma * sigma + 4.0 * (tau2 + u_star * u_star))));
+        f32 t[3];
+        for(int d = 0; d < 3; ++d)
+            t[d] = f32(tau[d] * double(1.0f / gamma_plus));
+        f32 const s = 1.0f / (1.0f + l2norm2(t));
+        f32 dpt = momp[0] * t[0];
+        dpt += momp[1] * t[1];
+        dpt += momp[2] * t[2];
+        cross(momp, t, cr);
+        for(int d = 0; d < 3; ++d)
+            mom[d] = s * (momp[d] + dpt * t[d] + cr[d]);
+        f32 vel[3];
+        velocityF(P, mom, mass, vel);
+        for(int d = 0; d < 3; ++d)
+            pos[d] += (vel[d] * dt) / P.cell[d];
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // moveParticle: P/particles/MoveParticle.hpp:48-160
+    // ---------------------------------------------------------------------------------------------
+    /** @param localCell in/out cell coordinates inside the supercell
+     *  @param dirOut per-dimension cell crossing direction (before masking to supercell crossings)
+     *  @return multiMask (1 = stays in supercell, >=2 leaves into direction multiMask-1) */
+    inline int moveParticle(int const sc[3], f32 const newPos[3], f32 posOut[3], int localCell[3], int dirOut[3])
+    {
+        f32 const shift = 0.5f;
+        int dir[3];
+        for(int i = 0; i < 3; ++i)
+        {
+            f32 pos = newPos[i] - shift;
+            f32 moveDir = 0.0f;
+            if(pos < -0.5f)
+                moveDir = -1.0f;
+            if(pos >= 0.5f)
+                moveDir = 1.0f;
+            pos -= moveDir;
+            posOut[i] = pos + shift;
+            dir[i] = int(moveDir);
+            dirOut[i] = dir[i];
+        }
+        int newMultimask = 1;
+        if(dir[0] != 0 || dir[1] != 0 || dir[2] != 0)
+        {
+            for(int i = 0; i < 3; ++i)
+                localCell[i] += dir[i];
+            for(int i = 0; i < 3; ++i)
+                dir[i] = uint32_t(localCell[i]) >= uint32_t(sc[i]) ? dir[i] : 0;
+            for(int i = 0; i < 3; ++i)
+                localCell[i] -= dir[i] * sc[i];
+            uint32_t exchangeType = 1;
+            for(int i = 0; i < 3; ++i)
+            {
+                newMultimask += (dir[i] == -1 ? 2 : dir[i]) * int(exchangeType);
+                exchangeType *= 3;
+            }
+        }
+        return newMultimask;
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Current deposition.  P/fields/FieldJ.kernel:110-142, currentDeposition/Esirkepov/Esirkepov.hpp:62-242,
+    // relayPoint.hpp:48-63, EmZ/EmZ.hpp:66-155, EmZ/DepositCurrent.hpp:35-119,
+    // PermutatedFieldValueAccess.hpp:77-99
+    // ---------------------------------------------------------------------------------------------
+    inline f32 relayPoint(bool isEven, int& i_1, int& i_2, f32 x_1, f32 x_2)
+    {
+        if(isEven)
+        {
+            i_1 = int(std::floor(x_1));
+            i_2 = int(std::floor(x_2));
+            return i_1 == i_2 ? x_2 : f32(std::max(i_1, i_2));
+        }
+        i_1 = int(std::floor(x_1 + 0.5f));
+        i_2 = int(std::floor(x_2 + 0.5f));
+        return i_1 == i_2 ? x_2 : f32(i_1 + i_2) / 2.0f;
+    }
+
+    /** Accumulator: adds `val` to component `comp` of J at cell (base + off). */
+    struct JAcc
+    {
+        Dom const* D;
+        f32* J[3];
+        inline void add(int comp, int x, int y, int z, f32 val) const
+        {
+            J[comp][D->idx(x, y, z)] += val;
+        }
+    };
+
+    /** Esirkepov::cptCurrent1D (Esirkepov.hpp:147-242) for one rotated direction.
+     * perm: rotated axis r -> original axis perm[r]; component = perm[2]. */
+    inline void esirkepovCpt1D(
+        OrcParams const& P,
+        JAcc const& acc,
+        int shape,
+        int const status[3], // rotated
+        int const baseCell[3], // original coordinates (already shifted by gridShift)
+        f32 const pos0[3], // rotated
+        f32 const pos1[3],
+        int const perm[3],
+        f32 cellEdgeLength,
+        f32 charge)
+    {
+        if(pos0[2] == pos1[2])
+            return;
+        int const supp = shapeSupport(shape);
+        int const begin = shapeBegin(shape);
+        int const end = begin + supp;
+        f32 S0[3][MAXS], S1[3][MAXS];
+        for(int r = 0; r < 3; ++r)
+        {
+            bool const startIn = (status[r] & 2) != 0;
+            bool const endIn = (status[r] & 4) != 0;
+            // shapes::Cached<ChargeAssignment>(pos, isInBase) -> shapeArray(pos, !isInBase)
+            shapeArrayOffSupport(shape, pos0[r], !startIn, S0[r]);
+            shapeArrayOffSupport(shape, pos1[r], !endIn, S1[r]);
+        }
+        f32 const vol = P.cell[0] * P.cell[1] * P.cell[2];
+        f32 const currentSurfaceDensity = charge * (1.0f / f32(vol * P.dt)) * cellEdgeLength;
+        int const leaveI = status[0] & 1, leaveJ = status[1] & 1, leaveK = status[2] & 1;
+        for(int i = begin; i < end + 1; ++i)
+            if(i < end + leaveI)
+            {
+                f32 const s0i = S0[0][i - begin];
+                f32 const dsi = S1[0][i - begin] - s0i;
+                for(int j = begin; j < end + 1; ++j)
+                    if(j < end + leaveJ)
+                    {
+                        f32 const s0j = S0[1][j - begin];
+                        f32 const dsj = S1[1][j - begin] - s0j;
+                        f32 const tmp = -currentSurfaceDensity
+                            * (s0i * s0j + 0.5f * (dsi * s0j + s0i * dsj) + (1.0f / 3.0f) * dsj * dsi);
+                        f32 accumulated_J = 0.0f;
+                        for(int k = begin; k < end; ++k)
+                            if(k < end + leaveK - 1)
+                            {
+                                f32 const W = (S1[2][k - begin] - S0[2][k - begin]) * tmp;
+                                accumulated_J += W;
+                                int o[3];
+                                o[perm[0]] = i;
+                                o[perm[1]] = j;
+                                o[perm[2]] = k;
+                                acc.add(perm[2], baseCell[0] + o[0], baseCell[1] + o[1], baseCell[2] + o[2], accumulated_J);
+                            }
+                    }
+            }
+    }
+
+    inline void depositEsirkepov(
+        OrcParams const& P,
+        JAcc const& acc,
+        int const cellG[3],
+        f32 const pos[3],
+        f32 const vel[3],
+        f32 charge)
+    {
+        int const shape = P.shape;
+        bool const isEven = (shapeSupport(shape) % 2) == 0;
+        f32 p0[3], p1[3];
+        int status[3] = {0, 0, 0};
+        int base[3];
+        for(int d = 0; d < 3; ++d)
+        {
+            f32 const deltaPos = vel[d] * P.dt / P.cell[d];
+            p0[d] = pos[d] - deltaPos;
+            p1[d] = pos[d];
+            int iStart, iEnd;
+            relayPoint(isEven, iStart, iEnd, p0[d], p1[d]);
+            int const gridShift = iStart < iEnd ? iStart : iEnd;
+            status[d] |= (gridShift == iStart) ? 2 : 0;
+            status[d] |= (gridShift == iEnd) ? 4 : 0;
+            status[d] |= (iStart != iEnd) ? 1 : 0;
+            p0[d] -= f32(gridShift);
+            p1[d] -= f32(gridShift);
+            base[d] = cellG[d] + gridShift;
+        }
+        {
+            int const perm[3] = {1, 2, 0};
+            int const st[3] = {status[1], status[2], status[0]};
+            f32 const a0[3] = {p0[1], p0[2], p0[0]}, a1[3] = {p1[1], p1[2], p1[0]};
+            esirkepovCpt1D(P, acc, shape, st, base, a0, a1, perm, P.cell[0], charge);
+        }
+        {
+            int const perm[3] = {2, 0, 1};
+            int const st[3] = {status[2], status[0], status[1]};
+            f32 const a0[3] = {p0[2], p0[0], p0[1]}, a1[3] = {p1[2], p1[0], p1[1]};
+            esirkepovCpt1D(P, acc, shape, st, base, a0, a1, perm, P.cell[1], charge);
+        }
+        {
+            int const perm[3] = {0, 1, 2};
+            esirkepovCpt1D(P, acc, shape, status, base, p0, p1, perm, P.cell[2], charge);
+        }
+    }
+
+    /** emz::DepositCurrent<...,DIM3>::cptCurrent1D (EmZ/DepositCurrent.hpp:77-118) */
+    inline void emzCpt1D(
+        JAcc const& acc,
+        int shape,
+        int const baseCell[3],
+        f32 const pos0[3],
+        f32 const pos1[3],
+        int const perm[3],
+        f32 currentSurfaceDensity)
+    {
+        if(pos0[2] == pos1[2])
+            return;
+        int const supp = shapeSupport(shape);
+        int const begin = shapeBegin(shape);
+        int const end = begin + supp;
+        f32 S0[3][MAXS], S1[3][MAXS];
+        for(int r = 0; r < 3; ++r)
+        {
+            shapeArrayOnSupport(shape, pos0[r], S0[r]);
+            shapeArrayOnSupport(shape, pos1[r], S1[r]);
+        }
+        for(int i = begin; i < end; ++i)
+        {
+            f32 const s0i = S0[0][i - begin];
+            f32 const dsi = S1[0][i - begin] - s0i;
+            for(int j = begin; j < end; ++j)
+            {
+                f32 const s0j = S0[1][j - begin];
+                f32 const dsj = S1[1][j - begin] - s0j;
+                f32 const tmp
+                    = -currentSurfaceDensity * (s0i * s0j + 0.5f * (dsi * s0j + s0i * dsj) + (1.0f / 3.0f) * dsj * dsi);
+                f32 accumulated_J = 0.0f;
+                for(int k = begin; k < end - 1; ++k)
+                {
+                    f32 const W = (S1[2][k - begin] - S0[2][k - begin]) * tmp;
+                    accumulated_J += W;
+                    int o[3];
+                    o[perm[0]] = i;
+                    o[perm[1]] = j;
+                    o[perm[2]] = k;
+                    acc.add(perm[2], baseCell[0] + o[0], baseCell[1] + o[1], baseCell[2] + o[2], accumulated_J);
+                }
+            }
+        }
+    }
+
+    inline void emzDeposit3(
+        OrcParams const& P,
+        JAcc const& acc,
+        int shape,
+        int const base[3],
+        f32 const p0[3],
+        f32 const p1[3],
+        f32 chargeDensity)
+    {
+        {
+            int const perm[3] = {1, 2, 0};
+            f32 const a0[3] = {p0[1], p0[2], p0[0]}, a1[3] = {p1[1], p1[2], p1[0]};
+            emzCpt1D(acc, shape, base, a0, a1, perm, P.cell[0] * chargeDensity / P.dt);
+        }
+        {
+            int const perm[3] = {2, 0, 1};
+            f32 const a0[3] = {p0[2], p0[0], p0[1]}, a1[3] = {p1[2], p1[0], p1[1]};
+            emzCpt1D(acc, shape, base, a0, a1, perm, P.cell[1] * chargeDensity / P.dt);
+        }
+        {
+            int const perm[3] = {0, 1, 2};
+            emzCpt1D(acc, shape, base, p0, p1, perm, P.cell[2] * chargeDensity / P.dt);
+        }
+    }
+
+    inline void depositEmZ(
+        OrcParams const& P,
+        JAcc const& acc,
+        int const cellG[3],
+        f32 const posEnd[3],
+        f32 const vel[3],
+        f32 charge)
+    {
+        int const shape = P.shape;
+        bool const isEven = (shapeSupport(shape) % 2) == 0;
+        f32 posStart[3], relay[3];
+        int shiftStart[3], shiftEnd[3];
+        for(int d = 0; d < 3; ++d)
+        {
+            f32 const deltaPos = (vel[d] * P.dt) / P.cell[d];
+            posStart[d] = posEnd[d] - deltaPos;
+            relay[d] = relayPoint(isEven, shiftStart[d], shiftEnd[d], posStart[d], posEnd[d]);
+        }
+        f32 const chargeDensity = charge / (P.cell[0] * P.cell[1] * P.cell[2]);
+        f32 l0[3], l1[3];
+        int base[3];
+        for(int d = 0; d < 3; ++d)
+        {
+            l0[d] = posStart[d] - f32(shiftStart[d]);
+            l1[d] = relay[d] - f32(shiftStart[d]);
+            base[d] = cellG[d] + shiftStart[d];
+        }
+        emzDeposit3(P, acc, shape, base, l0, l1, chargeDensity);
+        bool const two = shiftStart[0] != shiftEnd[0] || shiftStart[1] != shiftEnd[1] || shiftStart[2] != shiftEnd[2];
+        if(two)
+        {
+            for(int d = 0; d < 3; ++d)
+            {
+                l1[d] = posEnd[d] - f32(shiftEnd[d]);
+                l0[d] = relay[d] - f32(shiftEnd[d]);
+                base[d] = cellG[d] + shiftEnd[d];
+            }
+            emzDeposit3(P, acc, shape, base, l0, l1, chargeDensity);
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Field solver.  P/fields/MaxwellSolver/FDTD/FDTDBase.kernel:51-124, differentiation/Curl.hpp:84-90,
+    // ForwardDerivative.hpp:58-63, BackwardDerivative.hpp:58-63, Lehe/Derivative.hpp:66-236
+    // ---------------------------------------------------------------------------------------------
+    struct LeheCoeff
+    {
+        f32 alpha, delta, betaDir1, betaDir2;
+    };
+
+    inline LeheCoeff leheCoeff(OrcParams const& P, int dir0)
+    {
+        // Lehe/Derivative.hpp:94-111 (float_64 arithmetic on the float_X PIC-unit values), :134-137 (fp32 betas)
+        int const dir1 = (dir0 + 1) % 3, dir2 = (dir0 + 2) % 3;
+        LeheCoeff r;
+        double const stepRatio = double(P.cell[dir0] / (P.c * P.dt));
+        double const coeff = stepRatio * std::sin(1.5707963267948966 * double(P.c) * double(P.dt) / double(P.cell[dir0]));
+        r.delta = f32(0.25 * (1.0 - coeff * coeff));
+        double const sr1 = double(P.cell[dir0] / P.cell[dir1]);
+        double const sr2 = double(P.cell[dir0] / P.cell[dir2]);
+        double const b1 = 0.125 * sr1 * sr1, b2 = 0.125 * sr2 * sr2;
+        r.alpha = f32(1.0 - 2.0 * b1 - 2.0 * b2 - 3.0 * double(r.delta));
+        f32 const s1 = P.cell[dir0] / P.cell[dir1], s2 = P.cell[dir0] / P.cell[dir2];
+        r.betaDir1 = 0.125f * s1 * s1;
+        r.betaDir2 = 0.125f * s2 * s2;
+        return r;
+    }
+
+    /** derivative along `dir` of all three components at (x,y,z); mode 0 forward, 1 backward, 2 Lehe */
+    inline void derivative(
+        OrcParams const& P,
+        Dom const& D,
+        Field3 const& F,
+        int mode,
+        LeheCoeff const& lc,
+        int dir,
+        int x,
+        int y,
+        int z,
+        f32 out[3])
+    {
+        auto at = [&](int c, int dx, int dy, int dz) { return F.c[c][D.idx(x + dx, y + dy, z + dz)]; };
+        int e[3] = {0, 0, 0};
+        e[dir] = 1;
+        auto fwd = [&](int c, int ox, int oy, int oz)
+        { return (at(c, ox + e[0], oy + e[1], oz + e[2]) - at(c, ox, oy, oz)) / P.cell[dir]; };
+        if(mode == 0)
+        {
+            for(int c = 0; c < 3; ++c)
+                out[c] = fwd(c, 0, 0, 0);
+        }
+        else if(mode == 1)
+        {
+            for(int c = 0; c < 3; ++c)
+                out[c] = (at(c, 0, 0, 0) - at(c, -e[0], -e[1], -e[2])) / P.cell[dir];
+        }
+        else
+        {
+            int const cf = P.lehe_dir;
+            if(dir == cf)
+            {
+                int const dir1 = (dir + 1) % 3, dir2 = (dir + 2) % 3;
+                int u1[3] = {0, 0, 0}, u2[3] = {0, 0, 0};
+                u1[dir1] = 1;
+                u2[dir2] = 1;
+                for(int c = 0; c < 3; ++c)
+                {
+                    f32 r = lc.alpha * fwd(c, 0, 0, 0) + lc.betaDir1 * fwd(c, u1[0], u1[1], u1[2]);
+                    r = r + lc.betaDir1 * fwd(c, -u1[0], -u1[1], -u1[2]);
+                    r = r + lc.betaDir2 * fwd(c, u2[0], u2[1], u2[2]);
+                    r = r + lc.betaDir2 * fwd(c, -u2[0], -u2[1], -u2[2]);
+                    r = r + lc.delta * (at(c, 2 * e[0], 2 * e[1], 2 * e[2]) - at(c, -e[0], -e[1], -e[2])) / P.cell[dir];
+                    out[c] = r;
+                }
+            }
+            else
+            {
+                f32 const beta = 0.125f;
+                f32 const alpha = 1.0f - 2.0f * beta;
+                int u[3] = {0, 0, 0};
+                u[cf] = 1;
+                for(int c = 0; c < 3; ++c)
+                {
+                    f32 r = alpha * fwd(c, 0, 0, 0) + beta * fwd(c, u[0], u[1], u[2]);
+                    r = r + beta * fwd(c, -u[0], -u[1], -u[2]);
+                    out[c] = r;
+                }
+            }
+        }
+    }
+
+    inline void curlAt(
+        OrcParams const& P,
+        Dom const& D,
+        Field3 const& F,
+        int mode,
+        LeheCoeff const* lc,
+        int x,
+        int y,
+        int z,
+        f32 out[3])
+    {
+        f32 dx[3], dy[3], dz[3];
+        derivative(P, D, F, mode, lc[0], 0, x, y, z, dx);
+        derivative(P, D, F, mode, lc[1], 1, x, y, z, dy);
+        derivative(P, D, F, mode, lc[2], 2, x, y, z, dz);
+        out[0] = dy[2] - dz[1];
+        out[1] = dz[0] - dx[2];
+        out[2] = dx[1] - dy[0];
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Counter based RNG for the IC generator: Philox4x32-10 (Salmon et al. 2011), documented layout:
+    // key = (seed, species), counter = (particle index lo, hi, stream, 0).
+    // ---------------------------------------------------------------------------------------------
+    inline void philox4x32_10(uint32_t ctr[4], uint32_t const key_in[2])
+    {
+        uint32_t key[2] = {key_in[0], key_in[1]};
+        for(int r = 0; r < 10; ++r)
+        {
+            uint64_t const p0 = uint64_t(0xD2511F53u) * ctr[0];
+            uint64_t const p1 = uint64_t(0xCD9E8D57u) * ctr[2];
+            uint32_t const n0 = uint32_t(p1 >> 32) ^ ctr[1] ^ key[0];
+            uint32_t const n1 = uint32_t(p1);
+            uint32_t const n2 = uint32_t(p0 >> 32) ^ ctr[3] ^ key[1];
+            uint32_t const n3 = uint32_t(p0);
+            ctr[0] = n0;
+            ctr[1] = n1;
+            ctr[2] = n2;
+            ctr[3] = n3;
+            key[0] += 0x9E3779B9u;
+            key[1] += 0xBB67AE85u;
+        }
+    }
+    inline f32 u01(uint32_t r)
+    {
+        return (f32(r >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    }
+} // namespace
+
+extern "C"
+{
+    // ---------------------------------------------------------------------------------------------
+    // Unit-level entry points (used by the golden-vector tests)
+    // ---------------------------------------------------------------------------------------------
+    void orc_shape_array(int shape, int onSupport, float x, int isOutOfRange, float* out)
+    {
+        if(onSupport)
+            shapeArrayOnSupport(shape, x, out);
+        else
+            shapeArrayOffSupport(shape, x, isOutOfRange != 0, out);
+    }
+
+    float orc_shape_eval(int shape, int onSupport, float x)
+    {
+        return onSupport ? shapeEvalOnSupport(shape, x) : shapeEval(shape, x);
+    }
+
+    /** The reference's unit::shape test body (share/picongpu/unit/shape.cpp:128-141,176-207):
+     * positions from std::mt19937(42) + uniform_real_distribution<>(0,1), sum of shape(g - p). */
+    void orc_shape_unit_test(int shape, int onSupport, int numValues, float* positions, float* sums)
+    {
+        std::mt19937 mt(42.0);
+        std::uniform_real_distribution<> dist(0.0, 1.0);
+        int const supp = shapeSupport(shape);
+        bool const isEven = supp % 2 == 0;
+        int const begin = shapeBegin(shape);
+        int const end = onSupport ? begin + supp - 1 : begin + supp;
+        for(int n = 0; n < numValues; ++n)
+        {
+            f32 const pos = f32(dist(mt));
+            positions[n] = pos;
+            f32 res = 0.0f;
+            for(int g = begin; g <= end; ++g)
+            {
+                f32 p = pos;
+                if(onSupport)
+                {
+                    f32 const v_pos = pos - 0.5f;
+                    int s;
+                    if(isEven)
+                        s = v_pos >= -0.5f ? 0 : -1;
+                    else
+                        s = v_pos >= 0.0f ? 1 : 0;
+                    p = v_pos - f32(s) + 0.5f;
+                }
+                res += onSupport ? shapeEvalOnSupport(shape, f32(g) - p) : shapeEval(shape, f32(g) - p);
+            }
+            sums[n] = res;
+        }
+    }
+
+    /** moveParticle on one particle; localCellIdx linearised x-fastest in the supercell. */
+    int orc_move_particle(int const* sc, float const* newPos, int localCellIdx, float* posOut, int* localCellIdxOut)
+    {
+        int lc[3] = {localCellIdx % sc[0], (localCellIdx / sc[0]) % sc[1], localCellIdx / (sc[0] * sc[1])};
+        int dir[3];
+        int const mask = moveParticle(sc, newPos, posOut, lc, dir);
+        *localCellIdxOut = lc[0] + sc[0] * (lc[1] + sc[1] * lc[2]);
+        return mask;
+    }
+
+    /** SuperCell::getSizeLastFrame (M/particles/memory/dataTypes/SuperCell.hpp) */
+    unsigned orc_size_last_frame(unsigned numParticles, unsigned frameSize)
+    {
+        return numParticles ? ((numParticles - 1u) % frameSize + 1u) : 0u;
+    }
+
+    void orc_lehe_coeff(OrcParams const* P, int dir, float* out4)
+    {
+        LeheCoeff const c = leheCoeff(*P, dir);
+        out4[0] = c.alpha;
+        out4[1] = c.delta;
+        out4[2] = c.betaDir1;
+        out4[3] = c.betaDir2;
+    }
+
+    /** Boris/Vay momentum+position update for one particle in given fields (T/Pusher known-answer test). */
+    void orc_push_one(OrcParams const* P, float massRatio, float chargeRatio, float w, float const* E, float const* B, float* mom, float* pos)
+    {
+        f32 const mass = (P->base_mass * massRatio) * w;
+        f32 const charge = (P->base_charge * chargeRatio) * w;
+        if(P->pusher == 0)
+            pushBoris(*P, mass, charge, E, B, mom, pos);
+        else
+            pushVay(*P, mass, charge, E, B, mom, pos);
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Stage-level entry points
+    // ---------------------------------------------------------------------------------------------
+
+    /** Interpolate E and B to the particles only (for gather parity tests). Eout/Bout are [3][np]. */
+    void orc_gather(OrcParams const* Pp, float* E, float* B, int64_t np, float const* pos, int32_t const* cell, float* Eout, float* Bout)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        Field3 const FE(E, D.vol), FB(B, D.vol);
+#pragma omp parallel for schedule(static)
+        for(int64_t i = 0; i < np; ++i)
+        {
+            int c = cell[i];
+            int const cg[3] = {c % D.n[0] + D.g[0], (c / D.n[0]) % D.n[1] + D.g[1], c / (D.n[0] * D.n[1]) + D.g[2]};
+            f32 const p[3] = {pos[i], pos[np + i], pos[2 * np + i]};
+            for(int k = 0; k < 3; ++k)
+            {
+                Bout[k * np + i] = interpolateComponent(D, FB.c[k], P.shape, cg, p, fieldPosB[k]);
+                Eout[k * np + i] = interpolateComponent(D, FE.c[k], P.shape, cg, p, fieldPosE[k]);
+            }
+        }
+    }
+
+    /** KernelMoveAndMarkParticles + PushParticlePerFrame (P/particles/Particles.kernel:170-316) followed by
+     * the supercell re-assignment that KernelShiftParticles performs (M/particles/ParticlesBase.kernel:361-615),
+     * expressed on a flat particle list: pos/mom updated in place, cell[] becomes the new cell (periodic wrap
+     * where wrap[d]=1, else coordinate -1 / n[d] encoded in cellOut3), mask[] = multiMask from moveParticle.
+     * cellOut3 (optional, [3][np]) receives unwrapped new cell coordinates. */
+    void orc_push(
+        OrcParams const* Pp,
+        float massRatio,
+        float chargeRatio,
+        float* E,
+        float* B,
+        int64_t np,
+        float* pos,
+        float* mom,
+        float const* w,
+        int32_t* cell,
+        uint8_t* mask,
+        int32_t* cellOut3)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        Field3 const FE(E, D.vol), FB(B, D.vol);
+#pragma omp parallel for schedule(static)
+        for(int64_t i = 0; i < np; ++i)
+        {
+            int const c = cell[i];
+            int cc[3] = {c % D.n[0], (c / D.n[0]) % D.n[1], c / (D.n[0] * D.n[1])};
+            int const cg[3] = {cc[0] + D.g[0], cc[1] + D.g[1], cc[2] + D.g[2]};
+            f32 p[3] = {pos[i], pos[np + i], pos[2 * np + i]};
+            f32 m[3] = {mom[i], mom[np + i], mom[2 * np + i]};
+            f32 Ef[3], Bf[3];
+            for(int k = 0; k < 3; ++k)
+            {
+                Bf[k] = interpolateComponent(D, FB.c[k], P.shape, cg, p, fieldPosB[k]);
+                Ef[k] = interpolateComponent(D, FE.c[k], P.shape, cg, p, fieldPosE[k]);
+            }
+            f32 const mass = (P.base_mass * massRatio) * w[i];
+            f32 const charge = (P.base_charge * chargeRatio) * w[i];
+            if(P.pusher == 0)
+                pushBoris(P, mass, charge, Ef, Bf, m, p);
+            else
+                pushVay(P, mass, charge, Ef, Bf, m, p);
+            int lc[3] = {cc[0] % D.sc[0], cc[1] % D.sc[1], cc[2] % D.sc[2]};
+            int dir[3];
+            f32 pout[3];
+            int const mm = moveParticle(D.sc, p, pout, lc, dir);
+            for(int d = 0; d < 3; ++d)
+            {
+                cc[d] += dir[d];
+                if(cellOut3)
+                    cellOut3[d * np + i] = cc[d];
+                if(P.wrap[d])
+                    cc[d] = (cc[d] + D.n[d]) % D.n[d];
+                pos[d * np + i] = pout[d];
+                mom[d * np + i] = m[d];
+            }
+            bool const inside = cc[0] >= 0 && cc[0] < D.n[0] && cc[1] >= 0 && cc[1] < D.n[1] && cc[2] >= 0 && cc[2] < D.n[2];
+            cell[i] = inside ? cc[0] + D.n[0] * (cc[1] + D.n[1] * cc[2]) : -1;
+            if(mask)
+                mask[i] = uint8_t(mm);
+        }
+    }
+
+    /** KernelComputeCurrent + ComputePerFrame (P/fields/FieldJ.kernel:52-142): J += deposit(all particles).
+     * Particles are processed supercell by supercell (ascending linear supercell index, ascending particle
+     * index inside) in 8 checkerboard passes like the omp2b default StridedCachedSupercells
+     * (Strategy.def:78-85, Deposit.hpp:63-90); contributions are added directly into J (including guards). */
+    void orc_deposit(
+        OrcParams const* Pp,
+        float massRatio,
+        float chargeRatio,
+        float* J,
+        int64_t np,
+        float const* pos,
+        float const* mom,
+        float const* w,
+        int32_t const* cell)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        int const nscTot = D.nsc[0] * D.nsc[1] * D.nsc[2];
+        // CSR by supercell (stable)
+        std::vector<int64_t> off(size_t(nscTot) + 1, 0);
+        std::vector<int32_t> scOf(np);
+        for(int64_t i = 0; i < np; ++i)
+        {
+            int const c = cell[i];
+            int const cc[3] = {c % D.n[0], (c / D.n[0]) % D.n[1], c / (D.n[0] * D.n[1])};
+            int const s = cc[0] / D.sc[0] + D.nsc[0] * (cc[1] / D.sc[1] + D.nsc[1] * (cc[2] / D.sc[2]));
+            scOf[i] = s;
+            off[size_t(s) + 1]++;
+        }
+        for(int s = 0; s < nscTot; ++s)
+            off[size_t(s) + 1] += off[s];
+        std::vector<int64_t> order(np), cur(off.begin(), off.end() - 1);
+        for(int64_t i = 0; i < np; ++i)
+            order[cur[scOf[i]]++] = i;
+
+        JAcc acc;
+        acc.D = &D;
+        acc.J[0] = J;
+        acc.J[1] = J + D.vol;
+        acc.J[2] = J + 2 * D.vol;
+        for(int pass = 0; pass < 8; ++pass)
+        {
+            int const px = pass & 1, py = (pass >> 1) & 1, pz = (pass >> 2) & 1;
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+            for(int sz = pz; sz < D.nsc[2]; sz += 2)
+                for(int sy = py; sy < D.nsc[1]; sy += 2)
+                    for(int sx = px; sx < D.nsc[0]; sx += 2)
+                    {
+                        int const s = sx + D.nsc[0] * (sy + D.nsc[1] * sz);
+                        for(int64_t q = off[s]; q < off[size_t(s) + 1]; ++q)
+                        {
+                            int64_t const i = order[q];
+                            int const c = cell[i];
+                            int const cg[3]
+                                = {c % D.n[0] + D.g[0], (c / D.n[0]) % D.n[1] + D.g[1], c / (D.n[0] * D.n[1]) + D.g[2]};
+                            f32 const p[3] = {pos[i], pos[np + i], pos[2 * np + i]};
+                            f32 const m[3] = {mom[i], mom[np + i], mom[2 * np + i]};
+                            f32 const charge = (P.base_charge * chargeRatio) * w[i];
+                            f32 const mass = (P.base_mass * massRatio) * w[i];
+                            f32 vel[3];
+                            velocityF(P, m, mass, vel);
+                            if(P.current == 0)
+                                depositEsirkepov(P, acc, cg, p, vel, charge);
+                            else
+                                depositEmZ(P, acc, cg, p, vel, charge);
+                        }
+                    }
+        }
+    }
+
+    /** Deposit one particle given explicit velocity (T/CurrentDeposition known-answer test). */
+    void orc_deposit_one(OrcParams const* Pp, float* J, int const* cellCoord, float const* pos, float const* vel, float charge)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        JAcc acc;
+        acc.D = &D;
+        acc.J[0] = J;
+        acc.J[1] = J + D.vol;
+        acc.J[2] = J + 2 * D.vol;
+        int const cg[3] = {cellCoord[0] + D.g[0], cellCoord[1] + D.g[1], cellCoord[2] + D.g[2]};
+        if(P.current == 0)
+            depositEsirkepov(P, acc, cg, pos, vel, charge);
+        else
+            depositEmZ(P, acc, cg, pos, vel, charge);
+    }
+
+    /** Periodic guard fill for E/B: own GUARD := opposite BORDER (what GridBuffer::asyncCommunication does
+     * through the self-neighbour MPI topology, M/memory/buffers/GridBuffer.hpp:472-483). Full guard width. */
+    void orc_guard_copy(OrcParams const* Pp, float* F)
+    {
+        Dom const D(*Pp);
+        for(int c = 0; c < 3; ++c)
+        {
+            f32* f = F + c * D.vol;
+#pragma omp parallel for schedule(static)
+            for(int z = 0; z < D.N[2]; ++z)
+                for(int y = 0; y < D.N[1]; ++y)
+                    for(int x = 0; x < D.N[0]; ++x)
+                    {
+                        int const q[3] = {x, y, z};
+                        int s[3];
+                        bool guard = false;
+                        for(int d = 0; d < 3; ++d)
+                        {
+                            int l = q[d] - D.g[d];
+                            if(l < 0 || l >= D.n[d])
+                                guard = true;
+                            l = (l % D.n[d] + D.n[d]) % D.n[d];
+                            s[d] = l + D.g[d];
+                        }
+                        if(guard)
+                            f[D.idx(x, y, z)] = f[D.idx(s[0], s[1], s[2])];
+                    }
+        }
+    }
+
+    /** Periodic J guard reduction: BORDER += neighbour GUARD (M/fields/operations/AddExchangeToBorder.hpp:43-128
+     * driven by FieldJ::asyncCommunication P/fields/FieldJ.x.cpp:156-174). Guards are left untouched. */
+    void orc_guard_add(OrcParams const* Pp, float* F)
+    {
+        Dom const D(*Pp);
+        for(int c = 0; c < 3; ++c)
+        {
+            f32* f = F + c * D.vol;
+            // serial: several guard cells map onto the same border cell
+            for(int z = 0; z < D.N[2]; ++z)
+                for(int y = 0; y < D.N[1]; ++y)
+                    for(int x = 0; x < D.N[0]; ++x)
+                    {
+                        int const q[3] = {x, y, z};
+                        int s[3];
+                        bool guard = false;
+                        for(int d = 0; d < 3; ++d)
+                        {
+                            int l = q[d] - D.g[d];
+                            if(l < 0 || l >= D.n[d])
+                                guard = true;
+                            l = (l % D.n[d] + D.n[d]) % D.n[d];
+                            s[d] = l + D.g[d];
+                        }
+                        if(guard)
+                            f[D.idx(s[0], s[1], s[2])] += f[D.idx(x, y, z)];
+                    }
+        }
+    }
+
+    /** UpdateBHalfFunctor over CORE+BORDER: B -= curlE * 0.5 * dt (FDTDBase.kernel:115-121) */
+    void orc_update_b_half(OrcParams const* Pp, float const* E, float* B)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        Field3 const FE(const_cast<float*>(E), D.vol);
+        Field3 FB(B, D.vol);
+        LeheCoeff lc[3] = {leheCoeff(P, 0), leheCoeff(P, 1), leheCoeff(P, 2)};
+        int const mode = P.solver == 1 ? 2 : 0;
+#pragma omp parallel for schedule(static) collapse(2)
+        for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
+            for(int y = D.g[1]; y < D.g[1] + D.n[1]; ++y)
+                for(int x = D.g[0]; x < D.g[0] + D.n[0]; ++x)
+                {
+                    f32 cu[3];
+                    curlAt(P, D, FE, mode, lc, x, y, z, cu);
+                    int64_t const i = D.idx(x, y, z);
+                    for(int c = 0; c < 3; ++c)
+                        FB.c[c][i] -= cu[c] * 0.5f * P.dt;
+                }
+    }
+
+    /** UpdateEFunctor over CORE+BORDER: E += curlB * c^2 * dt (FDTDBase.kernel:74-81) */
+    void orc_update_e(OrcParams const* Pp, float* E, float const* B)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        Field3 FE(E, D.vol);
+        Field3 const FB(const_cast<float*>(B), D.vol);
+        LeheCoeff lc[3] = {leheCoeff(P, 0), leheCoeff(P, 1), leheCoeff(P, 2)};
+        f32 const c2 = P.c * P.c;
+#pragma omp parallel for schedule(static) collapse(2)
+        for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
+            for(int y = D.g[1]; y < D.g[1] + D.n[1]; ++y)
+                for(int x = D.g[0]; x < D.g[0] + D.n[0]; ++x)
+                {
+                    f32 cu[3];
+                    curlAt(P, D, FB, 1, lc, x, y, z, cu);
+                    int64_t const i = D.idx(x, y, z);
+                    for(int c = 0; c < 3; ++c)
+                        FE.c[c][i] += cu[c] * c2 * P.dt;
+                }
+    }
+
+    /** KernelAddCurrentDensity + currentInterpolation::None over CORE+BORDER: E += coeff * J,
+     * coeff = -(1/eps0) * dt (FDTD.hpp:84-85, None.hpp:60-64) */
+    void orc_add_current(OrcParams const* Pp, float* E, float const* J)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        f32 const coeff = -(1.0f / P.eps0) * P.dt;
+#pragma omp parallel for schedule(static) collapse(2)
+        for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
+            for(int y = D.g[1]; y < D.g[1] + D.n[1]; ++y)
+                for(int x = D.g[0]; x < D.g[0] + D.n[0]; ++x)
+                {
+                    int64_t const i = D.idx(x, y, z);
+                    for(int c = 0; c < 3; ++c)
+                        E[c * D.vol + i] += coeff * J[c * D.vol + i];
+                }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Metrics (parity observables named by the north star)
+    // ---------------------------------------------------------------------------------------------
+    /** EnergyFields (P/plugins/EnergyFields.x.cpp:198-233): out[0]=B energy, out[1]=E energy (PIC units) */
+    void orc_field_energy(OrcParams const* Pp, float const* E, float const* B, double* out2)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        double sB = 0, sE = 0;
+#pragma omp parallel for schedule(static) reduction(+ : sB, sE)
+        for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
+            for(int y = D.g[1]; y < D.g[1] + D.n[1]; ++y)
+                for(int x = D.g[0]; x < D.g[0] + D.n[0]; ++x)
+                {
+                    int64_t const i = D.idx(x, y, z);
+                    for(int c = 0; c < 3; ++c)
+                    {
+                        sB += double(B[c * D.vol + i]) * double(B[c * D.vol + i]);
+                        sE += double(E[c * D.vol + i]) * double(E[c * D.vol + i]);
+                    }
+                }
+        double const V = double(P.cell[0]) * double(P.cell[1]) * double(P.cell[2]);
+        out2[0] = sB * (0.5 / double(P.mue0) * V);
+        out2[1] = sE * (double(P.eps0) * V * 0.5);
+    }
+
+    /** EnergyParticles (P/plugins/EnergyParticles.x.cpp:100-131, P/algorithms/KinEnergy.hpp:38-68):
+     * out[0] = kinetic energy, out[1] = total energy */
+    void orc_particle_energy(OrcParams const* Pp, float massRatio, int64_t np, float const* mom, float const* w, double* out2)
+    {
+        OrcParams const& P = *Pp;
+        double ek = 0, et = 0;
+#pragma omp parallel for schedule(static) reduction(+ : ek, et)
+        for(int64_t i = 0; i < np; ++i)
+        {
+            f32 const m[3] = {mom[i], mom[np + i], mom[2 * np + i]};
+            f32 const mom2 = l2norm2(m);
+            f32 const mass = (P.base_mass * massRatio) * w[i];
+            f32 const c2 = P.c * P.c;
+            f32 const gamma = gammaF(P, m, mass);
+            f32 kin;
+            if(gamma < 1.005f)
+                kin = mom2 / (2.0f * mass);
+            else
+                kin = (gamma - 1.0f) * mass * c2;
+            ek += double(kin);
+            et += double(std::sqrt(mom2 + mass * mass * c2) * P.c);
+        }
+        out2[0] = ek;
+        out2[1] = et;
+    }
+
+    /** ChargeDensity on the cell origins (P/particles/particleToGrid/ComputeGridValuePerFrame.hpp:60-134,
+     * derivedAttributes/ChargeDensity.hpp): rho += charge/V * prod_d S(offset_d - pos_d); rho has guards. */
+    void orc_charge_density(OrcParams const* Pp, float chargeRatio, float* rho, int64_t np, float const* pos, float const* w, int32_t const* cell)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        int const supp = shapeSupport(P.shape);
+        int const lo = supp / 2, up = (supp + 1) / 2;
+        f32 const V = P.cell[0] * P.cell[1] * P.cell[2];
+        for(int64_t i = 0; i < np; ++i)
+        {
+            int const c = cell[i];
+            int const cg[3] = {c % D.n[0] + D.g[0], (c / D.n[0]) % D.n[1] + D.g[1], c / (D.n[0] * D.n[1]) + D.g[2]};
+            f32 const charge = (P.base_charge * chargeRatio) * w[i];
+            f32 const attr = charge / V;
+            for(int oz = -lo; oz <= up; ++oz)
+                for(int oy = -lo; oy <= up; ++oy)
+                    for(int ox = -lo; ox <= up; ++ox)
+                    {
+                        f32 assign = 1.0f;
+                        assign *= shapeEval(P.shape, f32(ox) - pos[i]);
+                        assign *= shapeEval(P.shape, f32(oy) - pos[np + i]);
+                        assign *= shapeEval(P.shape, f32(oz) - pos[2 * np + i]);
+                        rho[D.idx(cg[0] + ox, cg[1] + oy, cg[2] + oz)] += assign * attr;
+                    }
+        }
+    }
+
+    /** ChargeConservation (P/plugins/ChargeConservation.tpp:122-136,205-259): max |div E * eps0 - rho| * V.
+     * rho must already be guard-reduced. */
+    double orc_gauss_residual(OrcParams const* Pp, float const* E, float const* rho)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        f32 const rw = 1.0f / P.cell[0], rh = 1.0f / P.cell[1], rd = 1.0f / P.cell[2];
+        f32 mx = 0.0f;
+        for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
+            for(int y = D.g[1]; y < D.g[1] + D.n[1]; ++y)
+                for(int x = D.g[0]; x < D.g[0] + D.n[0]; ++x)
+                {
+                    int64_t const i = D.idx(x, y, z);
+                    f32 const div = (E[i] - E[D.idx(x - 1, y, z)]) * rw + (E[D.vol + i] - E[D.vol + D.idx(x, y - 1, z)]) * rh
+                        + (E[2 * D.vol + i] - E[2 * D.vol + D.idx(x, y, z - 1)]) * rd;
+                    f32 const dev = std::fabs(div * P.eps0 - rho[i]);
+                    mx = std::max(mx, dev);
+                }
+        return double(mx * (P.cell[0] * P.cell[1] * P.cell[2]));
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Whole step for a single periodic domain: Simulation::runOneStep (P/simulation/control/Simulation.hpp:522-542)
+    // ---------------------------------------------------------------------------------------------
+    struct OrcSpecies
+    {
+        float massRatio, chargeRatio;
+        int64_t np;
+        float *pos, *mom, *w;
+        int32_t* cell;
+    };
+
+    void orc_step(OrcParams const* Pp, float* E, float* B, float* J, int nSpecies, OrcSpecies* sp)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        std::memset(J, 0, sizeof(float) * 3 * size_t(D.vol)); // CurrentReset (stage/CurrentReset.hpp:45-52)
+        for(int s = 0; s < nSpecies; ++s) // ParticlePush (stage/ParticlePush.x.cpp:141-148)
+            orc_push(Pp, sp[s].massRatio, sp[s].chargeRatio, E, B, sp[s].np, sp[s].pos, sp[s].mom, sp[s].w, sp[s].cell, nullptr, nullptr);
+        // update_beforeCurrent (FDTDBase.hpp:97-121)
+        orc_update_b_half(Pp, E, B);
+        orc_guard_copy(Pp, B);
+        orc_update_e(Pp, E, B);
+        for(int s = 0; s < nSpecies; ++s) // CurrentDeposition (stage/CurrentDeposition.x.cpp:105-116)
+            orc_deposit(Pp, sp[s].massRatio, sp[s].chargeRatio, J, sp[s].np, sp[s].pos, sp[s].mom, sp[s].w, sp[s].cell);
+        orc_guard_add(Pp, J); // FieldJ::asyncCommunication (stage/CurrentInterpolationAndAdditionToEMF.hpp:99-148)
+        orc_add_current(Pp, E, J);
+        // update_afterCurrent (FDTDBase.hpp:151-183)
+        orc_guard_copy(Pp, E);
+        orc_update_b_half(Pp, E, B);
+        orc_guard_copy(Pp, B);
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // KelvinHelmholtz initial condition (share/picongpu/examples/KelvinHelmholtz/include/picongpu/param/*):
+    // Homogenous density, Quiet start 5x5x1 (QuietImpl.hpp:47-118, filled from the highest lattice index down),
+    // ions derived from electrons, drift gamma=1.021 along +-x by global y quarter (Drift.hpp:56-80,
+    // particleFilters.param), electron temperature 0.0005 keV (Temperature.hpp:63-87).
+    // RNG: Philox4x32-10, key=(seed, 0), counter=(global particle index lo, hi, 0, 0); 3 normals per
+    // particle via Box-Muller on (r0,r1) and (r2,r3). The reference's own RNG stream differs per backend
+    // (P/param/random.param), so ICs are generated here once and shared by oracle and GPU.
+    // ---------------------------------------------------------------------------------------------
+    /** @param globalN global grid cells, offset of this domain in the global grid `globalOff`
+     *  @param ppcDim particles per cell per dimension (5,5,1)
+     *  @param ev2joule_pic sim.pic.conv().eV2Joule(1.0) in PIC energy units
+     *  arrays sized n_cells*ppc; species 0 = electrons, 1 = ions */
+    void orc_khi_init(
+        OrcParams const* Pp,
+        int const* globalN,
+        int const* globalOff,
+        int const* ppcDim,
+        float realParticlesPerCell,
+        float massRatioIon,
+        double gammaDrift,
+        double temperature_keV,
+        double eV_pic,
+        uint32_t seed,
+        float* posE,
+        float* momE,
+        float* wE,
+        int32_t* cellE,
+        float* posI,
+        float* momI,
+        float* wI,
+        int32_t* cellI)
+    {
+        OrcParams const& P = *Pp;
+        int const ppc = ppcDim[0] * ppcDim[1] * ppcDim[2];
+        int64_t const ncell = int64_t(P.n[0]) * P.n[1] * P.n[2];
+        int64_t const np = ncell * ppc;
+        f32 const weighting = realParticlesPerCell / f32(ppc);
+        f32 spacing[3];
+        for(int d = 0; d < 3; ++d)
+            spacing[d] = 1.0f / f32(ppcDim[d]);
+        double const beta = std::sqrt(1.0 - 1.0 / (gammaDrift * gammaDrift));
+        f32 const massE = (P.base_mass * 1.0f) * weighting;
+        f32 const massI = (P.base_mass * massRatioIon) * weighting;
+        f32 const driftE = f32(gammaDrift * beta * double(massE) * double(P.c));
+        f32 const driftI = f32(gammaDrift * beta * double(massI) * double(P.c));
+        f32 const energy = f32(eV_pic * (temperature_keV * 1.0e3));
+        f32 const macroEnergy = weighting * energy;
+        f32 const stddev = std::sqrt(macroEnergy * massE);
+#pragma omp parallel for schedule(static)
+        for(int64_t c = 0; c < ncell; ++c)
+        {
+            int const cc[3] = {int(c % P.n[0]), int((c / P.n[0]) % P.n[1]), int(c / (int64_t(P.n[0]) * P.n[1]))};
+            // RelativeGlobalDomainPosition filter on y (dimension 1)
+            f32 const rel = f32(cc[1] + globalOff[1]) / f32(globalN[1]);
+            f32 const sign = (rel >= 0.25f && rel < 0.75f) ? -1.0f : 1.0f;
+            int64_t const gcell = int64_t(cc[0] + globalOff[0])
+                + int64_t(globalN[0]) * (int64_t(cc[1] + globalOff[1]) + int64_t(globalN[1]) * int64_t(cc[2] + globalOff[2]));
+            for(int k = 0; k < ppc; ++k)
+            {
+                int64_t const i = c * ppc + k;
+                int const cur = ppc - 1 - k; // m_currentMacroParticles counts down
+                int const ic[3] = {cur % ppcDim[0], (cur / ppcDim[0]) % ppcDim[1], cur / (ppcDim[0] * ppcDim[1])};
+                for(int d = 0; d < 3; ++d)
+                {
+                    f32 const p = f32(ic[d]) * spacing[d] + spacing[d] * 0.5f;
+                    posE[d * np + i] = p;
+                    posI[d * np + i] = p;
+                }
+                wE[i] = weighting;
+                wI[i] = weighting;
+                cellE[i] = int32_t(c);
+                cellI[i] = int32_t(c);
+                uint64_t const gid = uint64_t(gcell) * uint64_t(ppc) + uint64_t(k);
+                uint32_t ctr[4] = {uint32_t(gid), uint32_t(gid >> 32), 0u, 0u};
+                uint32_t const key[2] = {seed, 0u};
+                philox4x32_10(ctr, key);
+                f32 const r0 = std::sqrt(-2.0f * std::log(u01(ctr[0])));
+                f32 const r1 = std::sqrt(-2.0f * std::log(u01(ctr[2])));
+                f32 const a0 = 6.283185307179586f * u01(ctr[1]);
+                f32 const a1 = 6.283185307179586f * u01(ctr[3]);
+                f32 const nrm[3] = {r0 * std::cos(a0), r0 * std::sin(a0), r1 * std::cos(a1)};
+                momE[0 * np + i] = sign * driftE + nrm[0] * stddev;
+                momE[1 * np + i] = 0.0f + nrm[1] * stddev;
+                momE[2 * np + i] = 0.0f + nrm[2] * stddev;
+                momI[0 * np + i] = sign * driftI;
+                momI[1 * np + i] = 0.0f;
+                momI[2 * np + i] = 0.0f;
+            }
+        }
+    }
+
+    int orc_num_threads()
+    {
+#ifdef _OPENMP
+        return omp_get_max_threads();
+#else
+        return 1;
+#endif
+    }
+
+    void orc_set_num_threads(int n)
+    {
+#ifdef _OPENMP
+        omp_set_num_threads(n);
+#else
+        (void) n;
+#endif
+    }
+}

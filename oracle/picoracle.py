@@ -1,0 +1,218 @@
+"""ctypes binding of the CPU oracle (oracle/libpicoracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package picongpu_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+class OrcParams(C.Structure):
+    _fields_ = [
+        ("n", C.c_int * 3),
+        ("sc", C.c_int * 3),
+        ("g", C.c_int * 3),
+        ("cell", C.c_float * 3),
+        ("dt", C.c_float),
+        ("c", C.c_float),
+        ("eps0", C.c_float),
+        ("mue0", C.c_float),
+        ("base_mass", C.c_float),
+        ("base_charge", C.c_float),
+        ("shape", C.c_int),
+        ("pusher", C.c_int),
+        ("current", C.c_int),
+        ("solver", C.c_int),
+        ("lehe_dir", C.c_int),
+        ("wrap", C.c_int * 3),
+    ]
+
+
+class OrcSpecies(C.Structure):
+    _fields_ = [
+        ("massRatio", C.c_float),
+        ("chargeRatio", C.c_float),
+        ("np", C.c_int64),
+        ("pos", C.c_void_p),
+        ("mom", C.c_void_p),
+        ("w", C.c_void_p),
+        ("cell", C.c_void_p),
+    ]
+
+
+def build(force=False):
+    """Compile oracle/picoracle.cpp -> oracle/libpicoracle.so (g++, OpenMP if available)."""
+    so = os.path.join(_HERE, "libpicoracle.so")
+    src = os.path.join(_HERE, "picoracle.cpp")
+    if not force and os.path.exists(so) and os.path.getmtime(so) >= os.path.getmtime(src):
+        return so
+    base = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared", "-o", so, src]
+    for cxx, omp in (("/usr/bin/g++", ["-fopenmp"]), ("g++", ["-fopenmp"]), ("/usr/bin/g++", []), ("g++", [])):
+        try:
+            r = subprocess.run([cxx] + omp + base, capture_output=True, text=True)
+        except FileNotFoundError:
+            continue
+        if r.returncode == 0:
+            return so
+    raise RuntimeError("could not build oracle: " + r.stderr)
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    P = C.POINTER(OrcParams)
+    L.orc_shape_array.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, f32p]
+    L.orc_shape_eval.argtypes = [C.c_int, C.c_int, C.c_float]
+    L.orc_shape_eval.restype = C.c_float
+    L.orc_shape_unit_test.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p]
+    L.orc_move_particle.argtypes = [i32p, f32p, C.c_int, f32p, C.POINTER(C.c_int)]
+    L.orc_move_particle.restype = C.c_int
+    L.orc_size_last_frame.argtypes = [C.c_uint, C.c_uint]
+    L.orc_size_last_frame.restype = C.c_uint
+    L.orc_lehe_coeff.argtypes = [P, C.c_int, f32p]
+    L.orc_push_one.argtypes = [P, C.c_float, C.c_float, C.c_float, f32p, f32p, f32p, f32p]
+    L.orc_gather.argtypes = [P, f32p, f32p, C.c_int64, f32p, i32p, f32p, f32p]
+    L.orc_push.argtypes = [P, C.c_float, C.c_float, f32p, f32p, C.c_int64, f32p, f32p, f32p, i32p, C.c_void_p, C.c_void_p]
+    L.orc_deposit.argtypes = [P, C.c_float, C.c_float, f32p, C.c_int64, f32p, f32p, f32p, i32p]
+    L.orc_deposit_one.argtypes = [P, f32p, i32p, f32p, f32p, C.c_float]
+    L.orc_guard_copy.argtypes = [P, f32p]
+    L.orc_guard_add.argtypes = [P, f32p]
+    L.orc_update_b_half.argtypes = [P, f32p, f32p]
+    L.orc_update_e.argtypes = [P, f32p, f32p]
+    L.orc_add_current.argtypes = [P, f32p, f32p]
+    L.orc_field_energy.argtypes = [P, f32p, f32p, f64p]
+    L.orc_particle_energy.argtypes = [P, C.c_float, C.c_int64, f32p, f32p, f64p]
+    L.orc_charge_density.argtypes = [P, C.c_float, f32p, C.c_int64, f32p, f32p, i32p]
+    L.orc_gauss_residual.argtypes = [P, f32p, f32p]
+    L.orc_gauss_residual.restype = C.c_double
+    L.orc_step.argtypes = [P, f32p, f32p, f32p, C.c_int, C.POINTER(OrcSpecies)]
+    L.orc_khi_init.argtypes = [P, i32p, i32p, i32p, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double, C.c_uint32,
+                               f32p, f32p, f32p, i32p, f32p, f32p, f32p, i32p]
+    L.orc_num_threads.restype = C.c_int
+    L.orc_set_num_threads.argtypes = [C.c_int]
+    _LIB = L
+    return L
+
+
+def make_params(cfg):
+    """cfg: a picongpu_b200.param.SimParams-like object or dict with the same field names."""
+    g = (lambda k: cfg[k]) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k))
+    p = OrcParams()
+    for d in range(3):
+        p.n[d] = int(g("grid")[d])
+        p.sc[d] = int(g("supercell")[d])
+        p.g[d] = int(g("supercell")[d]) * int(g("guard_supercells")[d])
+        p.cell[d] = float(g("cell_size")[d])
+        p.wrap[d] = int(g("wrap")[d]) if _has(cfg, "wrap") else 1
+    p.dt = float(g("dt"))
+    p.c = float(g("c"))
+    p.eps0 = float(g("eps0"))
+    p.mue0 = float(g("mue0"))
+    p.base_mass = float(g("base_mass"))
+    p.base_charge = float(g("base_charge"))
+    p.shape = int(g("shape"))
+    p.pusher = int(g("pusher"))
+    p.current = int(g("current_solver"))
+    p.solver = int(g("field_solver"))
+    p.lehe_dir = int(g("lehe_dir"))
+    return p
+
+
+def _has(cfg, k):
+    return (k in cfg) if isinstance(cfg, dict) else hasattr(cfg, k)
+
+
+class Oracle:
+    """Thin object wrapper: holds OrcParams and exposes the stage calls on numpy arrays."""
+
+    def __init__(self, cfg):
+        self.p = make_params(cfg)
+        self.L = lib()
+        self.n = tuple(self.p.n)
+        self.g = tuple(self.p.g)
+        self.N = tuple(self.p.n[d] + 2 * self.p.g[d] for d in range(3))
+
+    def field(self):
+        return np.zeros((3, self.N[2], self.N[1], self.N[0]), np.float32)
+
+    def interior(self, F):
+        g, n = self.g, self.n
+        return F[..., g[2]:g[2] + n[2], g[1]:g[1] + n[1], g[0]:g[0] + n[0]]
+
+    def gather(self, E, B, pos, cell):
+        npart = pos.shape[1]
+        Eo = np.empty((3, npart), np.float32)
+        Bo = np.empty((3, npart), np.float32)
+        self.L.orc_gather(C.byref(self.p), E, B, npart, pos, cell, Eo, Bo)
+        return Eo, Bo
+
+    def push(self, mr, cr, E, B, pos, mom, w, cell, want_mask=False, want_cell3=False):
+        npart = pos.shape[1]
+        mask = np.zeros(npart, np.uint8) if want_mask else None
+        cell3 = np.zeros((3, npart), np.int32) if want_cell3 else None
+        self.L.orc_push(C.byref(self.p), mr, cr, E, B, npart, pos, mom, w, cell,
+                        mask.ctypes.data if want_mask else None, cell3.ctypes.data if want_cell3 else None)
+        return mask, cell3
+
+    def deposit(self, mr, cr, J, pos, mom, w, cell):
+        self.L.orc_deposit(C.byref(self.p), mr, cr, J, pos.shape[1], pos, mom, w, cell)
+
+    def guard_copy(self, F):
+        self.L.orc_guard_copy(C.byref(self.p), F)
+
+    def guard_add(self, F):
+        self.L.orc_guard_add(C.byref(self.p), F)
+
+    def update_b_half(self, E, B):
+        self.L.orc_update_b_half(C.byref(self.p), E, B)
+
+    def update_e(self, E, B):
+        self.L.orc_update_e(C.byref(self.p), E, B)
+
+    def add_current(self, E, J):
+        self.L.orc_add_current(C.byref(self.p), E, J)
+
+    def step(self, E, B, J, species):
+        """species: list of dicts(massRatio, chargeRatio, pos, mom, w, cell) updated in place."""
+        arr = (OrcSpecies * len(species))()
+        for i, s in enumerate(species):
+            arr[i].massRatio = s["massRatio"]
+            arr[i].chargeRatio = s["chargeRatio"]
+            arr[i].np = s["pos"].shape[1]
+            for k in ("pos", "mom", "w", "cell"):
+                assert s[k].flags["C_CONTIGUOUS"]
+                setattr(arr[i], k, s[k].ctypes.data)
+        self.L.orc_step(C.byref(self.p), E, B, J, len(species), arr)
+
+    def field_energy(self, E, B):
+        out = np.zeros(2, np.float64)
+        self.L.orc_field_energy(C.byref(self.p), E, B, out)
+        return out
+
+    def particle_energy(self, mr, mom, w):
+        out = np.zeros(2, np.float64)
+        self.L.orc_particle_energy(C.byref(self.p), mr, mom.shape[1], mom, w, out)
+        return out
+
+    def charge_density(self, cr, rho, pos, w, cell):
+        self.L.orc_charge_density(C.byref(self.p), cr, rho, pos.shape[1], pos, w, cell)
+
+    def gauss_residual(self, E, species):
+        rho3 = np.zeros((3,) + tuple(reversed(self.N)), np.float32)  # only component 0 used
+        for s in species:
+            self.charge_density(s["chargeRatio"], rho3[0], s["pos"], s["w"], s["cell"])
+        self.guard_add(rho3)
+        return self.L.orc_gauss_residual(C.byref(self.p), E, rho3[0])

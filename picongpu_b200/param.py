@@ -1,0 +1,143 @@
+"""Host-side mirror of the reference's compile-time `.param` / `.unitless` configuration for the PIC step.
+
+The reference selects pusher / shape / current solver / field solver through type aliases in
+`include/picongpu/param/{species,fieldSolver,memory,simulation}.param` and derives the PIC unit system in
+`include/picongpu/unitless/simulation.unitless:420-480`.  Here the same names are runtime values that are
+handed to the C ABI (`include/picstep.h`, `picstep_params`).
+"""
+from dataclasses import dataclass, field
+import math
+
+import numpy as np
+
+# enums shared with include/picstep.h
+SHAPE_NGP, SHAPE_CIC, SHAPE_TSC, SHAPE_PQS, SHAPE_PCS = range(5)
+PUSHER_BORIS, PUSHER_VAY = range(2)
+CURRENT_ESIRKEPOV, CURRENT_EMZ = range(2)
+SOLVER_YEE, SOLVER_LEHE = range(2)
+
+SHAPE_NAMES = {"NGP": 0, "CIC": 1, "TSC": 2, "PQS": 3, "PCS": 4}
+PUSHER_NAMES = {"Boris": 0, "Vay": 1}
+CURRENT_NAMES = {"Esirkepov": 0, "EmZ": 1, "EZ": 1}
+SOLVER_NAMES = {"Yee": 0, "Lehe": 1}
+
+# include/picongpu/param/physicalConstants.param:25-50
+SPEED_OF_LIGHT_SI = 2.99792458e8
+MUE0_SI = 1.25663706127e-6
+ELECTRON_MASS_SI = 9.1093837139e-31
+ELECTRON_CHARGE_SI = -1.602176634e-19
+EV_SI = 1.602176634e-19
+
+
+def _f32(x):
+    return float(np.float32(x))
+
+
+@dataclass
+class Species:
+    """A species definition: `Particles<Name, Flags, Attributes>` with massRatio<> / chargeRatio<> flags
+    (include/picongpu/param/speciesAttributes.param:195-256)."""
+
+    name: str
+    mass_ratio: float
+    charge_ratio: float
+
+
+@dataclass
+class SimParams:
+    # --- memory.param / grid ---
+    grid: tuple  # local cells per device (no guard), multiple of supercell
+    supercell: tuple = (8, 8, 4)  # SuperCellSize, memory.param:51
+    guard_supercells: tuple = (1, 1, 1)  # GuardSize, memory.param:73
+    # --- simulation.param (SI) ---
+    delta_t_si: float = 1.79e-16
+    cell_si: tuple = (9.34635e-8, 9.34635e-8, 9.34635e-8)
+    base_density_si: float = 1.0e25
+    typical_ppc: int = 25
+    # --- species.param / fieldSolver.param ---
+    shape: int = SHAPE_TSC
+    pusher: int = PUSHER_BORIS
+    current_solver: int = CURRENT_ESIRKEPOV
+    field_solver: int = SOLVER_YEE
+    lehe_dir: int = 1
+    # --- runtime (-d, --periodic) ---
+    periodic: tuple = (1, 1, 1)
+    devices: tuple = (1, 1, 1)
+    rank_pos: tuple = (0, 0, 0)
+    species: list = field(default_factory=list)
+
+    def __post_init__(self):
+        for d in range(3):
+            if self.grid[d] % self.supercell[d]:
+                raise ValueError("grid must be a multiple of the supercell size (DomainAdjuster)")
+            if self.grid[d] // self.supercell[d] < 3 and self.devices[d] > 1:
+                raise ValueError("at least 3 supercells per split axis")
+        # unit system: simulation.unitless:420-480 (all in float_64, cast to float_X on use)
+        self.unit_time = self.delta_t_si
+        self.unit_speed = SPEED_OF_LIGHT_SI
+        self.unit_length = self.unit_time * self.unit_speed
+        cell_vol_si = self.cell_si[0] * self.cell_si[1] * self.cell_si[2]
+        self.typical_num_particles_per_macro = self.base_density_si * cell_vol_si / float(self.typical_ppc)
+        self.unit_mass = ELECTRON_MASS_SI * self.typical_num_particles_per_macro
+        self.unit_charge = -1.0 * ELECTRON_CHARGE_SI * self.typical_num_particles_per_macro
+        self.unit_energy = self.unit_mass * self.unit_length**2 / self.unit_time**2
+        self.unit_efield = 1.0 / (self.unit_time**2 / self.unit_mass / self.unit_length * self.unit_charge)
+        self.unit_bfield = self.unit_mass / (self.unit_time * self.unit_charge)
+        # PIC-unit float_X values (simulation.unitless:34-110)
+        self.cell_size = tuple(_f32(c / self.unit_length) for c in self.cell_si)
+        self.dt = _f32(self.delta_t_si / self.unit_time)
+        self.c = _f32(SPEED_OF_LIGHT_SI / self.unit_speed)
+        self.base_mass = _f32(ELECTRON_MASS_SI / self.unit_mass)
+        self.base_charge = _f32(ELECTRON_CHARGE_SI / self.unit_charge)
+        self.mue0 = _f32(MUE0_SI / self.unit_length / self.unit_mass * self.unit_charge * self.unit_charge)
+        self.eps0 = _f32(1.0 / self.mue0 / self.c / self.c)
+        self.ev_pic = EV_SI / self.unit_energy
+        # densities
+        self.real_particles_per_cell = _f32(
+            _f32(self.base_density_si * self.unit_length**3)
+            * _f32(np.float32(self.cell_size[0]) * np.float32(self.cell_size[1]) * np.float32(self.cell_size[2]))
+        )
+        self.wrap = tuple(1 if (self.periodic[d] and self.devices[d] == 1) else 0 for d in range(3))
+
+    @property
+    def guard_cells(self):
+        return tuple(self.supercell[d] * self.guard_supercells[d] for d in range(3))
+
+    @property
+    def padded(self):
+        g = self.guard_cells
+        return tuple(self.grid[d] + 2 * g[d] for d in range(3))
+
+    @property
+    def num_supercells(self):
+        return tuple(self.grid[d] // self.supercell[d] for d in range(3))
+
+    @property
+    def global_grid(self):
+        return tuple(self.grid[d] * self.devices[d] for d in range(3))
+
+    @property
+    def global_offset(self):
+        return tuple(self.grid[d] * self.rank_pos[d] for d in range(3))
+
+    def cfl_ok(self):
+        """Yee CFL: c*dt <= 1/sqrt(sum 1/dx^2) (include/picongpu/fields/MaxwellSolver/CFLChecker.hpp)."""
+        s = sum(1.0 / (c * c) for c in self.cell_size)
+        return self.c * self.dt <= 1.0 / math.sqrt(s)
+
+
+def khi_params(grid=(64, 64, 64), **kw):
+    """share/picongpu/examples/KelvinHelmholtz/include/picongpu/param/*: Boris, Yee, Esirkepov, TSC, 25 ppc."""
+    p = SimParams(grid=tuple(grid), **kw)
+    p.species = [Species("e", 1.0, 1.0), Species("i", 1836.152672, -1.0)]
+    return p
+
+
+def thermal_params(grid=(64, 64, 64), **kw):
+    """share/picongpu/benchmarks/Thermal/include/picongpu/param/*: electrons only, uniform warm plasma."""
+    kw.setdefault("delta_t_si", 9.65531e-14)
+    kw.setdefault("cell_si", (5.78918e-5,) * 3)
+    kw.setdefault("base_density_si", 1.0e20)
+    p = SimParams(grid=tuple(grid), **kw)
+    p.species = [Species("e", 1.0, 1.0)]
+    return p
