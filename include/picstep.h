@@ -1,0 +1,202 @@
+/* picstep.h — C ABI of libpicstep.so: the B200-native (sm_100a) implementation of PIConGPU's core PIC step.
+ *
+ * The reference has no runtime plugin ABI for this path: pusher / shape / current solver / field solver are
+ * compile-time policy types selected in `.param` files and driven by `Simulation::runOneStep`
+ * (include/picongpu/simulation/control/Simulation.hpp:522-542).  This header turns that surface into plain C:
+ * every entry point names the reference interface it replaces.  All functions return a status code (0 = OK),
+ * never throw, take an opaque context bound to ONE CUDA device (+ one NCCL rank), are stream ordered and are not
+ * thread safe per context (same convention as the reference: one host thread per rank).
+ * The caller owns every host array it passes; the library owns all device memory.
+ *
+ * There is NO CPU fallback: picstep_create() fails with PICSTEP_ERR_NOGPU when no CUDA device is present.
+ */
+#ifndef PICSTEP_H
+#define PICSTEP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+    typedef struct picstep_ctx picstep_ctx;
+
+    enum picstep_status
+    {
+        PICSTEP_OK = 0,
+        PICSTEP_ERR_INVALID = 1, /* bad argument / unsupported configuration */
+        PICSTEP_ERR_CUDA = 2, /* CUDA runtime error, see picstep_last_error() */
+        PICSTEP_ERR_CAPACITY = 3, /* particle / exchange buffer too small */
+        PICSTEP_ERR_COMM = 4, /* NCCL error or communicator missing */
+        PICSTEP_ERR_NOGPU = 5 /* no CUDA device: the product path has no CPU fallback */
+    };
+
+    /* particles::shapes::{NGP,CIC,TSC,PQS,PCS} (include/picongpu/particles/shapes/) */
+    enum picstep_shape
+    {
+        PICSTEP_SHAPE_NGP = 0,
+        PICSTEP_SHAPE_CIC = 1,
+        PICSTEP_SHAPE_TSC = 2,
+        PICSTEP_SHAPE_PQS = 3,
+        PICSTEP_SHAPE_PCS = 4
+    };
+    /* particles::pusher::{Boris,Vay} (include/picongpu/unitless/pusher.unitless:43-86) */
+    enum picstep_pusher
+    {
+        PICSTEP_PUSHER_BORIS = 0,
+        PICSTEP_PUSHER_VAY = 1
+    };
+    /* currentSolver::{Esirkepov,EmZ} (include/picongpu/fields/currentDeposition/) */
+    enum picstep_current_solver
+    {
+        PICSTEP_CURRENT_ESIRKEPOV = 0,
+        PICSTEP_CURRENT_EMZ = 1
+    };
+    /* fields::maxwellSolver::{Yee,Lehe<dir>} (include/picongpu/fields/MaxwellSolver/) */
+    enum picstep_field_solver
+    {
+        PICSTEP_SOLVER_YEE = 0,
+        PICSTEP_SOLVER_LEHE = 1
+    };
+    /* FieldE / FieldB / FieldJ, as named through DataConnector ("E","B","J") */
+    enum picstep_field
+    {
+        PICSTEP_FIELD_E = 0,
+        PICSTEP_FIELD_B = 1,
+        PICSTEP_FIELD_J = 2
+    };
+    /* picstep_reduce() selectors */
+    enum picstep_reduction
+    {
+        PICSTEP_REDUCE_FIELD_ENERGY = 0, /* out[0]=B energy, out[1]=E energy   (plugins/EnergyFields.x.cpp:198-233) */
+        PICSTEP_REDUCE_PARTICLE_ENERGY = 1, /* out[0]=kinetic, out[1]=total, needs `species` (EnergyParticles.x.cpp:100-131) */
+        PICSTEP_REDUCE_GAUSS = 2, /* out[0]=max|eps0 div E - rho|*V     (plugins/ChargeConservation.tpp:181-259) */
+        PICSTEP_REDUCE_PARTICLE_COUNT = 3 /* out[0]=number of macro particles of `species` */
+    };
+
+    /* The `.param` surface of the hot path as runtime values (all physical values in PIC units, i.e. what
+     * `sim.pic.get*()` returns, include/picongpu/unitless/simulation.unitless:34-110). */
+    typedef struct picstep_params
+    {
+        int32_t grid[3]; /* local cells without guard (-g / gridDist), multiple of supercell */
+        int32_t supercell[3]; /* SuperCellSize  (param/memory.param:51); only 8x8x4 is compiled in */
+        int32_t guard_supercells[3]; /* GuardSize      (param/memory.param:73); only 1x1x1 */
+        float cell_size[3]; /* sim.pic.getCellSize() */
+        float dt; /* sim.pic.getDt() */
+        float c; /* sim.pic.getSpeedOfLight() */
+        float eps0; /* sim.pic.getEps0() */
+        float mue0; /* sim.pic.getMue0() */
+        float base_mass; /* sim.pic.getBaseMass() */
+        float base_charge; /* sim.pic.getBaseCharge() */
+        int32_t shape; /* picstep_shape            (species.param: UsedParticleShape) */
+        int32_t pusher; /* picstep_pusher           (species.param: UsedParticlePusher) */
+        int32_t current_solver; /* picstep_current_solver   (species.param: UsedParticleCurrentSolver) */
+        int32_t field_solver; /* picstep_field_solver     (fieldSolver.param:57) */
+        int32_t lehe_dir; /* Cherenkov free direction of Lehe */
+        int32_t periodic[3]; /* --periodic */
+        int32_t devices[3]; /* -d : ranks per axis (one axis may be > 1) */
+        int32_t rank_pos[3]; /* this rank's coordinate in the device grid */
+        int32_t device; /* CUDA device ordinal */
+        int32_t flags; /* bit0: deposit with the simple per-particle atomic kernel (debug / cross-check) */
+    } picstep_params;
+
+    /* library / build information: returns e.g. "picstep sm_100a fmad=on" */
+    const char* picstep_version(void);
+    /* last error text of a context (ctx may be NULL: error of the last failed picstep_create) */
+    const char* picstep_last_error(const picstep_ctx* ctx);
+
+    /* Simulation::init (Simulation.hpp:287-434): allocate E,B,J with guards and the kernel work buffers */
+    int picstep_create(const picstep_params* params, picstep_ctx** out);
+    int picstep_destroy(picstep_ctx* ctx);
+
+    /* `Particles<Name, Flags, Attributes>` with massRatio<> / chargeRatio<> (speciesDefinition.param).
+     * `capacity` = number of particle slots to reserve per buffer (0: sized at the first upload * 1.25). */
+    int picstep_species_add(picstep_ctx* ctx, const char* name, float mass_ratio, float charge_ratio, int64_t capacity, int32_t* species_id);
+
+    /* Field transfer in the reference's own layout: AoS float3, x fastest, guards included
+     * (dims = grid + 2*supercell*guard_supercells; include/pmacc/memory/buffers/DeviceBuffer.hpp:111-119). */
+    int picstep_fields_upload(picstep_ctx* ctx, int32_t field, const float* aos_with_guards);
+    int picstep_fields_download(picstep_ctx* ctx, int32_t field, float* aos_with_guards);
+    /* Same, component-major SoA [3][Nz][Ny][Nx] (the library's internal layout, no transposition). */
+    int picstep_fields_upload_soa(picstep_ctx* ctx, int32_t field, const float* soa_with_guards);
+    int picstep_fields_download_soa(picstep_ctx* ctx, int32_t field, float* soa_with_guards);
+
+    /* Particle transfer as flat SoA arrays: pos[3][n] (in-cell, [0,1)), mom[3][n], weighting[n] and the local cell
+     * index cell[n] = cx + grid.x*(cy + grid.y*cz).  Upload replaces the species' content and builds the
+     * supercell-resident frame runs.  Download returns particles in frame-run order (supercell-major, cell-minor). */
+    int picstep_particles_upload(picstep_ctx* ctx, int32_t species, int64_t n, const float* pos, const float* mom, const float* weighting, const int32_t* cell);
+    int picstep_particles_count(picstep_ctx* ctx, int32_t species, int64_t* n);
+    int picstep_particles_download(picstep_ctx* ctx, int32_t species, int64_t capacity, float* pos, float* mom, float* weighting, int32_t* cell, int64_t* n);
+    /* SuperCell bookkeeping (include/pmacc/particles/memory/dataTypes/SuperCell.hpp:32-118): per supercell
+     * (x fastest, no guard) the number of particles; frames = ceil(n/256), last frame size = ((n-1)%256)+1. */
+    int picstep_supercell_counts(picstep_ctx* ctx, int32_t species, int64_t* counts);
+
+    /* Synthetic KelvinHelmholtz initial condition generated on the device (bench input; same recipe and Philox
+     * stream as the oracle's orc_khi_init): species 0 = electrons, 1 = ions; ppc = ppc_dim[0]*[1]*[2] each. */
+    int picstep_init_khi(picstep_ctx* ctx, const int32_t* ppc_dim, float real_particles_per_cell, double gamma_drift, double temperature_keV, double ev_pic, uint32_t seed);
+
+    /* ---- stage calls, in the order of Simulation::runOneStep (Simulation.hpp:526-541) ---- */
+    /* CurrentReset              (simulation/stage/CurrentReset.hpp:45-52) */
+    int picstep_current_reset(picstep_ctx* ctx);
+    /* ParticlePush: species->update(step): gather + push + move, marks leavers
+     *                           (particles/Particles.tpp:322-368, Particles.kernel:170-316) */
+    int picstep_push(picstep_ctx* ctx, int32_t species, uint32_t step);
+    /* shiftBetweenSupercells + asyncCommunication(species): re-sort across supercells and migrate between ranks
+     *                           (pmacc/particles/ParticlesBase.hpp:217-237, AsyncCommunicationImpl.hpp:46-60) */
+    int picstep_migrate(picstep_ctx* ctx, int32_t species);
+    /* fields::Solver::update_beforeCurrent (fields/MaxwellSolver/FDTD/FDTDBase.hpp:97-121) */
+    int picstep_field_update_before_current(picstep_ctx* ctx, uint32_t step);
+    /* CurrentDeposition         (simulation/stage/CurrentDeposition.x.cpp:105-116, fields/FieldJ.kernel:52-142) */
+    int picstep_deposit(picstep_ctx* ctx, int32_t species);
+    /* CurrentInterpolationAndAdditionToEMF: J guard reduction + E += -dt/eps0 * J
+     *                           (simulation/stage/CurrentInterpolationAndAdditionToEMF.hpp:99-148) */
+    int picstep_add_current(picstep_ctx* ctx);
+    /* fields::Solver::update_afterCurrent (FDTDBase.hpp:151-183) */
+    int picstep_field_update_after_current(picstep_ctx* ctx, uint32_t step);
+    /* guard exchange of one field: E/B guards := neighbour border (GridBuffer::asyncCommunication,
+     * pmacc/memory/buffers/GridBuffer.hpp:472-483); for J: border += neighbour guard (FieldJ.x.cpp:156-174) */
+    int picstep_field_exchange(picstep_ctx* ctx, int32_t field);
+
+    /* runOneStep x n : all stages, all species, device resident */
+    int picstep_step(picstep_ctx* ctx, uint32_t first_step, uint32_t n);
+    /* One step through HOST buffers (used for the end-to-end measurement): uploads E,B (SoA) and every species
+     * from the given host arrays, runs one step, downloads E,B and the field/particle energies.
+     * species arrays: pos/mom/weighting/cell pointers per species, n[s] particles each. */
+    int picstep_step_host(picstep_ctx* ctx, uint32_t step, float* E_soa, float* B_soa, int32_t n_species, const int64_t* n, const float* const* pos, const float* const* mom, const float* const* weighting, const int32_t* const* cell, double* energies4);
+    /* wait for all queued device work of this context */
+    int picstep_sync(picstep_ctx* ctx);
+
+    /* plugins' reductions used as parity observables; see picstep_reduction */
+    int picstep_reduce(picstep_ctx* ctx, int32_t what, int32_t species, double* out);
+
+    /* parity hook (no reference counterpart as a call, the arithmetic is FieldToParticleInterpolation.hpp:97-124):
+     * E.x,E.y,E.z,B.x,B.y,B.z interpolated to every particle, out[6][capacity], frame-run order */
+    int picstep_debug_gather(picstep_ctx* ctx, int32_t species, int64_t capacity, float* out);
+
+    /* ---- multi GPU (replaces pmacc::CommunicatorMPI, include/pmacc/communication/CommunicatorMPI.cpp:70-149) ---- */
+    /* 128-byte NCCL unique id, created on rank 0 and broadcast by the caller (torch.distributed / MPI / file) */
+    int picstep_comm_unique_id(void* id128);
+    int picstep_comm_init(picstep_ctx* ctx, const void* id128, int32_t rank, int32_t nranks);
+
+    /* ---- measurement helpers ---- */
+    /* number of kernels this context launched since creation (bench.py's gpu_launches) */
+    int picstep_launch_count(picstep_ctx* ctx, int64_t* n);
+    /* accumulated device time per stage in ms since the last call with reset!=0; names via picstep_stage_name.
+     * stages: 0 current_reset 1 push 2 migrate 3 field_before 4 deposit 5 add_current 6 field_after */
+    int picstep_stage_times(picstep_ctx* ctx, int32_t enable, float* ms7);
+    /* the CUDA stream (cudaStream_t) all work of the context is queued on */
+    int picstep_stream(picstep_ctx* ctx, void** stream);
+
+    /* ---- host-side pure functions (no GPU needed): domain decomposition used by the exchange ---- */
+    /* neighbour ranks of `rank` along `axis` in a devices[3] grid, x fastest (CommunicatorMPI.cpp:70-111);
+     * -1 where the boundary is not periodic */
+    int picstep_neighbor_ranks(const int32_t* devices, const int32_t* periodic, int32_t rank, int32_t axis, int32_t* lower, int32_t* upper);
+    /* guard widths actually exchanged for E/B (max of interpolation and solver margins,
+     * fields/EMFieldBase.x.cpp:58-110) and J (current solver margins, FieldJ.x.cpp:78-118): out[0]=lower, out[1]=upper */
+    int picstep_exchange_widths(int32_t shape, int32_t field_solver, int32_t lehe_dir, int32_t field, int32_t axis, int32_t* out2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICSTEP_H */

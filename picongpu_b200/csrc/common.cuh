@@ -1,0 +1,93 @@
+// common.cuh — shared device-side definitions of libpicstep (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace picstep
+{
+    // SuperCellSize 8x8x4 and 256-slot frames (reference: include/picongpu/param/memory.param:51-60)
+    constexpr int SCX = 8, SCY = 8, SCZ = 4, SCVOL = SCX * SCY * SCZ;
+    constexpr int FRAME_SLOTS = 256;
+
+    // Re-sort keys: key = supercell_linear * 256 + localCellIdx for particles that stay on this rank.
+    // bit31 marks a particle leaving the rank along the split axis, bit30 the side (0 lower, 1 upper); the low
+    // 30 bits are then the key in the RECEIVER's key space.  KEY_DROP: particle left through an open boundary.
+    constexpr uint32_t KEY_LEAVE = 0x80000000u;
+    constexpr uint32_t KEY_UPPER = 0x40000000u;
+    constexpr uint32_t KEY_MASK = 0x3FFFFFFFu;
+    constexpr uint32_t KEY_DROP = 0xFFFFFFFFu;
+
+#ifdef PICSTEP_EXACT
+    // bit-exact build (-fmad=false): the reference's CPU backend computes rsqrt as 1/sqrt
+    __device__ __forceinline__ float ps_rsqrt(float x)
+    {
+        return 1.0f / sqrtf(x);
+    }
+#else
+    // production build: same as the reference's CUDA backend (alpaka rsqrt -> ::rsqrtf)
+    __device__ __forceinline__ float ps_rsqrt(float x)
+    {
+        return rsqrtf(x);
+    }
+#endif
+
+    struct DevParams
+    {
+        int n[3]; // local cells
+        int g[3]; // guard cells per side
+        int N[3]; // padded cells
+        int nsc[3]; // local supercells
+        int wrap[3]; // periodic wrap handled inside this rank
+        int open[3]; // 1: non-periodic outer boundary on this axis (particles leaving are dropped)
+        int split_axis; // axis decomposed over ranks, -1 if none
+        int has_lower, has_upper; // neighbour ranks exist along split_axis
+        long long vol; // N0*N1*N2
+        float cell[3];
+        float dt, c, eps0, mue0;
+        int lehe_dir;
+    };
+
+    struct SpeciesDev
+    {
+        float* pos[3];
+        float* mom[3];
+        float* w;
+        uint16_t* cell; // localCellIdx
+        float mass_per_w; // getMass<Frame>()  = base_mass * massRatio
+        float charge_per_w; // getCharge<Frame>() = base_charge * chargeRatio
+    };
+
+    struct Field3
+    {
+        float* c[3];
+    };
+
+    __device__ __forceinline__ long long fidx(DevParams const& P, int x, int y, int z)
+    {
+        return ((long long) z * P.N[1] + y) * P.N[0] + x;
+    }
+
+    // Lehe solver coefficients per differentiation direction (Lehe/Derivative.hpp:94-137)
+    struct LeheCoeffs
+    {
+        float alpha[3], delta[3], beta1[3], beta2[3];
+    };
+
+    // arguments of the synthetic KelvinHelmholtz initial condition (init.cu)
+    struct KhiArgs
+    {
+        int ppc[3];
+        int globalN[3];
+        int globalOff[3];
+        float weighting, driftE, driftI, stddev;
+        uint32_t seed;
+    };
+
+    // 32-byte migration record (KernelCopyGuardToExchange's "border frame", one particle per slot)
+    struct __align__(16) MigRecord
+    {
+        float px, py, pz, ux;
+        float uy, uz, w;
+        uint32_t key;
+    };
+} // namespace picstep

@@ -1,0 +1,475 @@
+// fields.cu — Maxwell solver (reference kernels K9/K10: KernelAddCurrentDensity, KernelUpdateField,
+// include/picongpu/fields/MaxwellSolver/FDTD/FDTDBase.kernel:51-199, AddCurrentDensity.kernel:38-96), guard
+// exchange kernels (K8: include/pmacc/fields/operations/{CopyGuardToExchange,AddExchangeToBorder}.hpp) and the
+// field-side reductions used as parity observables.
+//
+// Fields are SoA planes (one float array per component, x fastest, guards included).  The curl stencils are
+// pure streaming kernels: one thread per cell, x along the warp so every load is a coalesced 128-byte row
+// segment; the +-1 (Yee) / +-2 (Lehe) neighbours in y and z come out of L1/L2.  Per cell and launch the
+// algorithmic traffic is 12 B read + 24 B read/write.
+#include "common.cuh"
+#include "shapes.cuh"
+
+namespace picstep
+{
+    // MODE 0: forward difference (ForwardDerivative.hpp:58-63), 1: backward (BackwardDerivative.hpp:58-63),
+    // 2: Lehe (Lehe/Derivative.hpp:113-146 along the Cherenkov-free direction, :225-236 otherwise)
+    template<int MODE, int DIR>
+    __device__ __forceinline__ float deriv(DevParams const& P, LeheCoeffs const& L, float const* __restrict__ f, long long i, long long const st[3])
+    {
+        float const h = P.cell[DIR];
+        long long const s = st[DIR];
+        if constexpr(MODE == 0)
+            return (f[i + s] - f[i]) / h;
+        else if constexpr(MODE == 1)
+            return (f[i] - f[i - s]) / h;
+        else
+        {
+            auto fwd = [&](long long j) { return (f[j + s] - f[j]) / h; };
+            if(DIR == P.lehe_dir)
+            {
+                long long const s1 = st[(DIR + 1) % 3], s2 = st[(DIR + 2) % 3];
+                float r = L.alpha[DIR] * fwd(i) + L.beta1[DIR] * fwd(i + s1);
+                r = r + L.beta1[DIR] * fwd(i - s1);
+                r = r + L.beta2[DIR] * fwd(i + s2);
+                r = r + L.beta2[DIR] * fwd(i - s2);
+                r = r + L.delta[DIR] * (f[i + 2 * s] - f[i - s]) / h;
+                return r;
+            }
+            else
+            {
+                float const beta = 0.125f;
+                float const alpha = 1.0f - 2.0f * beta;
+                long long const sc = st[P.lehe_dir];
+                float r = alpha * fwd(i) + beta * fwd(i + sc);
+                r = r + beta * fwd(i - sc);
+                return r;
+            }
+        }
+    }
+
+    // curl (differentiation/Curl.hpp:84-90) = (dFz/dy - dFy/dz, dFx/dz - dFz/dx, dFy/dx - dFx/dy)
+    template<int MODE>
+    __device__ __forceinline__ void curl(DevParams const& P, LeheCoeffs const& L, Field3 const& F, long long i, long long const st[3], float out[3])
+    {
+        float const dzdy = deriv<MODE, 1>(P, L, F.c[2], i, st);
+        float const dydz = deriv<MODE, 2>(P, L, F.c[1], i, st);
+        float const dxdz = deriv<MODE, 2>(P, L, F.c[0], i, st);
+        float const dzdx = deriv<MODE, 0>(P, L, F.c[2], i, st);
+        float const dydx = deriv<MODE, 0>(P, L, F.c[1], i, st);
+        float const dxdy = deriv<MODE, 1>(P, L, F.c[0], i, st);
+        out[0] = dzdy - dydz;
+        out[1] = dxdz - dzdx;
+        out[2] = dydx - dxdy;
+    }
+
+    // UpdateBHalfFunctor: B -= curlE * 0.5 * dt   (FDTDBase.kernel:115-121)
+    template<int MODE>
+    __global__ void __launch_bounds__(256) updateBHalfKernel(DevParams P, LeheCoeffs L, Field3 E, Field3 B)
+    {
+        int const x = blockIdx.x * blockDim.x + threadIdx.x;
+        int const y = blockIdx.y * blockDim.y + threadIdx.y;
+        int const z = blockIdx.z * blockDim.z + threadIdx.z;
+        if(x >= P.n[0] || y >= P.n[1] || z >= P.n[2])
+            return;
+        long long const st[3] = {1, P.N[0], (long long) P.N[0] * P.N[1]};
+        long long const i = fidx(P, x + P.g[0], y + P.g[1], z + P.g[2]);
+        float cu[3];
+        curl<MODE>(P, L, E, i, st, cu);
+#pragma unroll
+        for(int c = 0; c < 3; ++c)
+            B.c[c][i] -= cu[c] * 0.5f * P.dt;
+    }
+
+    // UpdateEFunctor: E += curlB * c^2 * dt  (FDTDBase.kernel:74-81); optionally fused with the current term
+    // E += coeff * J (currentInterpolation/None.hpp:60-64) when ADDJ (two separate roundings, same as two kernels)
+    __global__ void __launch_bounds__(256) updateEKernel(DevParams P, LeheCoeffs L, Field3 E, Field3 B)
+    {
+        int const x = blockIdx.x * blockDim.x + threadIdx.x;
+        int const y = blockIdx.y * blockDim.y + threadIdx.y;
+        int const z = blockIdx.z * blockDim.z + threadIdx.z;
+        if(x >= P.n[0] || y >= P.n[1] || z >= P.n[2])
+            return;
+        long long const st[3] = {1, P.N[0], (long long) P.N[0] * P.N[1]};
+        long long const i = fidx(P, x + P.g[0], y + P.g[1], z + P.g[2]);
+        float cu[3];
+        curl<1>(P, L, B, i, st, cu);
+        float const c2 = P.c * P.c;
+#pragma unroll
+        for(int c = 0; c < 3; ++c)
+            E.c[c][i] += cu[c] * c2 * P.dt;
+    }
+
+    // KernelAddCurrentDensity + None: E += (-(1/eps0) * dt) * J   (FDTD.hpp:84-85)
+    __global__ void __launch_bounds__(256) addCurrentKernel(DevParams P, Field3 E, Field3 J)
+    {
+        int const x = blockIdx.x * blockDim.x + threadIdx.x;
+        int const y = blockIdx.y * blockDim.y + threadIdx.y;
+        int const z = blockIdx.z * blockDim.z + threadIdx.z;
+        if(x >= P.n[0] || y >= P.n[1] || z >= P.n[2])
+            return;
+        long long const i = fidx(P, x + P.g[0], y + P.g[1], z + P.g[2]);
+        float const coeff = -(1.0f / P.eps0) * P.dt;
+#pragma unroll
+        for(int c = 0; c < 3; ++c)
+            E.c[c][i] += coeff * J.c[c][i];
+    }
+
+    // ---- guard exchange ------------------------------------------------------------------------------------------
+    // One axis at a time (x, then y, then z for copies; the same order for the J reduction), every pass spanning the
+    // full padded extent of the two other axes, so the 26 directions of the reference collapse into 3 passes.
+    // slab geometry: `width` planes starting at plane `start` along `axis`.
+    __device__ __forceinline__ long long slabIndex(DevParams const& P, int axis, int plane, int u, int v)
+    {
+        // (u,v) run over the two other axes in ascending axis order
+        int c[3];
+        c[axis] = plane;
+        c[(axis == 0) ? 1 : 0] = u;
+        c[(axis == 2) ? 1 : 2] = v;
+        return fidx(P, c[0], c[1], c[2]);
+    }
+
+    // local periodic wrap: dst planes <- (or +=) src planes, all three components
+    template<bool ADD>
+    __global__ void __launch_bounds__(256) haloLocalKernel(DevParams P, Field3 F, int ncomp, int axis, int srcStart, int dstStart, int width)
+    {
+        int const U = P.N[(axis == 0) ? 1 : 0], V = P.N[(axis == 2) ? 1 : 2];
+        long long const per = (long long) U * V * width;
+        long long const total = per * ncomp;
+        for(long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x)
+        {
+            int const comp = int(t / per);
+            long long r = t % per;
+            int u, v, w;
+            if(axis == 0)
+            {
+                w = int(r % width);
+                r /= width;
+                u = int(r % U);
+                v = int(r / U);
+            }
+            else
+            {
+                u = int(r % U);
+                r /= U;
+                if(axis == 1)
+                {
+                    w = int(r % width);
+                    v = int(r / width);
+                }
+                else
+                {
+                    v = int(r % V);
+                    w = int(r / V);
+                }
+            }
+            long long const s = slabIndex(P, axis, srcStart + w, u, v), d = slabIndex(P, axis, dstStart + w, u, v);
+            if(ADD)
+                F.c[comp][d] += F.c[comp][s];
+            else
+                F.c[comp][d] = F.c[comp][s];
+        }
+    }
+
+    // pack `width` planes into a contiguous buffer [comp][w][v][u] / unpack (copy or add)
+    __global__ void __launch_bounds__(256) haloPackKernel(DevParams P, Field3 F, int ncomp, int axis, int start, int width, float* __restrict__ buf)
+    {
+        int const U = P.N[(axis == 0) ? 1 : 0], V = P.N[(axis == 2) ? 1 : 2];
+        long long const per = (long long) U * V * width;
+        long long const total = per * ncomp;
+        for(long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x)
+        {
+            int const comp = int(t / per);
+            long long r = t % per;
+            int const u = int(r % U);
+            r /= U;
+            int const v = int(r % V);
+            int const w = int(r / V);
+            buf[t] = F.c[comp][slabIndex(P, axis, start + w, u, v)];
+        }
+    }
+
+    template<bool ADD>
+    __global__ void __launch_bounds__(256) haloUnpackKernel(DevParams P, Field3 F, int ncomp, int axis, int start, int width, float const* __restrict__ buf)
+    {
+        int const U = P.N[(axis == 0) ? 1 : 0], V = P.N[(axis == 2) ? 1 : 2];
+        long long const per = (long long) U * V * width;
+        long long const total = per * ncomp;
+        for(long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x)
+        {
+            int const comp = int(t / per);
+            long long r = t % per;
+            int const u = int(r % U);
+            r /= U;
+            int const v = int(r % V);
+            int const w = int(r / V);
+            long long const d = slabIndex(P, axis, start + w, u, v);
+            if(ADD)
+                F.c[comp][d] += buf[t];
+            else
+                F.c[comp][d] = buf[t];
+        }
+    }
+
+    // ---- layout conversion (reference AoS float3 <-> SoA planes) -------------------------------------------------
+    __global__ void __launch_bounds__(256) aosToSoaKernel(float const* __restrict__ aos, Field3 F, long long vol)
+    {
+        for(long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < 3 * vol; t += (long long) gridDim.x * blockDim.x)
+            F.c[t % 3][t / 3] = aos[t];
+    }
+    __global__ void __launch_bounds__(256) soaToAosKernel(Field3 F, float* __restrict__ aos, long long vol)
+    {
+        for(long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < 3 * vol; t += (long long) gridDim.x * blockDim.x)
+            aos[t] = F.c[t % 3][t / 3];
+    }
+
+    // ---- reductions ----------------------------------------------------------------------------------------------
+    __device__ __forceinline__ double blockSum(double v)
+    {
+        __shared__ double ws[8];
+        __syncthreads();
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1)
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+        int const tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+        if((tid & 31) == 0)
+            ws[tid >> 5] = v;
+        __syncthreads();
+        double s = 0;
+        if(tid == 0)
+            for(int i = 0; i < 8; ++i)
+                s += ws[i];
+        return s;
+    }
+
+    // EnergyFields.x.cpp:198-233: sum of squares over CORE+BORDER, out[0] += B^2, out[1] += E^2
+    __global__ void __launch_bounds__(256) fieldEnergyKernel(DevParams P, Field3 E, Field3 B, double* __restrict__ out)
+    {
+        long long const ncell = (long long) P.n[0] * P.n[1] * P.n[2];
+        double sB = 0, sE = 0;
+        for(long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < ncell; t += (long long) gridDim.x * blockDim.x)
+        {
+            int const x = int(t % P.n[0]), y = int((t / P.n[0]) % P.n[1]), z = int(t / ((long long) P.n[0] * P.n[1]));
+            long long const i = fidx(P, x + P.g[0], y + P.g[1], z + P.g[2]);
+#pragma unroll
+            for(int c = 0; c < 3; ++c)
+            {
+                sB += double(B.c[c][i]) * double(B.c[c][i]);
+                sE += double(E.c[c][i]) * double(E.c[c][i]);
+            }
+        }
+        sB = blockSum(sB);
+        sE = blockSum(sE);
+        if(threadIdx.x == 0)
+        {
+            atomicAdd(&out[0], sB);
+            atomicAdd(&out[1], sE);
+        }
+    }
+
+    // EnergyParticles.x.cpp:100-131 + KinEnergy.hpp:38-68
+    __global__ void __launch_bounds__(256) particleEnergyKernel(DevParams P, SpeciesDev S, uint32_t const* __restrict__ nPart, double* __restrict__ out)
+    {
+        uint32_t const n = *nPart;
+        double ek = 0, et = 0;
+        float const c2 = P.c * P.c;
+        for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        {
+            float const ux = S.mom[0][i], uy = S.mom[1][i], uz = S.mom[2][i];
+            float m2 = ux * ux;
+            m2 += uy * uy;
+            m2 += uz * uz;
+            float const mass = S.mass_per_w * S.w[i];
+            float const gamma = sqrtf(1.0f + m2 * (1.0f / (mass * mass * c2)));
+            float kin;
+            if(gamma < 1.005f) // GAMMA_THRESH, param/speciesConstants.param:39
+                kin = m2 / (2.0f * mass);
+            else
+                kin = (gamma - 1.0f) * mass * c2;
+            ek += double(kin);
+            et += double(sqrtf(m2 + mass * mass * c2) * P.c);
+        }
+        ek = blockSum(ek);
+        et = blockSum(et);
+        if(threadIdx.x == 0)
+        {
+            atomicAdd(&out[0], ek);
+            atomicAdd(&out[1], et);
+        }
+    }
+
+    // ChargeDensity into a scalar grid (particleToGrid/ComputeGridValuePerFrame.hpp:60-134)
+    template<int SHAPE>
+    __global__ void __launch_bounds__(256) chargeDensityKernel(DevParams P, SpeciesDev S, uint32_t const* __restrict__ cellOff, float* __restrict__ rho)
+    {
+        using Sh = Shape<SHAPE>;
+        constexpr int lo = Sh::SUPP / 2, up = (Sh::SUPP + 1) / 2;
+        int const sc = blockIdx.x;
+        int const scx = sc % P.nsc[0], scy = (sc / P.nsc[0]) % P.nsc[1], scz = sc / (P.nsc[0] * P.nsc[1]);
+        uint32_t const p0 = cellOff[sc * SCVOL], p1 = cellOff[(sc + 1) * SCVOL];
+        float const V = P.cell[0] * P.cell[1] * P.cell[2];
+        for(uint32_t i = p0 + threadIdx.x; i < p1; i += blockDim.x)
+        {
+            int const lc = S.cell[i];
+            int const cx = scx * SCX + lc % SCX + P.g[0], cy = scy * SCY + (lc / SCX) % SCY + P.g[1], cz = scz * SCZ + lc / (SCX * SCY) + P.g[2];
+            float const px = S.pos[0][i], py = S.pos[1][i], pz = S.pos[2][i];
+            float const attr = (S.charge_per_w * S.w[i]) / V;
+            for(int oz = -lo; oz <= up; ++oz)
+                for(int oy = -lo; oy <= up; ++oy)
+                    for(int ox = -lo; ox <= up; ++ox)
+                    {
+                        float a = 1.0f;
+                        a *= shapeEval<SHAPE>(float(ox) - px);
+                        a *= shapeEval<SHAPE>(float(oy) - py);
+                        a *= shapeEval<SHAPE>(float(oz) - pz);
+                        atomicAdd(&rho[fidx(P, cx + ox, cy + oy, cz + oz)], a * attr);
+                    }
+        }
+    }
+
+    // ChargeConservation.tpp:122-136,205-259: max |div E * eps0 - rho| over CORE+BORDER (non-negative floats order
+    // like their bit patterns, so atomicMax on the int view is exact)
+    __global__ void __launch_bounds__(256) gaussResidualKernel(DevParams P, Field3 E, float const* __restrict__ rho, int* __restrict__ outMax)
+    {
+        long long const ncell = (long long) P.n[0] * P.n[1] * P.n[2];
+        float const rw = 1.0f / P.cell[0], rh = 1.0f / P.cell[1], rd = 1.0f / P.cell[2];
+        float mx = 0.0f;
+        long long const sy = P.N[0], sz = (long long) P.N[0] * P.N[1];
+        for(long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < ncell; t += (long long) gridDim.x * blockDim.x)
+        {
+            int const x = int(t % P.n[0]), y = int((t / P.n[0]) % P.n[1]), z = int(t / ((long long) P.n[0] * P.n[1]));
+            long long const i = fidx(P, x + P.g[0], y + P.g[1], z + P.g[2]);
+            float const div = (E.c[0][i] - E.c[0][i - 1]) * rw + (E.c[1][i] - E.c[1][i - sy]) * rh + (E.c[2][i] - E.c[2][i - sz]) * rd;
+            mx = fmaxf(mx, fabsf(div * P.eps0 - rho[i]));
+        }
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1)
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if((threadIdx.x & 31) == 0)
+            atomicMax(outMax, __float_as_int(mx));
+    }
+
+    // ---- launchers -----------------------------------------------------------------------------------------------
+    static inline dim3 cellGrid(DevParams const& P, dim3 b)
+    {
+        return dim3((P.n[0] + b.x - 1) / b.x, (P.n[1] + b.y - 1) / b.y, (P.n[2] + b.z - 1) / b.z);
+    }
+
+    cudaError_t launchUpdateBHalf(int solver, DevParams const& P, LeheCoeffs const& L, Field3 E, Field3 B, cudaStream_t st)
+    {
+        dim3 const b(32, 4, 2);
+        if(solver == 1)
+            updateBHalfKernel<2><<<cellGrid(P, b), b, 0, st>>>(P, L, E, B);
+        else
+            updateBHalfKernel<0><<<cellGrid(P, b), b, 0, st>>>(P, L, E, B);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchUpdateE(DevParams const& P, LeheCoeffs const& L, Field3 E, Field3 B, cudaStream_t st)
+    {
+        dim3 const b(32, 4, 2);
+        updateEKernel<<<cellGrid(P, b), b, 0, st>>>(P, L, E, B);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchAddCurrent(DevParams const& P, Field3 E, Field3 J, cudaStream_t st)
+    {
+        dim3 const b(32, 4, 2);
+        addCurrentKernel<<<cellGrid(P, b), b, 0, st>>>(P, E, J);
+        return cudaGetLastError();
+    }
+
+    static inline int slabGrid(DevParams const& P, int axis, int width, int ncomp)
+    {
+        long long const per = (long long) P.N[(axis == 0) ? 1 : 0] * P.N[(axis == 2) ? 1 : 2] * width * ncomp;
+        long long b = (per + 255) / 256;
+        if(b > 148 * 8)
+            b = 148 * 8;
+        if(b < 1)
+            b = 1;
+        return int(b);
+    }
+
+    cudaError_t launchHaloLocal(bool add, DevParams const& P, Field3 F, int ncomp, int axis, int srcStart, int dstStart, int width, cudaStream_t st)
+    {
+        if(width <= 0)
+            return cudaSuccess;
+        if(add)
+            haloLocalKernel<true><<<slabGrid(P, axis, width, ncomp), 256, 0, st>>>(P, F, ncomp, axis, srcStart, dstStart, width);
+        else
+            haloLocalKernel<false><<<slabGrid(P, axis, width, ncomp), 256, 0, st>>>(P, F, ncomp, axis, srcStart, dstStart, width);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchHaloPack(DevParams const& P, Field3 F, int ncomp, int axis, int start, int width, float* buf, cudaStream_t st)
+    {
+        if(width <= 0)
+            return cudaSuccess;
+        haloPackKernel<<<slabGrid(P, axis, width, ncomp), 256, 0, st>>>(P, F, ncomp, axis, start, width, buf);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchHaloUnpack(bool add, DevParams const& P, Field3 F, int ncomp, int axis, int start, int width, float const* buf, cudaStream_t st)
+    {
+        if(width <= 0)
+            return cudaSuccess;
+        if(add)
+            haloUnpackKernel<true><<<slabGrid(P, axis, width, ncomp), 256, 0, st>>>(P, F, ncomp, axis, start, width, buf);
+        else
+            haloUnpackKernel<false><<<slabGrid(P, axis, width, ncomp), 256, 0, st>>>(P, F, ncomp, axis, start, width, buf);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchAosToSoa(float const* aos, Field3 F, long long vol, cudaStream_t st)
+    {
+        aosToSoaKernel<<<148 * 8, 256, 0, st>>>(aos, F, vol);
+        return cudaGetLastError();
+    }
+    cudaError_t launchSoaToAos(Field3 F, float* aos, long long vol, cudaStream_t st)
+    {
+        soaToAosKernel<<<148 * 8, 256, 0, st>>>(F, aos, vol);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchFieldEnergy(DevParams const& P, Field3 E, Field3 B, double* out, cudaStream_t st)
+    {
+        fieldEnergyKernel<<<148 * 4, 256, 0, st>>>(P, E, B, out);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchParticleEnergy(DevParams const& P, SpeciesDev S, uint32_t const* nPart, double* out, cudaStream_t st)
+    {
+        particleEnergyKernel<<<148 * 8, 256, 0, st>>>(P, S, nPart, out);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchChargeDensity(int shape, DevParams const& P, SpeciesDev S, uint32_t const* cellOff, float* rho, cudaStream_t st)
+    {
+        int const nscTot = P.nsc[0] * P.nsc[1] * P.nsc[2];
+        switch(shape)
+        {
+        case 0:
+            chargeDensityKernel<0><<<nscTot, 256, 0, st>>>(P, S, cellOff, rho);
+            break;
+        case 1:
+            chargeDensityKernel<1><<<nscTot, 256, 0, st>>>(P, S, cellOff, rho);
+            break;
+        case 2:
+            chargeDensityKernel<2><<<nscTot, 256, 0, st>>>(P, S, cellOff, rho);
+            break;
+        case 3:
+            chargeDensityKernel<3><<<nscTot, 256, 0, st>>>(P, S, cellOff, rho);
+            break;
+        default:
+            chargeDensityKernel<4><<<nscTot, 256, 0, st>>>(P, S, cellOff, rho);
+            break;
+        }
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchGaussResidual(DevParams const& P, Field3 E, float const* rho, int* outMax, cudaStream_t st)
+    {
+        gaussResidualKernel<<<148 * 4, 256, 0, st>>>(P, E, rho, outMax);
+        return cudaGetLastError();
+    }
+} // namespace picstep

@@ -1,0 +1,1162 @@
+// picstep.cu — C ABI (include/picstep.h) and the C++17 host driver that mirrors Simulation::runOneStep
+// (reference: include/picongpu/simulation/control/Simulation.hpp:522-542).  All device work of a context is queued
+// on one compute stream; guard/migration traffic between ranks goes through NCCL send/recv (comm.cu).
+#include "../../include/picstep.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace picstep
+{
+    // kernels (push.cu, deposit.cu, resort.cu, fields.cu, init.cu)
+    cudaError_t launchPush(int, int, DevParams const&, SpeciesDev const&, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, cudaStream_t);
+    cudaError_t launchGather(int, DevParams const&, SpeciesDev const&, Field3, Field3, uint32_t const*, float*, long long, cudaStream_t);
+    cudaError_t launchDeposit(int, int, bool, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
+    cudaError_t launchScan(uint32_t const*, uint32_t*, uint32_t*, uint32_t*, int, uint32_t*, uint32_t, int*, cudaStream_t);
+    cudaError_t launchScatter(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t*, cudaStream_t);
+    cudaError_t launchCountRecords(MigRecord const*, uint32_t, uint32_t*, cudaStream_t);
+    cudaError_t launchScatterRecords(MigRecord const*, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, cudaStream_t);
+    cudaError_t launchPackLeavers(DevParams const&, SpeciesDev, uint32_t const*, uint32_t const*, MigRecord*, MigRecord*, uint32_t*, uint32_t, int*, cudaStream_t);
+    cudaError_t launchKeysFromCells(DevParams const&, int32_t const*, uint32_t, uint32_t*, uint32_t*, int*, cudaStream_t);
+    cudaError_t launchCellsFromRuns(DevParams const&, uint16_t const*, uint32_t const*, int32_t*, cudaStream_t);
+    cudaError_t launchSupercellCounts(uint32_t const*, long long*, int, cudaStream_t);
+    cudaError_t launchUpdateBHalf(int, DevParams const&, LeheCoeffs const&, Field3, Field3, cudaStream_t);
+    cudaError_t launchUpdateE(DevParams const&, LeheCoeffs const&, Field3, Field3, cudaStream_t);
+    cudaError_t launchAddCurrent(DevParams const&, Field3, Field3, cudaStream_t);
+    cudaError_t launchHaloLocal(bool, DevParams const&, Field3, int, int, int, int, int, cudaStream_t);
+    cudaError_t launchHaloPack(DevParams const&, Field3, int, int, int, int, float*, cudaStream_t);
+    cudaError_t launchHaloUnpack(bool, DevParams const&, Field3, int, int, int, int, float const*, cudaStream_t);
+    cudaError_t launchAosToSoa(float const*, Field3, long long, cudaStream_t);
+    cudaError_t launchSoaToAos(Field3, float*, long long, cudaStream_t);
+    cudaError_t launchFieldEnergy(DevParams const&, Field3, Field3, double*, cudaStream_t);
+    cudaError_t launchParticleEnergy(DevParams const&, SpeciesDev, uint32_t const*, double*, cudaStream_t);
+    cudaError_t launchChargeDensity(int, DevParams const&, SpeciesDev, uint32_t const*, float*, cudaStream_t);
+    cudaError_t launchGaussResidual(DevParams const&, Field3, float const*, int*, cudaStream_t);
+    cudaError_t launchKhiInit(DevParams const&, SpeciesDev, SpeciesDev, uint32_t*, uint32_t*, KhiArgs const&, cudaStream_t);
+
+    // NCCL transport (comm.cu)
+    struct Comm;
+    int commUniqueId(void* id128, std::string& err);
+    int commInit(Comm** out, void const* id128, int rank, int nranks, std::string& err);
+    void commDestroy(Comm*);
+    // exchange with the lower / upper neighbour in one NCCL group; null pointers or zero counts are skipped
+    int commSendRecv(Comm*, void const* sendLo, size_t nSendLo, void* recvLo, size_t nRecvLo, int rankLo, void const* sendHi, size_t nSendHi, void* recvHi, size_t nRecvHi, int rankHi, cudaStream_t, std::string& err);
+
+    struct SpeciesHost
+    {
+        std::string name;
+        float massRatio = 1, chargeRatio = 1;
+        int64_t capacity = 0;
+        float* attr[2][7] = {}; // px,py,pz,ux,uy,uz,w per buffer
+        uint16_t* cell[2] = {};
+        int cur = 0;
+        uint32_t* key = nullptr;
+        uint32_t* cellOff[2] = {};
+        uint32_t* cellCnt = nullptr;
+        uint32_t *scSum = nullptr, *scOff = nullptr;
+        uint32_t* nDev = nullptr; // [2], indexed like cur
+        uint32_t nUpper = 0; // host side upper bound of the particle count
+        // migration
+        MigRecord *sendLo = nullptr, *sendHi = nullptr, *recvLo = nullptr, *recvHi = nullptr;
+        uint32_t capRec = 0;
+        uint32_t* sendCnt = nullptr; // device [2]
+    };
+
+    constexpr int NSTAGE = 7;
+} // namespace picstep
+
+using namespace picstep;
+
+struct picstep_ctx
+{
+    picstep_params prm{};
+    DevParams P{};
+    LeheCoeffs lehe{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    float* fieldMem[3] = {}; // E,B,J : 3*vol floats each
+    float* rho = nullptr; // vol floats (Gauss check scratch)
+    float* aosTmp = nullptr; // 3*vol floats (layout conversion scratch)
+    float* haloBuf[4] = {}; // sendLo, sendHi, recvLo, recvHi
+    size_t haloBufFloats = 0;
+    double* redBuf = nullptr; // device [4]
+    int* flags = nullptr; // device [4]: 0 overflow, 1 bad cell index, 2 record overflow, 3 gauss max
+    uint32_t* hostPinned = nullptr; // pinned [8] readback
+    std::vector<SpeciesHost> species;
+    std::string err;
+    int64_t launches = 0;
+    // multi GPU
+    Comm* comm = nullptr;
+    int rank = 0, nranks = 1, rankLo = -1, rankHi = -1;
+    // stage timing
+    bool timing = false;
+    cudaEvent_t ev[2] = {};
+    float stageMs[NSTAGE] = {};
+};
+
+static std::string g_createErr;
+
+namespace
+{
+    int fail(picstep_ctx* c, int code, std::string const& msg)
+    {
+        if(c)
+            c->err = msg;
+        else
+            g_createErr = msg;
+        return code;
+    }
+
+#define CU(ctx, call)                                                                                                 \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaError_t e_ = (call);                                                                                      \
+        if(e_ != cudaSuccess)                                                                                         \
+            return fail(ctx, PICSTEP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while(0)
+
+#define KL(ctx, nk, call)                                                                                             \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaError_t e_ = (call);                                                                                      \
+        if(e_ != cudaSuccess)                                                                                         \
+            return fail(ctx, PICSTEP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+        (ctx)->launches += (nk);                                                                                      \
+    } while(0)
+
+    Field3 fieldOf(picstep_ctx* c, int f)
+    {
+        Field3 F;
+        for(int k = 0; k < 3; ++k)
+            F.c[k] = c->fieldMem[f] + (long long) k * c->P.vol;
+        return F;
+    }
+
+    SpeciesDev devOf(picstep_ctx* c, SpeciesHost const& s, int buf)
+    {
+        SpeciesDev d;
+        for(int k = 0; k < 3; ++k)
+        {
+            d.pos[k] = s.attr[buf][k];
+            d.mom[k] = s.attr[buf][3 + k];
+        }
+        d.w = s.attr[buf][6];
+        d.cell = s.cell[buf];
+        d.mass_per_w = c->prm.base_mass * s.massRatio;
+        d.charge_per_w = c->prm.base_charge * s.chargeRatio;
+        return d;
+    }
+
+    int numCells(picstep_ctx* c)
+    {
+        return c->P.nsc[0] * c->P.nsc[1] * c->P.nsc[2] * SCVOL;
+    }
+
+    void freeSpeciesBuffers(SpeciesHost& s)
+    {
+        for(int b = 0; b < 2; ++b)
+        {
+            for(int k = 0; k < 7; ++k)
+            {
+                cudaFree(s.attr[b][k]);
+                s.attr[b][k] = nullptr;
+            }
+            cudaFree(s.cell[b]);
+            s.cell[b] = nullptr;
+        }
+        cudaFree(s.key);
+        s.key = nullptr;
+        cudaFree(s.sendLo);
+        cudaFree(s.sendHi);
+        cudaFree(s.recvLo);
+        cudaFree(s.recvHi);
+        s.sendLo = s.sendHi = s.recvLo = s.recvHi = nullptr;
+    }
+
+    int allocSpeciesBuffers(picstep_ctx* c, SpeciesHost& s, int64_t capacity)
+    {
+        freeSpeciesBuffers(s);
+        if(capacity < 1024)
+            capacity = 1024;
+        if(capacity >= (int64_t(1) << 32) - 1)
+            return fail(c, PICSTEP_ERR_CAPACITY, "species capacity must be < 2^32 particles per rank");
+        s.capacity = capacity;
+        for(int b = 0; b < 2; ++b)
+        {
+            for(int k = 0; k < 7; ++k)
+                CU(c, cudaMalloc(&s.attr[b][k], sizeof(float) * capacity));
+            CU(c, cudaMalloc(&s.cell[b], sizeof(uint16_t) * capacity));
+        }
+        CU(c, cudaMalloc(&s.key, sizeof(uint32_t) * capacity));
+        if(c->P.split_axis >= 0)
+        {
+            // exchange capacity: particles of one border supercell layer could at most all leave; reserve a
+            // quarter of a layer's share of the capacity, at least 64k records (the reference uses fixed
+            // BYTES_EXCHANGE_* sizes with a retry loop, include/picongpu/param/memory.param:82-104)
+            int const a = c->P.split_axis;
+            int64_t const layerShare = capacity / std::max(1, c->P.nsc[a]);
+            s.capRec = uint32_t(std::max<int64_t>(65536, layerShare / 2));
+            CU(c, cudaMalloc(&s.sendLo, sizeof(MigRecord) * s.capRec));
+            CU(c, cudaMalloc(&s.sendHi, sizeof(MigRecord) * s.capRec));
+            CU(c, cudaMalloc(&s.recvLo, sizeof(MigRecord) * s.capRec));
+            CU(c, cudaMalloc(&s.recvHi, sizeof(MigRecord) * s.capRec));
+        }
+        return PICSTEP_OK;
+    }
+
+    // Lehe coefficients in fp64 -> fp32 (Lehe/Derivative.hpp:94-111); betas in fp32 (:134-137)
+    void computeLehe(picstep_params const& p, LeheCoeffs& L)
+    {
+        for(int dir0 = 0; dir0 < 3; ++dir0)
+        {
+            int const dir1 = (dir0 + 1) % 3, dir2 = (dir0 + 2) % 3;
+            double const stepRatio = double(p.cell_size[dir0] / (p.c * p.dt));
+            double const coeff = stepRatio * std::sin(1.5707963267948966 * double(p.c) * double(p.dt) / double(p.cell_size[dir0]));
+            L.delta[dir0] = float(0.25 * (1.0 - coeff * coeff));
+            double const sr1 = double(p.cell_size[dir0] / p.cell_size[dir1]);
+            double const sr2 = double(p.cell_size[dir0] / p.cell_size[dir2]);
+            L.alpha[dir0] = float(1.0 - 2.0 * (0.125 * sr1 * sr1) - 2.0 * (0.125 * sr2 * sr2) - 3.0 * double(L.delta[dir0]));
+            float const s1 = p.cell_size[dir0] / p.cell_size[dir1], s2 = p.cell_size[dir0] / p.cell_size[dir2];
+            L.beta1[dir0] = 0.125f * s1 * s1;
+            L.beta2[dir0] = 0.125f * s2 * s2;
+        }
+    }
+
+    struct StageTimer
+    {
+        picstep_ctx* c;
+        int stage;
+        StageTimer(picstep_ctx* ctx, int st) : c(ctx), stage(st)
+        {
+            if(c->timing)
+                cudaEventRecord(c->ev[0], c->stream);
+        }
+        ~StageTimer()
+        {
+            if(c->timing)
+            {
+                cudaEventRecord(c->ev[1], c->stream);
+                cudaEventSynchronize(c->ev[1]);
+                float ms = 0;
+                cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+                c->stageMs[stage] += ms;
+            }
+        }
+    };
+
+    // ---- guard exchange of one field along all axes ------------------------------------------------------------
+    int exchangeField(picstep_ctx* c, int f)
+    {
+        DevParams const& P = c->P;
+        Field3 F = fieldOf(c, f);
+        bool const add = (f == PICSTEP_FIELD_J);
+        for(int a = 0; a < 3; ++a)
+        {
+            int w[2];
+            picstep_exchange_widths(c->prm.shape, c->prm.field_solver, c->prm.lehe_dir, f, a, w);
+            int const lo = w[0], up = w[1];
+            int const g = P.g[a], n = P.n[a];
+            if(P.wrap[a])
+            {
+                if(!add)
+                {
+                    KL(c, 1, launchHaloLocal(false, P, F, 3, a, g + n - lo, g - lo, lo, c->stream)); // lower guard <- upper border
+                    KL(c, 1, launchHaloLocal(false, P, F, 3, a, g, g + n, up, c->stream)); // upper guard <- lower border
+                }
+                else
+                {
+                    KL(c, 1, launchHaloLocal(true, P, F, 3, a, g - lo, g + n - lo, lo, c->stream)); // upper border += lower guard
+                    KL(c, 1, launchHaloLocal(true, P, F, 3, a, g + n, g, up, c->stream)); // lower border += upper guard
+                }
+            }
+            else if(a == P.split_axis && c->nranks > 1)
+            {
+                if(!c->comm)
+                    return fail(c, PICSTEP_ERR_COMM, "devices > 1 but picstep_comm_init was not called");
+                long long const plane = (long long) P.N[(a == 0) ? 1 : 0] * P.N[(a == 2) ? 1 : 2] * 3;
+                size_t nSendLo, nSendHi, nRecvLo, nRecvHi;
+                if(!add)
+                {
+                    // my lower border (up planes) -> lower neighbour's upper guard; my upper border (lo planes) -> upper neighbour's lower guard
+                    nSendLo = size_t(plane * up);
+                    nSendHi = size_t(plane * lo);
+                    nRecvLo = size_t(plane * lo); // from lower neighbour: its upper border -> my lower guard
+                    nRecvHi = size_t(plane * up);
+                    if(c->rankLo >= 0)
+                        KL(c, 1, launchHaloPack(P, F, 3, a, g, up, c->haloBuf[0], c->stream));
+                    if(c->rankHi >= 0)
+                        KL(c, 1, launchHaloPack(P, F, 3, a, g + n - lo, lo, c->haloBuf[1], c->stream));
+                }
+                else
+                {
+                    // my lower guard (lo planes) -> lower neighbour adds to its upper border; my upper guard (up planes) -> upper neighbour
+                    nSendLo = size_t(plane * lo);
+                    nSendHi = size_t(plane * up);
+                    nRecvLo = size_t(plane * up); // lower neighbour's upper guard -> add to my lower border
+                    nRecvHi = size_t(plane * lo);
+                    if(c->rankLo >= 0)
+                        KL(c, 1, launchHaloPack(P, F, 3, a, g - lo, lo, c->haloBuf[0], c->stream));
+                    if(c->rankHi >= 0)
+                        KL(c, 1, launchHaloPack(P, F, 3, a, g + n, up, c->haloBuf[1], c->stream));
+                }
+                int const rc = commSendRecv(
+                    c->comm,
+                    c->haloBuf[0],
+                    nSendLo * sizeof(float),
+                    c->haloBuf[2],
+                    nRecvLo * sizeof(float),
+                    c->rankLo,
+                    c->haloBuf[1],
+                    nSendHi * sizeof(float),
+                    c->haloBuf[3],
+                    nRecvHi * sizeof(float),
+                    c->rankHi,
+                    c->stream,
+                    c->err);
+                if(rc)
+                    return PICSTEP_ERR_COMM;
+                if(!add)
+                {
+                    if(c->rankLo >= 0)
+                        KL(c, 1, launchHaloUnpack(false, P, F, 3, a, g - lo, lo, c->haloBuf[2], c->stream));
+                    if(c->rankHi >= 0)
+                        KL(c, 1, launchHaloUnpack(false, P, F, 3, a, g + n, up, c->haloBuf[3], c->stream));
+                }
+                else
+                {
+                    if(c->rankLo >= 0)
+                        KL(c, 1, launchHaloUnpack(true, P, F, 3, a, g, up, c->haloBuf[2], c->stream));
+                    if(c->rankHi >= 0)
+                        KL(c, 1, launchHaloUnpack(true, P, F, 3, a, g + n - lo, lo, c->haloBuf[3], c->stream));
+                }
+            }
+            // else: open boundary, guards stay as they are
+        }
+        return PICSTEP_OK;
+    }
+
+    int checkFlags(picstep_ctx* c)
+    {
+        CU(c, cudaMemcpyAsync(c->hostPinned, c->flags, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        int const* f = reinterpret_cast<int const*>(c->hostPinned);
+        if(f[0])
+            return fail(c, PICSTEP_ERR_CAPACITY, "particle capacity exceeded during re-sort");
+        if(f[1])
+            return fail(c, PICSTEP_ERR_INVALID, "particle cell index out of range");
+        if(f[2])
+            return fail(c, PICSTEP_ERR_CAPACITY, "migration record buffer overflow");
+        return PICSTEP_OK;
+    }
+
+    // counting sort of species s from buffer `cur` (keys + histogram ready) into the other buffer
+    int resortSpecies(picstep_ctx* c, SpeciesHost& s, uint32_t nRecLo, uint32_t nRecHi)
+    {
+        int const nscTot = c->P.nsc[0] * c->P.nsc[1] * c->P.nsc[2];
+        int const nxt = s.cur ^ 1;
+        if(nRecLo)
+            KL(c, 1, launchCountRecords(s.recvLo, nRecLo, s.cellCnt, c->stream));
+        if(nRecHi)
+            KL(c, 1, launchCountRecords(s.recvHi, nRecHi, s.cellCnt, c->stream));
+        KL(c, 3, launchScan(s.cellCnt, s.scSum, s.scOff, s.cellOff[nxt], nscTot, s.nDev + nxt, uint32_t(s.capacity), c->flags, c->stream));
+        KL(c, 1, launchScatter(devOf(c, s, s.cur), devOf(c, s, nxt), s.key, s.nDev + s.cur, s.nUpper, s.cellOff[nxt], s.cellCnt, c->stream));
+        if(nRecLo)
+            KL(c, 1, launchScatterRecords(s.recvLo, nRecLo, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+        if(nRecHi)
+            KL(c, 1, launchScatterRecords(s.recvHi, nRecHi, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+        s.cur = nxt;
+        s.nUpper = uint32_t(std::min<int64_t>(s.capacity, int64_t(s.nUpper) + nRecLo + nRecHi));
+        return PICSTEP_OK;
+    }
+} // namespace
+
+extern "C"
+{
+    const char* picstep_version(void)
+    {
+#ifdef PICSTEP_EXACT
+        return "picstep 0.1 sm_100a exact(fmad=off)";
+#else
+        return "picstep 0.1 sm_100a fmad=on";
+#endif
+    }
+
+    const char* picstep_last_error(const picstep_ctx* ctx)
+    {
+        return ctx ? ctx->err.c_str() : g_createErr.c_str();
+    }
+
+    int picstep_neighbor_ranks(const int32_t* devices, const int32_t* periodic, int32_t rank, int32_t axis, int32_t* lower, int32_t* upper)
+    {
+        if(!devices || !periodic || axis < 0 || axis > 2)
+            return PICSTEP_ERR_INVALID;
+        int const total = devices[0] * devices[1] * devices[2];
+        if(rank < 0 || rank >= total)
+            return PICSTEP_ERR_INVALID;
+        int pos[3] = {rank % devices[0], (rank / devices[0]) % devices[1], rank / (devices[0] * devices[1])};
+        auto lin = [&](int const* p) { return p[0] + devices[0] * (p[1] + devices[1] * p[2]); };
+        int lo[3] = {pos[0], pos[1], pos[2]}, hi[3] = {pos[0], pos[1], pos[2]};
+        lo[axis] -= 1;
+        hi[axis] += 1;
+        int rl = -1, rh = -1;
+        if(lo[axis] >= 0)
+            rl = lin(lo);
+        else if(periodic[axis])
+        {
+            lo[axis] = devices[axis] - 1;
+            rl = lin(lo);
+        }
+        if(hi[axis] < devices[axis])
+            rh = lin(hi);
+        else if(periodic[axis])
+        {
+            hi[axis] = 0;
+            rh = lin(hi);
+        }
+        if(lower)
+            *lower = rl;
+        if(upper)
+            *upper = rh;
+        return PICSTEP_OK;
+    }
+
+    int picstep_exchange_widths(int32_t shape, int32_t field_solver, int32_t lehe_dir, int32_t field, int32_t axis, int32_t* out2)
+    {
+        if(shape < 0 || shape > 4 || !out2 || axis < 0 || axis > 2)
+            return PICSTEP_ERR_INVALID;
+        int const supp = shape + 1;
+        if(field == PICSTEP_FIELD_J)
+        {
+            out2[0] = supp / 2 + 1 - (supp + 1) % 2; // Esirkepov.hpp:42-43
+            out2[1] = (supp + 1) / 2 + 1;
+        }
+        else
+        {
+            int const glo = supp / 2, gup = (supp + 1) / 2; // FieldToParticleInterpolation.hpp:49-50
+            int slo = 1, sup = 1; // Yee curls: backward / forward difference
+            if(field_solver == PICSTEP_SOLVER_LEHE)
+                sup = (axis == lehe_dir) ? 2 : 1; // Lehe/Derivative.hpp:77-91
+            out2[0] = std::max(glo, slo);
+            out2[1] = std::max(gup, sup);
+        }
+        return PICSTEP_OK;
+    }
+
+    int picstep_create(const picstep_params* p, picstep_ctx** out)
+    {
+        if(!p || !out)
+            return fail(nullptr, PICSTEP_ERR_INVALID, "null argument");
+        *out = nullptr;
+        int ndev = 0;
+        if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            return fail(nullptr, PICSTEP_ERR_NOGPU, "no CUDA device: libpicstep has no CPU fallback");
+        if(p->device < 0 || p->device >= ndev)
+            return fail(nullptr, PICSTEP_ERR_INVALID, "bad device ordinal");
+        if(p->supercell[0] != SCX || p->supercell[1] != SCY || p->supercell[2] != SCZ)
+            return fail(nullptr, PICSTEP_ERR_INVALID, "only SuperCellSize 8x8x4 is compiled in");
+        if(p->guard_supercells[0] != 1 || p->guard_supercells[1] != 1 || p->guard_supercells[2] != 1)
+            return fail(nullptr, PICSTEP_ERR_INVALID, "only GuardSize 1x1x1 is supported");
+        if(p->shape < 0 || p->shape > 4 || p->pusher < 0 || p->pusher > 1 || p->current_solver < 0 || p->current_solver > 1 || p->field_solver < 0 || p->field_solver > 1 || p->lehe_dir < 0 || p->lehe_dir > 2)
+            return fail(nullptr, PICSTEP_ERR_INVALID, "unknown shape / pusher / current solver / field solver");
+        if(p->current_solver == PICSTEP_CURRENT_EMZ && p->shape == PICSTEP_SHAPE_NGP)
+            return fail(nullptr, PICSTEP_ERR_INVALID, "EmZ needs at least CIC");
+        int nsplit = 0, split = -1;
+        for(int d = 0; d < 3; ++d)
+        {
+            if(p->grid[d] <= 0 || p->grid[d] % p->supercell[d])
+                return fail(nullptr, PICSTEP_ERR_INVALID, "grid must be a positive multiple of the supercell size");
+            if(p->devices[d] < 1 || p->rank_pos[d] < 0 || p->rank_pos[d] >= p->devices[d])
+                return fail(nullptr, PICSTEP_ERR_INVALID, "bad devices / rank_pos");
+            if(p->devices[d] > 1)
+            {
+                ++nsplit;
+                split = d;
+            }
+        }
+        if(nsplit > 1)
+            return fail(nullptr, PICSTEP_ERR_INVALID, "only a 1-D domain decomposition (one axis with devices > 1) is supported");
+
+        auto* c = new picstep_ctx();
+        c->prm = *p;
+        c->device = p->device;
+        DevParams& P = c->P;
+        for(int d = 0; d < 3; ++d)
+        {
+            P.n[d] = p->grid[d];
+            P.g[d] = p->supercell[d] * p->guard_supercells[d];
+            P.N[d] = P.n[d] + 2 * P.g[d];
+            P.nsc[d] = P.n[d] / p->supercell[d];
+            P.wrap[d] = (p->periodic[d] && p->devices[d] == 1) ? 1 : 0;
+            P.open[d] = p->periodic[d] ? 0 : 1;
+            P.cell[d] = p->cell_size[d];
+        }
+        P.split_axis = split;
+        P.vol = (long long) P.N[0] * P.N[1] * P.N[2];
+        P.dt = p->dt;
+        P.c = p->c;
+        P.eps0 = p->eps0;
+        P.mue0 = p->mue0;
+        P.lehe_dir = p->lehe_dir;
+        c->nranks = p->devices[0] * p->devices[1] * p->devices[2];
+        c->rank = p->rank_pos[0] + p->devices[0] * (p->rank_pos[1] + p->devices[1] * p->rank_pos[2]);
+        if(split >= 0)
+            picstep_neighbor_ranks(p->devices, p->periodic, c->rank, split, &c->rankLo, &c->rankHi);
+        P.has_lower = c->rankLo >= 0;
+        P.has_upper = c->rankHi >= 0;
+        computeLehe(*p, c->lehe);
+        if((long long) numCells(c) >= (1ll << 30))
+        {
+            delete c;
+            return fail(nullptr, PICSTEP_ERR_INVALID, "more than 2^30 cells per rank");
+        }
+
+#define CUC(call)                                                                                                     \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaError_t e_ = (call);                                                                                      \
+        if(e_ != cudaSuccess)                                                                                         \
+        {                                                                                                             \
+            std::string m = std::string(#call) + ": " + cudaGetErrorString(e_);                                       \
+            picstep_destroy(c);                                                                                       \
+            return fail(nullptr, PICSTEP_ERR_CUDA, m);                                                                \
+        }                                                                                                             \
+    } while(0)
+        CUC(cudaSetDevice(c->device));
+        CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for(int f = 0; f < 3; ++f)
+        {
+            CUC(cudaMalloc(&c->fieldMem[f], sizeof(float) * 3 * P.vol));
+            CUC(cudaMemsetAsync(c->fieldMem[f], 0, sizeof(float) * 3 * P.vol, c->stream));
+        }
+        CUC(cudaMalloc(&c->redBuf, sizeof(double) * 4));
+        CUC(cudaMalloc(&c->flags, sizeof(int) * 4));
+        CUC(cudaMemsetAsync(c->flags, 0, sizeof(int) * 4, c->stream));
+        CUC(cudaMallocHost(&c->hostPinned, sizeof(double) * 8));
+        CUC(cudaEventCreate(&c->ev[0]));
+        CUC(cudaEventCreate(&c->ev[1]));
+        if(split >= 0)
+        {
+            long long const plane = (long long) P.N[(split == 0) ? 1 : 0] * P.N[(split == 2) ? 1 : 2] * 3;
+            c->haloBufFloats = size_t(plane) * 4; // widest exchange: PCS current margin 4
+            for(int b = 0; b < 4; ++b)
+                CUC(cudaMalloc(&c->haloBuf[b], sizeof(float) * c->haloBufFloats));
+        }
+        CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+        *out = c;
+        return PICSTEP_OK;
+    }
+
+    int picstep_destroy(picstep_ctx* c)
+    {
+        if(!c)
+            return PICSTEP_OK;
+        cudaSetDevice(c->device);
+        if(c->stream)
+            cudaStreamSynchronize(c->stream);
+        for(auto& s : c->species)
+        {
+            freeSpeciesBuffers(s);
+            cudaFree(s.cellOff[0]);
+            cudaFree(s.cellOff[1]);
+            cudaFree(s.cellCnt);
+            cudaFree(s.scSum);
+            cudaFree(s.scOff);
+            cudaFree(s.nDev);
+            cudaFree(s.sendCnt);
+        }
+        for(int f = 0; f < 3; ++f)
+            cudaFree(c->fieldMem[f]);
+        cudaFree(c->rho);
+        cudaFree(c->aosTmp);
+        for(int b = 0; b < 4; ++b)
+            cudaFree(c->haloBuf[b]);
+        cudaFree(c->redBuf);
+        cudaFree(c->flags);
+        if(c->hostPinned)
+            cudaFreeHost(c->hostPinned);
+        if(c->ev[0])
+            cudaEventDestroy(c->ev[0]);
+        if(c->ev[1])
+            cudaEventDestroy(c->ev[1]);
+        if(c->comm)
+            commDestroy(c->comm);
+        if(c->stream)
+            cudaStreamDestroy(c->stream);
+        delete c;
+        return PICSTEP_OK;
+    }
+
+    int picstep_species_add(picstep_ctx* c, const char* name, float mass_ratio, float charge_ratio, int64_t capacity, int32_t* species_id)
+    {
+        if(!c || !name)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        SpeciesHost s;
+        s.name = name;
+        s.massRatio = mass_ratio;
+        s.chargeRatio = charge_ratio;
+        int const ncell = numCells(c);
+        int const nsc = ncell / SCVOL;
+        for(int b = 0; b < 2; ++b)
+        {
+            CU(c, cudaMalloc(&s.cellOff[b], sizeof(uint32_t) * (size_t(ncell) + 1)));
+            CU(c, cudaMemsetAsync(s.cellOff[b], 0, sizeof(uint32_t) * (size_t(ncell) + 1), c->stream));
+        }
+        CU(c, cudaMalloc(&s.cellCnt, sizeof(uint32_t) * ncell));
+        CU(c, cudaMemsetAsync(s.cellCnt, 0, sizeof(uint32_t) * ncell, c->stream));
+        CU(c, cudaMalloc(&s.scSum, sizeof(uint32_t) * nsc));
+        CU(c, cudaMalloc(&s.scOff, sizeof(uint32_t) * (nsc + 1)));
+        CU(c, cudaMalloc(&s.nDev, sizeof(uint32_t) * 2));
+        CU(c, cudaMemsetAsync(s.nDev, 0, sizeof(uint32_t) * 2, c->stream));
+        CU(c, cudaMalloc(&s.sendCnt, sizeof(uint32_t) * 2));
+        CU(c, cudaMemsetAsync(s.sendCnt, 0, sizeof(uint32_t) * 2, c->stream));
+        if(capacity > 0)
+        {
+            int const rc = allocSpeciesBuffers(c, s, capacity);
+            if(rc)
+                return rc;
+        }
+        c->species.push_back(s);
+        if(species_id)
+            *species_id = int32_t(c->species.size()) - 1;
+        return PICSTEP_OK;
+    }
+
+    // ---- fields ---------------------------------------------------------------------------------------------------
+    int picstep_fields_upload_soa(picstep_ctx* c, int32_t f, const float* soa)
+    {
+        if(!c || f < 0 || f > 2 || !soa)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        CU(c, cudaMemcpyAsync(c->fieldMem[f], soa, sizeof(float) * 3 * c->P.vol, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        return PICSTEP_OK;
+    }
+
+    int picstep_fields_download_soa(picstep_ctx* c, int32_t f, float* soa)
+    {
+        if(!c || f < 0 || f > 2 || !soa)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        CU(c, cudaMemcpyAsync(soa, c->fieldMem[f], sizeof(float) * 3 * c->P.vol, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        return PICSTEP_OK;
+    }
+
+    int picstep_fields_upload(picstep_ctx* c, int32_t f, const float* aos)
+    {
+        if(!c || f < 0 || f > 2 || !aos)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        if(!c->aosTmp)
+            CU(c, cudaMalloc(&c->aosTmp, sizeof(float) * 3 * c->P.vol));
+        CU(c, cudaMemcpyAsync(c->aosTmp, aos, sizeof(float) * 3 * c->P.vol, cudaMemcpyHostToDevice, c->stream));
+        KL(c, 1, launchAosToSoa(c->aosTmp, fieldOf(c, f), c->P.vol, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        return PICSTEP_OK;
+    }
+
+    int picstep_fields_download(picstep_ctx* c, int32_t f, float* aos)
+    {
+        if(!c || f < 0 || f > 2 || !aos)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        if(!c->aosTmp)
+            CU(c, cudaMalloc(&c->aosTmp, sizeof(float) * 3 * c->P.vol));
+        KL(c, 1, launchSoaToAos(fieldOf(c, f), c->aosTmp, c->P.vol, c->stream));
+        CU(c, cudaMemcpyAsync(aos, c->aosTmp, sizeof(float) * 3 * c->P.vol, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        return PICSTEP_OK;
+    }
+
+    // ---- particles ------------------------------------------------------------------------------------------------
+    static int uploadAsync(picstep_ctx* c, int32_t sp, int64_t n, const float* pos, const float* mom, const float* w, const int32_t* cell)
+    {
+        SpeciesHost& s = c->species[sp];
+        if(n > s.capacity || s.capacity == 0)
+        {
+            int const rc = allocSpeciesBuffers(c, s, std::max<int64_t>(n + n / 4, 4096));
+            if(rc)
+                return rc;
+        }
+        // stage the unsorted input in the inactive buffer, build keys + histogram, then scatter into the active one
+        int const stage = s.cur ^ 1;
+        int const ncell = numCells(c);
+        CU(c, cudaMemsetAsync(s.cellCnt, 0, sizeof(uint32_t) * ncell, c->stream));
+        uint32_t const n32 = uint32_t(n);
+        CU(c, cudaMemcpyAsync(s.nDev + stage, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        for(int k = 0; k < 3; ++k)
+        {
+            CU(c, cudaMemcpyAsync(s.attr[stage][k], pos + k * n, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+            CU(c, cudaMemcpyAsync(s.attr[stage][3 + k], mom + k * n, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+        }
+        CU(c, cudaMemcpyAsync(s.attr[stage][6], w, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+        // the int32 host cell indices travel through the (not yet used) key array of the active buffer's pos.x
+        int32_t* cellIn = reinterpret_cast<int32_t*>(s.attr[s.cur][0]);
+        CU(c, cudaMemcpyAsync(cellIn, cell, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        KL(c, 1, launchKeysFromCells(c->P, cellIn, n32, s.key, s.cellCnt, c->flags + 1, c->stream));
+        s.cur = stage; // resortSpecies reads from `cur` and writes to the other one
+        s.nUpper = n32;
+        return resortSpecies(c, s, 0, 0);
+    }
+
+    int picstep_particles_upload(picstep_ctx* c, int32_t sp, int64_t n, const float* pos, const float* mom, const float* w, const int32_t* cell)
+    {
+        if(!c || sp < 0 || sp >= int(c->species.size()) || n < 0 || (n > 0 && (!pos || !mom || !w || !cell)))
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        int rc = uploadAsync(c, sp, n, pos, mom, w, cell);
+        if(rc)
+            return rc;
+        return checkFlags(c);
+    }
+
+    int picstep_particles_count(picstep_ctx* c, int32_t sp, int64_t* n)
+    {
+        if(!c || sp < 0 || sp >= int(c->species.size()) || !n)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        SpeciesHost& s = c->species[sp];
+        CU(c, cudaMemcpyAsync(c->hostPinned, s.nDev + s.cur, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        *n = int64_t(c->hostPinned[0]);
+        s.nUpper = c->hostPinned[0];
+        return PICSTEP_OK;
+    }
+
+    int picstep_particles_download(picstep_ctx* c, int32_t sp, int64_t capacity, float* pos, float* mom, float* w, int32_t* cell, int64_t* nOut)
+    {
+        int64_t n = 0;
+        int rc = picstep_particles_count(c, sp, &n);
+        if(rc)
+            return rc;
+        if(nOut)
+            *nOut = n;
+        if(n > capacity)
+            return fail(c, PICSTEP_ERR_CAPACITY, "download buffer too small");
+        if(n == 0)
+            return PICSTEP_OK;
+        SpeciesHost& s = c->species[sp];
+        for(int k = 0; k < 3; ++k)
+        {
+            if(pos)
+                CU(c, cudaMemcpyAsync(pos + k * capacity, s.attr[s.cur][k], sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+            if(mom)
+                CU(c, cudaMemcpyAsync(mom + k * capacity, s.attr[s.cur][3 + k], sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if(w)
+            CU(c, cudaMemcpyAsync(w, s.attr[s.cur][6], sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+        if(cell)
+        {
+            int32_t* tmp = reinterpret_cast<int32_t*>(s.key); // key array is free between steps
+            KL(c, 1, launchCellsFromRuns(c->P, s.cell[s.cur], s.cellOff[s.cur], tmp, c->stream));
+            CU(c, cudaMemcpyAsync(cell, tmp, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(c, cudaStreamSynchronize(c->stream));
+        return PICSTEP_OK;
+    }
+
+    int picstep_supercell_counts(picstep_ctx* c, int32_t sp, int64_t* counts)
+    {
+        if(!c || sp < 0 || sp >= int(c->species.size()) || !counts)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        SpeciesHost& s = c->species[sp];
+        int const nsc = numCells(c) / SCVOL;
+        long long* tmp = nullptr;
+        CU(c, cudaMalloc(&tmp, sizeof(long long) * nsc));
+        KL(c, 1, launchSupercellCounts(s.cellOff[s.cur], tmp, nsc, c->stream));
+        CU(c, cudaMemcpyAsync(counts, tmp, sizeof(long long) * nsc, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(tmp);
+        return PICSTEP_OK;
+    }
+
+    int picstep_init_khi(picstep_ctx* c, const int32_t* ppc_dim, float realPPC, double gammaDrift, double temperature_keV, double ev_pic, uint32_t seed)
+    {
+        if(!c || !ppc_dim || c->species.size() < 2)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        int const ppc = ppc_dim[0] * ppc_dim[1] * ppc_dim[2];
+        int64_t const n = int64_t(numCells(c)) * ppc;
+        for(int sp = 0; sp < 2; ++sp)
+        {
+            SpeciesHost& s = c->species[sp];
+            if(n > s.capacity)
+            {
+                int const rc = allocSpeciesBuffers(c, s, n + n / 4);
+                if(rc)
+                    return rc;
+            }
+            s.nUpper = uint32_t(n);
+            uint32_t const n32 = uint32_t(n);
+            CU(c, cudaMemcpyAsync(s.nDev + s.cur, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        }
+        SpeciesHost& e = c->species[0];
+        SpeciesHost& i = c->species[1];
+        float const weighting = realPPC / float(ppc);
+        double const beta = std::sqrt(1.0 - 1.0 / (gammaDrift * gammaDrift));
+        float const massE = (c->prm.base_mass * e.massRatio) * weighting;
+        float const massI = (c->prm.base_mass * i.massRatio) * weighting;
+        float const driftE = float(gammaDrift * beta * double(massE) * double(c->prm.c));
+        float const driftI = float(gammaDrift * beta * double(massI) * double(c->prm.c));
+        float const energy = float(ev_pic * (temperature_keV * 1.0e3));
+        float const stddev = std::sqrt((weighting * energy) * massE);
+        KhiArgs A;
+        for(int d = 0; d < 3; ++d)
+        {
+            A.ppc[d] = ppc_dim[d];
+            A.globalN[d] = c->prm.grid[d] * c->prm.devices[d];
+            A.globalOff[d] = c->prm.grid[d] * c->prm.rank_pos[d];
+        }
+        A.weighting = weighting;
+        A.driftE = driftE;
+        A.driftI = driftI;
+        A.stddev = stddev;
+        A.seed = seed;
+        KL(c, 1, launchKhiInit(c->P, devOf(c, e, e.cur), devOf(c, i, i.cur), e.cellOff[e.cur], i.cellOff[i.cur], A, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        return PICSTEP_OK;
+    }
+
+    // ---- stages ---------------------------------------------------------------------------------------------------
+    int picstep_current_reset(picstep_ctx* c)
+    {
+        if(!c)
+            return PICSTEP_ERR_INVALID;
+        StageTimer t(c, 0);
+        CU(c, cudaMemsetAsync(c->fieldMem[PICSTEP_FIELD_J], 0, sizeof(float) * 3 * c->P.vol, c->stream));
+        c->launches += 1;
+        return PICSTEP_OK;
+    }
+
+    int picstep_push(picstep_ctx* c, int32_t sp, uint32_t)
+    {
+        if(!c || sp < 0 || sp >= int(c->species.size()))
+            return PICSTEP_ERR_INVALID;
+        StageTimer t(c, 1);
+        SpeciesHost& s = c->species[sp];
+        if(s.capacity == 0)
+            return PICSTEP_OK;
+        KL(c, 1, launchPush(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], s.cellCnt, s.key, c->stream));
+        return PICSTEP_OK;
+    }
+
+    int picstep_migrate(picstep_ctx* c, int32_t sp)
+    {
+        if(!c || sp < 0 || sp >= int(c->species.size()))
+            return PICSTEP_ERR_INVALID;
+        StageTimer t(c, 2);
+        SpeciesHost& s = c->species[sp];
+        if(s.capacity == 0)
+            return PICSTEP_OK;
+        uint32_t nRecLo = 0, nRecHi = 0;
+        if(c->P.split_axis >= 0 && c->nranks > 1)
+        {
+            if(!c->comm)
+                return fail(c, PICSTEP_ERR_COMM, "devices > 1 but picstep_comm_init was not called");
+            CU(c, cudaMemsetAsync(s.sendCnt, 0, sizeof(uint32_t) * 2, c->stream));
+            KL(c, 1, launchPackLeavers(c->P, devOf(c, s, s.cur), s.key, s.cellOff[s.cur], s.sendLo, s.sendHi, s.sendCnt, s.capRec, c->flags + 2, c->stream));
+            // counts first (fixed-size header), so receive buffers can never overflow silently
+            CU(c, cudaMemcpyAsync(c->hostPinned, s.sendCnt, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+            uint32_t* cntDev = s.sendCnt; // reuse: [0],[1] send counts; receive counts land in scSum[0..1] scratch
+            int rc = commSendRecv(c->comm, cntDev, sizeof(uint32_t), s.scSum, sizeof(uint32_t), c->rankLo, cntDev + 1, sizeof(uint32_t), s.scSum + 1, sizeof(uint32_t), c->rankHi, c->stream, c->err);
+            if(rc)
+                return PICSTEP_ERR_COMM;
+            CU(c, cudaMemcpyAsync(c->hostPinned + 2, s.scSum, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            uint32_t const nSendLo = c->rankLo >= 0 ? c->hostPinned[0] : 0u, nSendHi = c->rankHi >= 0 ? c->hostPinned[1] : 0u;
+            nRecLo = c->rankLo >= 0 ? c->hostPinned[2] : 0u;
+            nRecHi = c->rankHi >= 0 ? c->hostPinned[3] : 0u;
+            if(nSendLo > s.capRec || nSendHi > s.capRec || nRecLo > s.capRec || nRecHi > s.capRec)
+                return fail(c, PICSTEP_ERR_CAPACITY, "migration record buffer overflow");
+            rc = commSendRecv(c->comm, s.sendLo, sizeof(MigRecord) * nSendLo, s.recvLo, sizeof(MigRecord) * nRecLo, c->rankLo, s.sendHi, sizeof(MigRecord) * nSendHi, s.recvHi, sizeof(MigRecord) * nRecHi, c->rankHi, c->stream, c->err);
+            if(rc)
+                return PICSTEP_ERR_COMM;
+        }
+        return resortSpecies(c, s, nRecLo, nRecHi);
+    }
+
+    int picstep_field_exchange(picstep_ctx* c, int32_t f)
+    {
+        if(!c || f < 0 || f > 2)
+            return PICSTEP_ERR_INVALID;
+        return exchangeField(c, f);
+    }
+
+    int picstep_field_update_before_current(picstep_ctx* c, uint32_t)
+    {
+        if(!c)
+            return PICSTEP_ERR_INVALID;
+        StageTimer t(c, 3);
+        Field3 E = fieldOf(c, PICSTEP_FIELD_E), B = fieldOf(c, PICSTEP_FIELD_B);
+        KL(c, 1, launchUpdateBHalf(c->prm.field_solver, c->P, c->lehe, E, B, c->stream)); // updateBSecondHalf
+        int rc = exchangeField(c, PICSTEP_FIELD_B);
+        if(rc)
+            return rc;
+        KL(c, 1, launchUpdateE(c->P, c->lehe, E, B, c->stream));
+        return PICSTEP_OK;
+    }
+
+    int picstep_deposit(picstep_ctx* c, int32_t sp)
+    {
+        if(!c || sp < 0 || sp >= int(c->species.size()))
+            return PICSTEP_ERR_INVALID;
+        StageTimer t(c, 4);
+        SpeciesHost& s = c->species[sp];
+        if(s.capacity == 0)
+            return PICSTEP_OK;
+        KL(c, 1, launchDeposit(c->prm.shape, c->prm.current_solver, (c->prm.flags & 1) != 0, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
+        return PICSTEP_OK;
+    }
+
+    int picstep_add_current(picstep_ctx* c)
+    {
+        if(!c)
+            return PICSTEP_ERR_INVALID;
+        StageTimer t(c, 5);
+        int rc = exchangeField(c, PICSTEP_FIELD_J);
+        if(rc)
+            return rc;
+        KL(c, 1, launchAddCurrent(c->P, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_J), c->stream));
+        return PICSTEP_OK;
+    }
+
+    int picstep_field_update_after_current(picstep_ctx* c, uint32_t)
+    {
+        if(!c)
+            return PICSTEP_ERR_INVALID;
+        StageTimer t(c, 6);
+        Field3 E = fieldOf(c, PICSTEP_FIELD_E), B = fieldOf(c, PICSTEP_FIELD_B);
+        int rc = exchangeField(c, PICSTEP_FIELD_E);
+        if(rc)
+            return rc;
+        KL(c, 1, launchUpdateBHalf(c->prm.field_solver, c->P, c->lehe, E, B, c->stream)); // updateBFirstHalf
+        return exchangeField(c, PICSTEP_FIELD_B);
+    }
+
+    int picstep_step(picstep_ctx* c, uint32_t first, uint32_t n)
+    {
+        if(!c)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        int const ns = int(c->species.size());
+        for(uint32_t it = 0; it < n; ++it)
+        {
+            uint32_t const step = first + it;
+            int rc = picstep_current_reset(c);
+            for(int s = 0; s < ns && !rc; ++s)
+            {
+                rc = picstep_push(c, s, step);
+                if(!rc)
+                    rc = picstep_migrate(c, s);
+            }
+            if(!rc)
+                rc = picstep_field_update_before_current(c, step);
+            for(int s = 0; s < ns && !rc; ++s)
+                rc = picstep_deposit(c, s);
+            if(!rc)
+                rc = picstep_add_current(c);
+            if(!rc)
+                rc = picstep_field_update_after_current(c, step);
+            if(rc)
+                return rc;
+        }
+        return PICSTEP_OK;
+    }
+
+    int picstep_step_host(picstep_ctx* c, uint32_t step, float* E, float* B, int32_t nSpecies, const int64_t* n, const float* const* pos, const float* const* mom, const float* const* w, const int32_t* const* cell, double* energies4)
+    {
+        if(!c || !E || !B || nSpecies != int(c->species.size()))
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        size_t const fbytes = sizeof(float) * 3 * c->P.vol;
+        CU(c, cudaMemcpyAsync(c->fieldMem[PICSTEP_FIELD_E], E, fbytes, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->fieldMem[PICSTEP_FIELD_B], B, fbytes, cudaMemcpyHostToDevice, c->stream));
+        for(int s = 0; s < nSpecies; ++s)
+        {
+            int const rc = uploadAsync(c, s, n[s], pos[s], mom[s], w[s], cell[s]);
+            if(rc)
+                return rc;
+        }
+        int rc = picstep_step(c, step, 1);
+        if(rc)
+            return rc;
+        CU(c, cudaMemcpyAsync(E, c->fieldMem[PICSTEP_FIELD_E], fbytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(B, c->fieldMem[PICSTEP_FIELD_B], fbytes, cudaMemcpyDeviceToHost, c->stream));
+        if(energies4)
+        {
+            rc = picstep_reduce(c, PICSTEP_REDUCE_FIELD_ENERGY, 0, energies4);
+            double pe[2] = {0, 0}, acc[2] = {0, 0};
+            for(int s = 0; s < nSpecies && !rc; ++s)
+            {
+                rc = picstep_reduce(c, PICSTEP_REDUCE_PARTICLE_ENERGY, s, pe);
+                acc[0] += pe[0];
+                acc[1] += pe[1];
+            }
+            energies4[2] = acc[0];
+            energies4[3] = acc[1];
+            if(rc)
+                return rc;
+        }
+        return checkFlags(c);
+    }
+
+    int picstep_sync(picstep_ctx* c)
+    {
+        if(!c)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        return checkFlags(c);
+    }
+
+    int picstep_reduce(picstep_ctx* c, int32_t what, int32_t sp, double* out)
+    {
+        if(!c || !out)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        DevParams const& P = c->P;
+        double const V = double(P.cell[0]) * double(P.cell[1]) * double(P.cell[2]);
+        if(what == PICSTEP_REDUCE_FIELD_ENERGY)
+        {
+            CU(c, cudaMemsetAsync(c->redBuf, 0, sizeof(double) * 2, c->stream));
+            KL(c, 1, launchFieldEnergy(P, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), c->redBuf, c->stream));
+            CU(c, cudaMemcpyAsync(c->hostPinned, c->redBuf, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            double const* r = reinterpret_cast<double const*>(c->hostPinned);
+            out[0] = r[0] * (0.5 / double(P.mue0) * V);
+            out[1] = r[1] * (double(P.eps0) * V * 0.5);
+            return PICSTEP_OK;
+        }
+        if(sp < 0 || sp >= int(c->species.size()))
+            if(what != PICSTEP_REDUCE_GAUSS)
+                return PICSTEP_ERR_INVALID;
+        if(what == PICSTEP_REDUCE_PARTICLE_ENERGY)
+        {
+            SpeciesHost& s = c->species[sp];
+            CU(c, cudaMemsetAsync(c->redBuf, 0, sizeof(double) * 2, c->stream));
+            if(s.capacity)
+                KL(c, 1, launchParticleEnergy(P, devOf(c, s, s.cur), s.nDev + s.cur, c->redBuf, c->stream));
+            CU(c, cudaMemcpyAsync(c->hostPinned, c->redBuf, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            double const* r = reinterpret_cast<double const*>(c->hostPinned);
+            out[0] = r[0];
+            out[1] = r[1];
+            return PICSTEP_OK;
+        }
+        if(what == PICSTEP_REDUCE_PARTICLE_COUNT)
+        {
+            int64_t n = 0;
+            int rc = picstep_particles_count(c, sp, &n);
+            out[0] = double(n);
+            return rc;
+        }
+        if(what == PICSTEP_REDUCE_GAUSS)
+        {
+            if(!c->rho)
+                CU(c, cudaMalloc(&c->rho, sizeof(float) * 3 * P.vol));
+            CU(c, cudaMemsetAsync(c->rho, 0, sizeof(float) * 3 * P.vol, c->stream));
+            for(auto& s : c->species)
+                if(s.capacity)
+                    KL(c, 1, launchChargeDensity(c->prm.shape, P, devOf(c, s, s.cur), s.cellOff[s.cur], c->rho, c->stream));
+            // guard reduction of rho with the J machinery: temporarily view rho as a 3-component field whose
+            // components 1,2 are zero (FieldTmp::asyncCommunication in the reference)
+            float* saved = c->fieldMem[PICSTEP_FIELD_J];
+            c->fieldMem[PICSTEP_FIELD_J] = c->rho;
+            int rc = exchangeField(c, PICSTEP_FIELD_J);
+            c->fieldMem[PICSTEP_FIELD_J] = saved;
+            if(rc)
+                return rc;
+            CU(c, cudaMemsetAsync(c->flags + 3, 0, sizeof(int), c->stream));
+            KL(c, 1, launchGaussResidual(P, fieldOf(c, PICSTEP_FIELD_E), c->rho, c->flags + 3, c->stream));
+            CU(c, cudaMemcpyAsync(c->hostPinned, c->flags + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            float mx;
+            std::memcpy(&mx, c->hostPinned, sizeof(float));
+            out[0] = double(mx * (P.cell[0] * P.cell[1] * P.cell[2]));
+            return PICSTEP_OK;
+        }
+        return PICSTEP_ERR_INVALID;
+    }
+
+    // ---- parity hook: gather only -------------------------------------------------------------------------------
+    // out[6][n]: E.x,E.y,E.z,B.x,B.y,B.z at the particles, frame-run order (not part of the reference surface;
+    // exported for the FieldToParticleInterpolation parity test)
+    int picstep_debug_gather(picstep_ctx* c, int32_t sp, int64_t capacity, float* out)
+    {
+        if(!c || sp < 0 || sp >= int(c->species.size()) || !out)
+            return PICSTEP_ERR_INVALID;
+        int64_t n = 0;
+        int rc = picstep_particles_count(c, sp, &n);
+        if(rc)
+            return rc;
+        if(n > capacity)
+            return fail(c, PICSTEP_ERR_CAPACITY, "gather buffer too small");
+        SpeciesHost& s = c->species[sp];
+        float* tmp = nullptr;
+        CU(c, cudaMalloc(&tmp, sizeof(float) * 6 * std::max<int64_t>(n, 1)));
+        KL(c, 1, launchGather(c->prm.shape, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], tmp, n, c->stream));
+        for(int k = 0; k < 6; ++k)
+            CU(c, cudaMemcpyAsync(out + k * capacity, tmp + k * n, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(tmp);
+        return PICSTEP_OK;
+    }
+
+    // ---- multi GPU ------------------------------------------------------------------------------------------------
+    int picstep_comm_unique_id(void* id128)
+    {
+        std::string err;
+        int const rc = commUniqueId(id128, err);
+        if(rc)
+            g_createErr = err;
+        return rc ? PICSTEP_ERR_COMM : PICSTEP_OK;
+    }
+
+    int picstep_comm_init(picstep_ctx* c, const void* id128, int32_t rank, int32_t nranks)
+    {
+        if(!c || !id128)
+            return PICSTEP_ERR_INVALID;
+        if(nranks != c->nranks || rank != c->rank)
+            return fail(c, PICSTEP_ERR_INVALID, "rank / nranks do not match devices and rank_pos of the context");
+        CU(c, cudaSetDevice(c->device));
+        int const rc = commInit(&c->comm, id128, rank, nranks, c->err);
+        return rc ? PICSTEP_ERR_COMM : PICSTEP_OK;
+    }
+
+    // ---- measurement ----------------------------------------------------------------------------------------------
+    int picstep_launch_count(picstep_ctx* c, int64_t* n)
+    {
+        if(!c || !n)
+            return PICSTEP_ERR_INVALID;
+        *n = c->launches;
+        return PICSTEP_OK;
+    }
+
+    int picstep_stage_times(picstep_ctx* c, int32_t enable, float* ms7)
+    {
+        if(!c)
+            return PICSTEP_ERR_INVALID;
+        if(ms7)
+            for(int i = 0; i < NSTAGE; ++i)
+                ms7[i] = c->stageMs[i];
+        for(int i = 0; i < NSTAGE; ++i)
+            c->stageMs[i] = 0;
+        c->timing = enable != 0;
+        return PICSTEP_OK;
+    }
+
+    int picstep_stream(picstep_ctx* c, void** stream)
+    {
+        if(!c || !stream)
+            return PICSTEP_ERR_INVALID;
+        *stream = c->stream;
+        return PICSTEP_OK;
+    }
+}

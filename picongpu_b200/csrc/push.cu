@@ -1,0 +1,432 @@
+// push.cu — gather + push + move (reference kernel K1: KernelMoveAndMarkParticles,
+// include/picongpu/particles/Particles.kernel:170-316).
+//
+// One CTA per supercell.  The six E/B component tiles (supercell + interpolation margins) are staged in shared
+// memory as SoA planes; every thread then owns particles of the supercell's frame run (contiguous, cell sorted,
+// coalesced SoA loads), interpolates E and B on the Yee-staggered positions, applies Boris/Vay in registers,
+// moves the particle and emits its re-sort key.  The per-destination-cell histogram for the re-sort is
+// accumulated in shared memory and flushed with one global atomic per touched cell.
+#include "common.cuh"
+#include "shapes.cuh"
+
+namespace picstep
+{
+    // Yee stagger (include/picongpu/fields/YeeCell.hpp:70-130); component c of E sits at +0.5 along c,
+    // component c of B at +0.5 along the two other axes.
+    __device__ __forceinline__ float stagE(int comp, int d)
+    {
+        return comp == d ? 0.5f : 0.0f;
+    }
+    __device__ __forceinline__ float stagB(int comp, int d)
+    {
+        return comp == d ? 0.0f : 0.5f;
+    }
+
+    template<int SHAPE>
+    struct Tile
+    {
+        static constexpr int LO = GatherMargin<SHAPE>::LO, UP = GatherMargin<SHAPE>::UP;
+        static constexpr int TX = SCX + LO + UP, TY = SCY + LO + UP, TZ = SCZ + LO + UP;
+        // odd row pitch keeps the y/z neighbours of a cell on different banks
+        static constexpr int PX = (TX % 2 == 0) ? TX + 1 : TX;
+        static constexpr int TV = PX * TY * TZ;
+    };
+
+    /** Interpolate one field component to the particle (FieldToParticleInterpolation.hpp:97-124 +
+     * ShiftCoordinateSystem.hpp:54-79 + AssignedTrilinearInterpolation.hpp:54-86; x innermost). */
+    template<int SHAPE, bool IS_B>
+    __device__ __forceinline__ float gatherComp(float const* __restrict__ t, int comp, int lx, int ly, int lz, float px, float py, float pz)
+    {
+        using S = Shape<SHAPE>;
+        using T = Tile<SHAPE>;
+        constexpr bool even = (S::SUPP % 2) == 0;
+        constexpr int begin = -S::SUPP / 2 + (S::SUPP + 1) % 2;
+        float sx[S::SUPP], sy[S::SUPP], sz[S::SUPP];
+        int base;
+        {
+            float const p[3] = {px, py, pz};
+            int const l[3] = {lx, ly, lz};
+            int sh[3];
+            float q[3];
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+            {
+                float const fp = IS_B ? stagB(comp, d) : stagE(comp, d);
+                float const v = p[d] - fp - 0.5f;
+                if constexpr(even)
+                    sh[d] = v >= -0.5f ? 0 : -1;
+                else
+                    sh[d] = v >= 0.0f ? 1 : 0;
+                q[d] = v - float(sh[d]) + 0.5f;
+                sh[d] += l[d] + T::LO + begin;
+            }
+            S::on(q[0], sx);
+            S::on(q[1], sy);
+            S::on(q[2], sz);
+            base = (sh[2] * T::TY + sh[1]) * T::PX + sh[0];
+        }
+        float rz = 0.0f;
+#pragma unroll
+        for(int z = 0; z < S::SUPP; ++z)
+        {
+            float ry = 0.0f;
+#pragma unroll
+            for(int y = 0; y < S::SUPP; ++y)
+            {
+                float rx = 0.0f;
+#pragma unroll
+                for(int x = 0; x < S::SUPP; ++x)
+                    rx += t[base + (z * T::TY + y) * T::PX + x] * sx[x];
+                ry += rx * sy[y];
+            }
+            rz += ry * sz[z];
+        }
+        return rz;
+    }
+
+    __device__ __forceinline__ float norm2(float x, float y, float z)
+    {
+        float t = x * x;
+        t += y * y;
+        t += z * z;
+        return t;
+    }
+
+    // Gamma.hpp:30-38
+    __device__ __forceinline__ float gammaOf(float c, float ux, float uy, float uz, float mass)
+    {
+        float const c2 = c * c;
+        float const r = 1.0f / (mass * mass * c2);
+        return sqrtf(1.0f + norm2(ux, uy, uz) * r);
+    }
+
+    // Velocity.hpp:28-38: v = p * rsqrt(m^2 + p^2/c^2)
+    __device__ __forceinline__ void velocityOf(float rc2, float mass, float ux, float uy, float uz, float& vx, float& vy, float& vz)
+    {
+        float const t = ps_rsqrt(mass * mass + norm2(ux, uy, uz) * rc2);
+        vx = t * ux;
+        vy = t * uy;
+        vz = t * uz;
+    }
+
+    // particlePusherBoris.hpp:42-91
+    __device__ __forceinline__ void boris(DevParams const& P, float mass, float charge, float const E[3], float const B[3], float u[3])
+    {
+        float const QoM = charge / mass;
+        float const dt = P.dt;
+        float m[3], t[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            m[d] = u[d] + 0.5f * charge * E[d] * dt;
+        float const gr = 1.0f / gammaOf(P.c, m[0], m[1], m[2], mass);
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            t[d] = 0.5f * QoM * B[d] * gr * dt;
+        float const sf = 1.0f / (1.0f + norm2(t[0], t[1], t[2]));
+        float s[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            s[d] = 2.0f * t[d] * sf;
+        float pr[3];
+        pr[0] = m[0] + (m[1] * t[2] - m[2] * t[1]);
+        pr[1] = m[1] + (m[2] * t[0] - m[0] * t[2]);
+        pr[2] = m[2] + (m[0] * t[1] - m[1] * t[0]);
+        float pl[3];
+        pl[0] = m[0] + (pr[1] * s[2] - pr[2] * s[1]);
+        pl[1] = m[1] + (pr[2] * s[0] - pr[0] * s[2]);
+        pl[2] = m[2] + (pr[0] * s[1] - pr[1] * s[0]);
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            u[d] = pl[d] + 0.5f * charge * E[d] * dt;
+    }
+
+    // particlePusherVay.hpp:43-112 (sqrt section in fp64: sqrt_Vay = precision64Bit, param/pusher.param:62)
+    __device__ __forceinline__ void vay(DevParams const& P, float rc2, float mass, float charge, float const E[3], float const B[3], float u[3])
+    {
+        float const factor = float(0.5 * double(charge) * double(P.dt));
+        float v0[3];
+        velocityOf(rc2, mass, u[0], u[1], u[2], v0[0], v0[1], v0[2]);
+        float cr[3];
+        cr[0] = v0[1] * B[2] - v0[2] * B[1];
+        cr[1] = v0[2] * B[0] - v0[0] * B[2];
+        cr[2] = v0[0] * B[1] - v0[1] * B[0];
+        float mp[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+        {
+            float const m0 = u[d] + factor * (E[d] + cr[d]);
+            mp[d] = m0 + factor * E[d];
+        }
+        float const gp = gammaOf(P.c, mp[0], mp[1], mp[2], mass);
+        double tau[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            tau[d] = double(factor / mass * B[d]);
+        double dpt = double(mp[0]) * tau[0];
+        dpt += double(mp[1]) * tau[1];
+        dpt += double(mp[2]) * tau[2];
+        double const ustar = dpt / double(P.c * mass);
+        double tau2 = tau[0] * tau[0];
+        tau2 += tau[1] * tau[1];
+        tau2 += tau[2] * tau[2];
+        double const sigma = double(gp * gp) - tau2;
+        double const gplus = sqrt(0.5 * (sigma + sqrt(sigma * sigma + 4.0 * (tau2 + ustar * ustar))));
+        float t[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            t[d] = float(tau[d] * (1.0 / gplus));
+        float const s = 1.0f / (1.0f + norm2(t[0], t[1], t[2]));
+        float dp = mp[0] * t[0];
+        dp += mp[1] * t[1];
+        dp += mp[2] * t[2];
+        cr[0] = mp[1] * t[2] - mp[2] * t[1];
+        cr[1] = mp[2] * t[0] - mp[0] * t[2];
+        cr[2] = mp[0] * t[1] - mp[1] * t[0];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            u[d] = s * (mp[d] + dp * t[d] + cr[d]);
+    }
+
+    template<int SHAPE, int PUSHER>
+    __global__ void __launch_bounds__(256) pushKernel(
+        DevParams P,
+        SpeciesDev S,
+        Field3 E,
+        Field3 B,
+        uint32_t const* __restrict__ cellOff,
+        uint32_t* __restrict__ cellCnt,
+        uint32_t* __restrict__ key)
+    {
+        using T = Tile<SHAPE>;
+        extern __shared__ float tile[]; // [B0,B1,B2,E0,E1,E2][TZ][TY][PX] followed by the 10x10x6 histogram
+        uint32_t* hist = reinterpret_cast<uint32_t*>(tile + 6 * T::TV);
+        constexpr int HX = SCX + 2, HY = SCY + 2, HZ = SCZ + 2, HV = HX * HY * HZ;
+
+        int const sc = blockIdx.x;
+        int const scx = sc % P.nsc[0], scy = (sc / P.nsc[0]) % P.nsc[1], scz = sc / (P.nsc[0] * P.nsc[1]);
+        uint32_t const p0 = cellOff[sc * SCVOL], p1 = cellOff[(sc + 1) * SCVOL];
+        if(p0 == p1)
+            return;
+
+        for(int i = threadIdx.x; i < HV; i += blockDim.x)
+            hist[i] = 0u;
+        // stage the tiles: rows of TX consecutive floats, coalesced per row
+        {
+            int const ox = scx * SCX + P.g[0] - T::LO, oy = scy * SCY + P.g[1] - T::LO, oz = scz * SCZ + P.g[2] - T::LO;
+            constexpr int ROWS = T::TY * T::TZ;
+            for(int i = threadIdx.x; i < 6 * ROWS * T::TX; i += blockDim.x)
+            {
+                int const x = i % T::TX;
+                int const row = (i / T::TX) % ROWS;
+                int const comp = i / (T::TX * ROWS);
+                int const y = row % T::TY, z = row / T::TY;
+                float const* src = comp < 3 ? B.c[comp] : E.c[comp - 3];
+                tile[comp * T::TV + row * T::PX + x] = __ldg(src + fidx(P, ox + x, oy + y, oz + z));
+            }
+        }
+        __syncthreads();
+
+        float const rc2 = float(1.0 / double(P.c) / double(P.c));
+        float const* tB = tile;
+        float const* tE = tile + 3 * T::TV;
+
+        for(uint32_t i = p0 + threadIdx.x; i < p1; i += blockDim.x)
+        {
+            float px = S.pos[0][i], py = S.pos[1][i], pz = S.pos[2][i];
+            float u[3] = {S.mom[0][i], S.mom[1][i], S.mom[2][i]};
+            float const w = S.w[i];
+            int const lc = S.cell[i];
+            int const lx = lc % SCX, ly = (lc / SCX) % SCY, lz = lc / (SCX * SCY);
+
+            float Bf[3], Ef[3];
+#pragma unroll
+            for(int k = 0; k < 3; ++k)
+            {
+                Bf[k] = gatherComp<SHAPE, true>(tB + k * T::TV, k, lx, ly, lz, px, py, pz);
+                Ef[k] = gatherComp<SHAPE, false>(tE + k * T::TV, k, lx, ly, lz, px, py, pz);
+            }
+            float const mass = S.mass_per_w * w;
+            float const charge = S.charge_per_w * w;
+            if constexpr(PUSHER == 0)
+                boris(P, mass, charge, Ef, Bf, u);
+            else
+                vay(P, rc2, mass, charge, Ef, Bf, u);
+            float vx, vy, vz;
+            velocityOf(rc2, mass, u[0], u[1], u[2], vx, vy, vz);
+            float np[3] = {px + (vx * P.dt) / P.cell[0], py + (vy * P.dt) / P.cell[1], pz + (vz * P.dt) / P.cell[2]};
+
+            // moveParticle (MoveParticle.hpp:48-160): wrap to [0,1) with the +-0.5 shift trick, cell crossing
+            int dir[3];
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+            {
+                float q = np[d] - 0.5f;
+                float mv = 0.0f;
+                if(q < -0.5f)
+                    mv = -1.0f;
+                if(q >= 0.5f)
+                    mv = 1.0f;
+                q -= mv;
+                np[d] = q + 0.5f;
+                dir[d] = int(mv);
+            }
+            S.pos[0][i] = np[0];
+            S.pos[1][i] = np[1];
+            S.pos[2][i] = np[2];
+            S.mom[0][i] = u[0];
+            S.mom[1][i] = u[1];
+            S.mom[2][i] = u[2];
+
+            // re-sort key: destination supercell + cell (the reference encodes this as localCellIdx + multiMask and
+            // resolves it in KernelShiftParticles, pmacc/particles/ParticlesBase.kernel:361-615)
+            int const nl[3] = {lx + dir[0], ly + dir[1], lz + dir[2]};
+            int gc[3] = {scx * SCX + nl[0], scy * SCY + nl[1], scz * SCZ + nl[2]};
+            uint32_t flag = 0u;
+            bool drop = false;
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+            {
+                if(gc[d] < 0 || gc[d] >= P.n[d])
+                {
+                    bool const up = gc[d] >= P.n[d];
+                    if(P.wrap[d])
+                        gc[d] += up ? -P.n[d] : P.n[d];
+                    else if(d == P.split_axis && (up ? P.has_upper : P.has_lower))
+                    {
+                        flag = KEY_LEAVE | (up ? KEY_UPPER : 0u);
+                        gc[d] += up ? -P.n[d] : P.n[d]; // coordinate in the receiver's local grid
+                    }
+                    else
+                        drop = true;
+                }
+            }
+            uint32_t k;
+            if(drop)
+                k = KEY_DROP;
+            else
+            {
+                int const dsc = gc[0] / SCX + P.nsc[0] * (gc[1] / SCY + P.nsc[1] * (gc[2] / SCZ));
+                int const dlc = gc[0] % SCX + SCX * (gc[1] % SCY + SCY * (gc[2] % SCZ));
+                k = uint32_t(dsc) * SCVOL + uint32_t(dlc);
+                if(flag)
+                    k |= flag;
+                else
+                    atomicAdd(&hist[(nl[0] + 1) + HX * ((nl[1] + 1) + HY * (nl[2] + 1))], 1u);
+            }
+            key[i] = k;
+        }
+        __syncthreads();
+        // flush the histogram: destination cell of histogram bin (hx,hy,hz) with the same wrap rules
+        for(int i = threadIdx.x; i < HV; i += blockDim.x)
+        {
+            uint32_t const c = hist[i];
+            if(c == 0u)
+                continue;
+            int gc[3] = {scx * SCX + i % HX - 1, scy * SCY + (i / HX) % HY - 1, scz * SCZ + i / (HX * HY) - 1};
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+            {
+                if(gc[d] < 0)
+                    gc[d] += P.n[d];
+                else if(gc[d] >= P.n[d])
+                    gc[d] -= P.n[d];
+            }
+            int const dsc = gc[0] / SCX + P.nsc[0] * (gc[1] / SCY + P.nsc[1] * (gc[2] / SCZ));
+            int const dlc = gc[0] % SCX + SCX * (gc[1] % SCY + SCY * (gc[2] % SCZ));
+            atomicAdd(&cellCnt[dsc * SCVOL + dlc], c);
+        }
+    }
+
+    template<int SHAPE>
+    size_t pushSmemBytes()
+    {
+        return sizeof(float) * 6 * Tile<SHAPE>::TV + sizeof(uint32_t) * (SCX + 2) * (SCY + 2) * (SCZ + 2);
+    }
+
+    template<int SHAPE, int PUSHER>
+    cudaError_t launchPushT(DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* key, cudaStream_t st)
+    {
+        int const nscTot = P.nsc[0] * P.nsc[1] * P.nsc[2];
+        size_t const smem = pushSmemBytes<SHAPE>();
+        cudaError_t e = cudaFuncSetAttribute(pushKernel<SHAPE, PUSHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if(e != cudaSuccess)
+            return e;
+        pushKernel<SHAPE, PUSHER><<<nscTot, 256, smem, st>>>(P, S, E, B, cellOff, cellCnt, key);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchPush(int shape, int pusher, DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* key, cudaStream_t st)
+    {
+#define PS_CASE(SH, PU)                                                                                               \
+    if(shape == SH && pusher == PU)                                                                                   \
+        return launchPushT<SH, PU>(P, S, E, B, cellOff, cellCnt, key, st);
+        PS_CASE(0, 0)
+        PS_CASE(1, 0)
+        PS_CASE(2, 0)
+        PS_CASE(3, 0)
+        PS_CASE(4, 0)
+        PS_CASE(0, 1)
+        PS_CASE(1, 1)
+        PS_CASE(2, 1)
+        PS_CASE(3, 1)
+        PS_CASE(4, 1)
+#undef PS_CASE
+        return cudaErrorInvalidValue;
+    }
+
+    // ---- gather only (parity test hook for FieldToParticleInterpolation) --------------------------------------
+    template<int SHAPE>
+    __global__ void __launch_bounds__(256) gatherKernel(DevParams P, SpeciesDev S, Field3 E, Field3 B, uint32_t const* __restrict__ cellOff, float* __restrict__ out, long long np)
+    {
+        using T = Tile<SHAPE>;
+        extern __shared__ float tile[];
+        int const sc = blockIdx.x;
+        int const scx = sc % P.nsc[0], scy = (sc / P.nsc[0]) % P.nsc[1], scz = sc / (P.nsc[0] * P.nsc[1]);
+        uint32_t const p0 = cellOff[sc * SCVOL], p1 = cellOff[(sc + 1) * SCVOL];
+        if(p0 == p1)
+            return;
+        int const ox = scx * SCX + P.g[0] - T::LO, oy = scy * SCY + P.g[1] - T::LO, oz = scz * SCZ + P.g[2] - T::LO;
+        constexpr int ROWS = T::TY * T::TZ;
+        for(int i = threadIdx.x; i < 6 * ROWS * T::TX; i += blockDim.x)
+        {
+            int const x = i % T::TX;
+            int const row = (i / T::TX) % ROWS;
+            int const comp = i / (T::TX * ROWS);
+            float const* src = comp < 3 ? B.c[comp] : E.c[comp - 3];
+            tile[comp * T::TV + row * T::PX + x] = __ldg(src + fidx(P, ox + x, oy + row % T::TY, oz + row / T::TY));
+        }
+        __syncthreads();
+        for(uint32_t i = p0 + threadIdx.x; i < p1; i += blockDim.x)
+        {
+            float const px = S.pos[0][i], py = S.pos[1][i], pz = S.pos[2][i];
+            int const lc = S.cell[i];
+            int const lx = lc % SCX, ly = (lc / SCX) % SCY, lz = lc / (SCX * SCY);
+#pragma unroll
+            for(int k = 0; k < 3; ++k)
+            {
+                out[(long long) k * np + i] = gatherComp<SHAPE, false>(tile + (3 + k) * T::TV, k, lx, ly, lz, px, py, pz);
+                out[(long long) (3 + k) * np + i] = gatherComp<SHAPE, true>(tile + k * T::TV, k, lx, ly, lz, px, py, pz);
+            }
+        }
+    }
+
+    cudaError_t launchGather(int shape, DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, uint32_t const* cellOff, float* out, long long np, cudaStream_t st)
+    {
+        int const nscTot = P.nsc[0] * P.nsc[1] * P.nsc[2];
+#define PS_CASE(SH)                                                                                                   \
+    if(shape == SH)                                                                                                   \
+    {                                                                                                                 \
+        size_t const smem = sizeof(float) * 6 * Tile<SH>::TV;                                                         \
+        cudaFuncSetAttribute(gatherKernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));               \
+        gatherKernel<SH><<<nscTot, 256, smem, st>>>(P, S, E, B, cellOff, out, np);                                    \
+        return cudaGetLastError();                                                                                    \
+    }
+        PS_CASE(0)
+        PS_CASE(1)
+        PS_CASE(2)
+        PS_CASE(3)
+        PS_CASE(4)
+#undef PS_CASE
+        return cudaErrorInvalidValue;
+    }
+} // namespace picstep
