@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the PIC step (BASELINE.json: macro-particle updates/s and ms/PIC step).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (libpicstep.so, device resident + e2e)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (restated oracle, OpenMP)
+
+Workload (config.workload): KelvinHelmholtz 3D, 256^3 cells per GPU, 25 electrons + 25 ions per cell, TSC / Boris /
+Esirkepov / Yee, periodic, weak-scaled in y (`-d 1 N 1`) like share/picongpu/examples/KelvinHelmholtz/etc/picongpu/
+8_bench.cfg.  One "step" is one full PIC step (current reset, push + re-sort/migration of both species, field
+update, deposition, J reduction, field update).  One macro-particle update = gather + push + move + deposit of one
+macro particle for one step.  Inputs are synthetic (device-side KHI generator, Philox seed 42).
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from picongpu_b200 import param as prm  # noqa: E402
+
+# algorithmic bytes
+BYTES_PER_UPDATE = 54.0  # read 30 B + write 24 B per macro-particle update (fused gather+push+move+deposit)
+BYTES_PER_CELL = 168.0  # E,B gather 24 + J 36 + 2x B-half 72 + E update 36
+# per launch of the two particle kernels
+PUSH_BYTES_PER_PARTICLE = 30.0 + 24.0 + 4.0  # read pos,mom,w,cell; write pos,mom; write re-sort key
+DEPOSIT_BYTES_PER_PARTICLE = 30.0  # read pos,mom,w,cell
+DEPOSIT_BYTES_PER_CELL = 24.0  # J read-modify-write, 3 components
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_name(grid, ppc, n):
+    return "KelvinHelmholtz3D_%dx%dx%d_per_gpu_%d+%dppc_TSC_Boris_Esirkepov_Yee_periodic_d1x%dx1" % (grid[0], grid[1], grid[2], ppc, ppc, n)
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm restated (oracle/picoracle.cpp), OpenMP over all host cores
+# -------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(steps, warmup, grid=(64, 64, 64)):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    from oracle import picoracle
+
+    p = prm.khi_params(grid=grid)
+    o, e, i = util.khi_ic(picoracle, p)
+    E, B, J = o.field(), o.field(), o.field()
+    npart = 2 * e["w"].shape[0]
+    for _ in range(warmup):
+        o.step(E, B, J, [e, i])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step(E, B, J, [e, i])
+    dt = (time.perf_counter() - t0) / steps
+    return npart / dt, dt * 1e3, o.L.orc_num_threads(), npart
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 3))
+    rate, ms, cores, npart = cpu_oracle_rate(steps, warm)
+    sample = "KelvinHelmholtz 64x64x64, 25+25 ppc (%d macro particles), %d timed steps of the restated reference step" % (npart, steps)
+    line = {
+        "impl": "reference",
+        "metric": "macro_particle_updates_per_s",
+        "value": rate,
+        "unit": "updates/s",
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": warm,
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.grid, args.ppc, args.gpus), "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "reference binary not buildable here (needs Boost+MPI); OpenMP restatement of the same arithmetic"},
+        "e2e": {"value": rate, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from picongpu_b200 import picstep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=dev)
+        try:
+            import nvidia.nccl as _n
+
+            os.environ.setdefault("PICSTEP_NCCL_LIB", os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so.2"))
+        except Exception:
+            pass
+
+    grid = tuple(args.grid)
+    p = prm.khi_params(grid=grid, devices=(1, world, 1), rank_pos=(0, rank, 0))
+    sim = picstep.Simulation(p, device=local, exact=False)
+    if world > 1:
+        if rank == 0:
+            uid = sim.comm_unique_id()
+        else:
+            uid = bytes(128)
+        t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        sim.comm_init(bytes(t.cpu().tolist()), rank, world)
+    ppc_dim = {25: (5, 5, 1), 16: (4, 4, 1), 9: (3, 3, 1), 8: (2, 2, 2), 4: (2, 2, 1), 1: (1, 1, 1)}[args.ppc]
+    sim.init_khi(ppc_dim=ppc_dim)
+    ncell = grid[0] * grid[1] * grid[2]
+    n_e, n_i = sim.particle_count("e"), sim.particle_count("i")
+    npart = n_e + n_i
+    stream = torch.cuda.ExternalStream(sim.stream(), device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+        sim.sync()
+
+    # ---- device resident: W warm-up + K timed steps ------------------------------------------------------------
+    sim.step(args.warmup)
+    barrier()
+    sim.stage_times(True)  # reset + enable asynchronous per-stage events
+    l0 = sim.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    sim.step(args.steps)
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    sampler.stop_flag = True
+    sampler.join()
+    stage = sim.stage_times(False)
+    launches = sim.launch_count() - l0
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+        cnt = torch.tensor([float(sim.particle_count("e") + sim.particle_count("i"))], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        npart_total = float(cnt.item())
+    else:
+        npart_total = float(sim.particle_count("e") + sim.particle_count("i"))
+    ms_step = ms_total / args.steps
+    value = npart_total / (ms_step * 1e-3)
+
+    # size independent properties at the benchmark size: particle conservation (periodic), Gauss residual at round-off
+    checks = {"particles_conserved": bool(abs(npart_total - npart * world) < 0.5)}
+    try:
+        gr = sim.gauss_residual()
+        checks["gauss_residual_over_cell_charge"] = gr / (25.0 * abs(p.base_charge) * p.typical_num_particles_per_macro)
+    except Exception as ex:  # pragma: no cover
+        checks["gauss_error"] = str(ex)
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------
+    peak, peak_kind = measured_peaks()
+    nspec = 2
+    per_launch = {
+        "deposit": (stage["deposit"] / (args.steps * nspec), (npart / nspec) * DEPOSIT_BYTES_PER_PARTICLE + ncell * DEPOSIT_BYTES_PER_CELL, "depositCellKernel<TSC,Esirkepov>"),
+        "push": (stage["push"] / (args.steps * nspec), (npart / nspec) * PUSH_BYTES_PER_PARTICLE + ncell * 24.0, "pushKernel<TSC,Boris>"),
+    }
+    dom = max(per_launch, key=lambda k: per_launch[k][0])
+    ms_k, bytes_k, kname = per_launch[dom]
+    achieved = bytes_k / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
+                "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": bytes_k,
+                "share_of_step": ms_k * nspec / ms_step if ms_step > 0 else None}
+    step_bytes = npart * BYTES_PER_UPDATE + ncell * BYTES_PER_CELL
+    step_roofline = {"bound": "hbm", "achieved": step_bytes / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step_per_gpu": step_bytes,
+                     "roofline_ms_per_step": step_bytes / (peak * 1e9) * 1e3}
+
+    # ---- end to end: host buffers in, host buffers out, every step ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(sim, p, args, stream, world, local, dev)
+        except Exception as ex:  # pragma: no cover
+            e2e = {"value": None, "unit": "updates/s", "error": str(ex)[:200]}
+    sim.close()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, cms, cores, cn = cpu_oracle_rate(steps=3, warmup=1)
+        cpu = {"value": rate, "unit": "updates/s", "cores": cores, "kind": "port",
+               "sample": "KelvinHelmholtz 64x64x64, 25+25 ppc (%d macro particles), 3 timed steps, %.0f ms/step" % (cn, cms)}
+
+    if rank == 0:
+        line = {
+            "metric": "macro_particle_updates_per_s",
+            "value": value,
+            "unit": "updates/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(grid, args.ppc, world), "macro_particles_per_gpu": npart,
+                       "cells_per_gpu": ncell, "l2_policy": "inputs (%.1f GB of particle data per GPU) are far larger than the 126 MB L2" % (npart * 30 / 1e9),
+                       "parallelism": "domain decomposition 1x%dx1" % world},
+            "updates_per_s_per_gpu": value / world,
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "roofline": roofline,
+            "step_roofline": step_roofline,
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "checks": checks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(sim, p, args, stream, world, local, dev):
+    """Same step through picstep_step_host: pinned host state -> H2D -> step -> D2H of E,B + energies, every step."""
+    import torch
+    import torch.distributed as dist
+
+    from picongpu_b200 import picstep
+
+    sp = []
+    for name in ("e", "i"):
+        pos, mom, w, cell = sim.download_particles(name)
+        arrs = []
+        for a in (pos, mom, w, cell):
+            t = torch.from_numpy(a).pin_memory()
+            arrs.append(t)
+        sp.append(arrs)
+    E = torch.from_numpy(sim.download_field(picstep.FIELD_E)).pin_memory()
+    B = torch.from_numpy(sim.download_field(picstep.FIELD_B)).pin_memory()
+    sp_np = [tuple(t.numpy() for t in arrs) for arrs in sp]
+    h2d = sum(t.numel() * t.element_size() for arrs in sp for t in arrs) + E.numel() * 4 + B.numel() * 4
+    d2h = E.numel() * 4 + B.numel() * 4 + 4 * 8
+    steps = max(1, min(args.steps, args.e2e_steps))
+    npart = sum(a[2].shape[0] for a in sp_np)
+    sim.step_host(E.numpy(), B.numpy(), sp_np)  # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(device_ids=[local])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.step_host(E.numpy(), B.numpy(), sp_np)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    if world > 1:
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    return {"value": npart * world / dt, "unit": "updates/s", "ms_per_step": dt * 1e3, "steps": steps,
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "api": "picstep_step_host (pinned host buffers -> H2D -> one PIC step -> D2H of E,B and energies)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, nargs=3, default=[256, 256, 256], help="cells per GPU")
+    ap.add_argument("--ppc", type=int, default=25, help="macro particles per cell and species")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1177,6 +1177,45 @@ extern "C"
         }
     }
 
+    /** One axis pass of the guard exchange for a single periodic rank along `axis`, spanning the full padded extent
+     * of the two other axes (the 26 exchange directions of pmacc/type/Exchange.hpp:46-54 collapse into the passes
+     * x, y, z).  add=0: guards [g-lo,g) and [g+n,g+n+up) := opposite border planes (E/B);
+     * add=1: border planes += opposite guards (J, AddExchangeToBorder.hpp:43-128). */
+    void orc_halo_axis(OrcParams const* Pp, float* F, int ncomp, int axis, int lo, int up, int add)
+    {
+        Dom const D(*Pp);
+        int const g = D.g[axis], n = D.n[axis];
+        for(int c = 0; c < ncomp; ++c)
+        {
+            f32* f = F + c * D.vol;
+            for(int z = 0; z < (axis == 2 ? 1 : D.N[2]); ++z)
+                for(int y = 0; y < (axis == 1 ? 1 : D.N[1]); ++y)
+                    for(int x = 0; x < (axis == 0 ? 1 : D.N[0]); ++x)
+                    {
+                        auto at = [&](int pl) -> f32&
+                        {
+                            int q[3] = {x, y, z};
+                            q[axis] = pl;
+                            return f[D.idx(q[0], q[1], q[2])];
+                        };
+                        if(!add)
+                        {
+                            for(int w = 0; w < lo; ++w)
+                                at(g - lo + w) = at(g + n - lo + w);
+                            for(int w = 0; w < up; ++w)
+                                at(g + n + w) = at(g + w);
+                        }
+                        else
+                        {
+                            for(int w = 0; w < lo; ++w)
+                                at(g + n - lo + w) += at(g - lo + w);
+                            for(int w = 0; w < up; ++w)
+                                at(g + w) += at(g + n + w);
+                        }
+                    }
+        }
+    }
+
     /** UpdateBHalfFunctor over CORE+BORDER: B -= curlE * 0.5 * dt (FDTDBase.kernel:115-121) */
     void orc_update_b_half(OrcParams const* Pp, float const* E, float* B)
     {

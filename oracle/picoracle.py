@@ -90,6 +90,7 @@ def lib():
     L.orc_deposit_one.argtypes = [P, f32p, i32p, f32p, f32p, C.c_float]
     L.orc_guard_copy.argtypes = [P, f32p]
     L.orc_guard_add.argtypes = [P, f32p]
+    L.orc_halo_axis.argtypes = [P, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.orc_update_b_half.argtypes = [P, f32p, f32p]
     L.orc_update_e.argtypes = [P, f32p, f32p]
     L.orc_add_current.argtypes = [P, f32p, f32p]
@@ -175,6 +176,9 @@ class Oracle:
 
     def guard_add(self, F):
         self.L.orc_guard_add(C.byref(self.p), F)
+
+    def halo_axis(self, F, axis, lo, up, add=False):
+        self.L.orc_halo_axis(C.byref(self.p), F, F.shape[0], axis, lo, up, 1 if add else 0)
 
     def update_b_half(self, E, B):
         self.L.orc_update_b_half(C.byref(self.p), E, B)

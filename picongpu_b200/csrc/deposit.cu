@@ -339,7 +339,8 @@ namespace picstep
 
         extern __shared__ float smem[];
         float* tiles = smem; // WARPS * 3 * PV warp-private tiles
-        float* recs = smem + WARPS * 3 * W::PV; // WARPS * 32 * NSEG * RECP
+        float* recs = smem + WARPS * 3 * W::PV; // WARPS * 32 * RECP
+        constexpr int CHUNK = 32 / NSEG; // particles per phase-1 pass: 32 records per warp
 
         int const sc = blockIdx.x;
         int const scx = sc % P.nsc[0], scy = (sc / P.nsc[0]) % P.nsc[1], scz = sc / (P.nsc[0] * P.nsc[1]);
@@ -352,7 +353,7 @@ namespace picstep
 
         int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         float* const myTile = tiles + warp * 3 * W::PV;
-        float* const myRecs = recs + warp * 32 * NSEG * W::RECP;
+        float* const myRecs = recs + warp * 32 * W::RECP;
         float const rc2 = float(1.0 / double(P.c) / double(P.c));
         float const vol = P.cell[0] * P.cell[1] * P.cell[2];
 
@@ -384,13 +385,13 @@ namespace picstep
                     for(int k = 0; k < WN - 1; ++k)
                         accX[q][k] = accY[q][k] = accZ[q][k] = 0.0f;
 
-                for(uint32_t chunk = c0; chunk < c1; chunk += 32)
+                for(uint32_t chunk = c0; chunk < c1; chunk += CHUNK)
                 {
                     uint32_t const i = chunk + lane;
-                    int const nIn = int(min(32u, c1 - chunk));
+                    int const nIn = int(min(uint32_t(CHUNK), c1 - chunk));
                     __syncwarp();
                     // ---- phase 1: lane = particle --------------------------------------------------------------
-                    if(i < c1)
+                    if(lane < CHUNK && i < c1)
                     {
                         float const pos[3] = {S.pos[0][i], S.pos[1][i], S.pos[2][i]};
                         float const ux = S.mom[0][i], uy = S.mom[1][i], uz = S.mom[2][i];
@@ -550,8 +551,7 @@ namespace picstep
         else
         {
             constexpr int WARPS = SCY;
-            constexpr int NSEG = SOLVER == 0 ? 1 : 2;
-            size_t const smem = sizeof(float) * (WARPS * 3 * Win<SHAPE>::PV + WARPS * 32 * NSEG * Win<SHAPE>::RECP);
+            size_t const smem = sizeof(float) * (WARPS * 3 * Win<SHAPE>::PV + WARPS * 32 * Win<SHAPE>::RECP);
             cudaError_t e = cudaFuncSetAttribute(depositCellKernel<SHAPE, SOLVER, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
             if(e != cudaSuccess)
                 return e;

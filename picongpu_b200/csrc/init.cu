@@ -62,7 +62,8 @@ namespace picstep
 #pragma unroll
             for(int d = 0; d < 3; ++d)
             {
-                float const p = float(ic[d]) * sp[d] + sp[d] * 0.5f;
+                // explicit roundings: identical bits with and without FMA contraction
+                float const p = __fadd_rn(__fmul_rn(float(ic[d]), sp[d]), __fmul_rn(sp[d], 0.5f));
                 E.pos[d][i] = p;
                 I.pos[d][i] = p;
             }

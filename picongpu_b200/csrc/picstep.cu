@@ -93,9 +93,16 @@ struct picstep_ctx
     // multi GPU
     Comm* comm = nullptr;
     int rank = 0, nranks = 1, rankLo = -1, rankHi = -1;
-    // stage timing
+    // stage timing: event pairs are recorded asynchronously and resolved when picstep_stage_times() is called,
+    // so enabling it does not add host synchronisation to the step
+    struct Span
+    {
+        int stage;
+        cudaEvent_t a, b;
+    };
     bool timing = false;
-    cudaEvent_t ev[2] = {};
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> evPool;
     float stageMs[NSTAGE] = {};
 };
 
@@ -227,24 +234,39 @@ namespace
         }
     }
 
+    cudaEvent_t takeEvent(picstep_ctx* c)
+    {
+        if(!c->evPool.empty())
+        {
+            cudaEvent_t e = c->evPool.back();
+            c->evPool.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+
     struct StageTimer
     {
         picstep_ctx* c;
-        int stage;
-        StageTimer(picstep_ctx* ctx, int st) : c(ctx), stage(st)
-        {
-            if(c->timing)
-                cudaEventRecord(c->ev[0], c->stream);
-        }
-        ~StageTimer()
+        picstep_ctx::Span sp{};
+        StageTimer(picstep_ctx* ctx, int st) : c(ctx)
         {
             if(c->timing)
             {
-                cudaEventRecord(c->ev[1], c->stream);
-                cudaEventSynchronize(c->ev[1]);
-                float ms = 0;
-                cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-                c->stageMs[stage] += ms;
+                sp.stage = st;
+                sp.a = takeEvent(c);
+                sp.b = takeEvent(c);
+                cudaEventRecord(sp.a, c->stream);
+            }
+        }
+        ~StageTimer()
+        {
+            if(c->timing && sp.a)
+            {
+                cudaEventRecord(sp.b, c->stream);
+                c->spans.push_back(sp);
             }
         }
     };
@@ -476,6 +498,8 @@ extern "C"
             {
                 ++nsplit;
                 split = d;
+                if(p->grid[d] / p->supercell[d] < 2)
+                    return fail(nullptr, PICSTEP_ERR_INVALID, "at least 2 supercells per rank along the split axis");
             }
         }
         if(nsplit > 1)
@@ -537,8 +561,6 @@ extern "C"
         CUC(cudaMalloc(&c->flags, sizeof(int) * 4));
         CUC(cudaMemsetAsync(c->flags, 0, sizeof(int) * 4, c->stream));
         CUC(cudaMallocHost(&c->hostPinned, sizeof(double) * 8));
-        CUC(cudaEventCreate(&c->ev[0]));
-        CUC(cudaEventCreate(&c->ev[1]));
         if(split >= 0)
         {
             long long const plane = (long long) P.N[(split == 0) ? 1 : 0] * P.N[(split == 2) ? 1 : 2] * 3;
@@ -580,10 +602,13 @@ extern "C"
         cudaFree(c->flags);
         if(c->hostPinned)
             cudaFreeHost(c->hostPinned);
-        if(c->ev[0])
-            cudaEventDestroy(c->ev[0]);
-        if(c->ev[1])
-            cudaEventDestroy(c->ev[1]);
+        for(auto& sp : c->spans)
+        {
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+        for(auto e : c->evPool)
+            cudaEventDestroy(e);
         if(c->comm)
             commDestroy(c->comm);
         if(c->stream)
@@ -1143,6 +1168,20 @@ extern "C"
     {
         if(!c)
             return PICSTEP_ERR_INVALID;
+        if(!c->spans.empty())
+        {
+            CU(c, cudaSetDevice(c->device));
+            CU(c, cudaStreamSynchronize(c->stream));
+            for(auto& sp : c->spans)
+            {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, sp.a, sp.b);
+                c->stageMs[sp.stage] += ms;
+                c->evPool.push_back(sp.a);
+                c->evPool.push_back(sp.b);
+            }
+            c->spans.clear();
+        }
         if(ms7)
             for(int i = 0; i < NSTAGE; ++i)
                 ms7[i] = c->stageMs[i];

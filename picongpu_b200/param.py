@@ -70,8 +70,8 @@ class SimParams:
         for d in range(3):
             if self.grid[d] % self.supercell[d]:
                 raise ValueError("grid must be a multiple of the supercell size (DomainAdjuster)")
-            if self.grid[d] // self.supercell[d] < 3 and self.devices[d] > 1:
-                raise ValueError("at least 3 supercells per split axis")
+            if self.grid[d] // self.supercell[d] < 2 and self.devices[d] > 1:
+                raise ValueError("at least 2 supercells per split axis")
         # unit system: simulation.unitless:420-480 (all in float_64, cast to float_X on use)
         self.unit_time = self.delta_t_si
         self.unit_speed = SPEED_OF_LIGHT_SI

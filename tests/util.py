@@ -85,3 +85,13 @@ def khi_ic(orc, p, seed=42, ppc_dim=(5, 5, 1)):
                      np.array(ppc_dim, np.int32), p.real_particles_per_cell, 1836.152672, 1.021, 0.0005, p.ev_pic, seed,
                      e["pos"], e["mom"], e["w"], e["cell"], i["pos"], i["mom"], i["w"], i["cell"])
     return o, e, i
+
+
+def khi_scales(p, steps=1, ppc=25, beta_gamma=0.2):
+    """Error scales for the KelvinHelmholtz start: electron and ion drift currents cancel down to the thermal noise,
+    so deviations are measured against the per-species current n*q*v/V (and the E it would drive in `steps` steps),
+    not against max|J_net|."""
+    V = float(np.prod(np.float64(p.cell_size)))
+    jscale = ppc * 1.0 * beta_gamma / V
+    escale = p.dt / p.eps0 * jscale * steps
+    return jscale, escale
