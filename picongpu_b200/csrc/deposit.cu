@@ -272,54 +272,150 @@ namespace picstep
     }
 
     // ------------------------------------------------------------------------------------------------------------
-    // Cell-sorted kernel: warp per cell, lane per transverse node, register accumulation
+    // Cell-sorted kernel: warp per cell, lane groups per particle, register accumulation
     // ------------------------------------------------------------------------------------------------------------
-    // Window of grid offsets, relative to the particle's (new) cell, that any trajectory ending in the cell can
-    // touch: [-LO, UP] with the current solver margins (Esirkepov.hpp:42-45), WN = LO + UP + 1 points.
+    // Window of grid offsets, relative to the particle's (new) cell, that a trajectory ending in the cell can touch:
+    //   wide   [-LO, UP]       with the current solver margins (Esirkepov.hpp:42-45), WN_W = LO + UP + 1 points;
+    //   narrow [-LO+1, UP-1]   for odd supports when start and end point both have their assignment cell at offset
+    //                          0 or +1, i.e. the particle moved less than half a cell -- the common case.
     template<int SHAPE>
     struct Win
     {
+        using S = Shape<SHAPE>;
         static constexpr int WLO = CurrentMargin<SHAPE>::LO;
         static constexpr int WN = CurrentMargin<SHAPE>::LO + CurrentMargin<SHAPE>::UP + 1;
-        // per particle(-segment) record in shared memory:
+        static constexpr bool HAS_NARROW = (S::SUPP % 2 == 1) && (WN - 2 >= 4);
+        static constexpr int WN_N = HAS_NARROW ? WN - 2 : WN;
+        static constexpr int OFF_N = HAS_NARROW ? 1 : 0;
+        // per particle(-segment) record in shared memory, laid out on the WIDE window:
         //   float2 {S0, DS} [3 axes][WN]   then   C[3][WN-1] = prefix sums of DS * (-currentSurfaceDensity)
         static constexpr int REC = 6 * WN + 3 * (WN - 1);
-        // record stride == 2 (mod 4) words: 8-byte aligned and conflict free for the 64-bit lane-strided stores
-        static constexpr int RECP = REC + ((2 - REC % 4) + 4) % 4;
+        // stride == 4 (mod 8) words: 16-byte aligned records, conflict free 128-bit lane-strided stores
+        static constexpr int RECP = REC + ((4 - REC % 8) + 8) % 8;
+        static constexpr int NREC = 33; // 32 records + one all-zero record for the tail of a pass
         // warp-private J tile: a warp owns one y-row of cells of the supercell
         static constexpr int PX = SCX + WN - 1, PY = WN, PZ = SCZ + WN - 1, PV = PX * PY * PZ;
     };
 
-    /** Phase 1 helper: S0 and DS on the WN-point window of one axis, and the scaled prefix sums of DS.
-     *  x0,x1: end points relative to their own assignment cell (on support); shift0/1: offset of that assignment
-     *  cell from the particle cell.  Window index n <-> grid offset n - WLO. */
-    template<int SHAPE>
-    __device__ __forceinline__ void windowArrays(float2* __restrict__ sd, float* __restrict__ cpre, float x0, float x1, int shift0, int shift1, float factor)
+    /** Phase 1 helper: place the FR-entry frame arrays (S0, S1) of one axis at window index n0 of a zeroed record
+     * and write the scaled prefix sums of DS for the first NC frame entries (accumulated_J recursion of
+     * Esirkepov.hpp:223-236, factored: J_k = C_k * transverse weight). */
+    template<int FR>
+    __device__ __forceinline__ void placeFrame(float2* __restrict__ sd, float* __restrict__ cpre, int n0, float const* s0, float const* s1, int nc, float factor)
     {
-        using S = Shape<SHAPE>;
-        using W = Win<SHAPE>;
-        float a0[S::SUPP], a1[S::SUPP];
-        S::on(x0, a0);
-        S::on(x1, a1);
         float run = 0.0f;
 #pragma unroll
-        for(int n = 0; n < W::WN; ++n)
+        for(int s = 0; s < FR; ++s)
         {
-            int const o = n - W::WLO;
-            int const k0 = o - shift0 - S::BEGIN, k1 = o - shift1 - S::BEGIN;
-            float v0 = 0.0f, v1 = 0.0f;
+            float const ds = s1[s] - s0[s];
+            sd[n0 + s] = make_float2(s0[s], ds);
+            run += ds;
+            if(s < nc)
+                cpre[n0 + s] = run * factor;
+        }
+    }
+
+    /** Phase 2: accumulate the records [0, nrec) of this warp into register accumulators and add them to the
+     * warp-private tile.  WN_: window width handled (wide or narrow), OFF: index offset of that window inside the
+     * wide-layout record.  Lane groups of G lanes work on one record each (PP records per pass); inside a group a
+     * lane owns the transverse nodes (a = ah*AW + j, b), j < AW, and WN_-1 prefix values along the current axis. */
+    template<int SHAPE, int WN_, int OFF>
+    __device__ __forceinline__ void accumulateAndFlush(float const* __restrict__ myRecs, int nrec, float* __restrict__ myTile, int cxl, int cz, int lane)
+    {
+        using W = Win<SHAPE>;
+        constexpr int AW = (WN_ == 6) ? 3 : 2;
+        constexpr int NA = WN_ / AW; // a-groups
+        constexpr int GUSED = NA * WN_;
+        constexpr int G = GUSED <= 8 ? 8 : (GUSED <= 16 ? 16 : 32);
+        constexpr int PP = 32 / G;
+        constexpr int NK = WN_ - 1;
+        static_assert(WN_ % AW == 0 && GUSED <= 32, "unsupported window width");
+        int const g = lane % G, slot = lane / G;
+        bool const valid = g < GUSED;
+        int const ah = valid ? g / WN_ : 0, b = valid ? g % WN_ : 0;
+        int const a0 = ah * AW;
+
+        float accX[AW][NK], accY[AW][NK], accZ[AW][NK];
 #pragma unroll
-            for(int s = 0; s < S::SUPP; ++s)
+        for(int j = 0; j < AW; ++j)
+#pragma unroll
+            for(int k = 0; k < NK; ++k)
+                accX[j][k] = accY[j][k] = accZ[j][k] = 0.0f;
+
+        for(int base = 0; base < nrec; base += PP)
+        {
+            int const r = base + slot;
+            float const* rec = myRecs + (r < nrec ? r : 32) * W::RECP; // record 32 is all zero
+            float2 const* rx = reinterpret_cast<float2 const*>(rec) + OFF;
+            float2 const* ry = rx + W::WN;
+            float2 const* rz = rx + 2 * W::WN;
+            float const* cxp = rec + 6 * W::WN + OFF;
+            float const* cyp = cxp + (W::WN - 1);
+            float const* czp = cyp + (W::WN - 1);
+            float2 const zb = rz[b], yb = ry[b];
+            // transverse weight S0i*S0j + 1/2 (DSi*S0j + S0i*DSj) + 1/3 DSi*DSj = S0i*(S0j + DSj/2) + DSi*(S0j/2 + DSj/3)
+            float const zP = zb.x + 0.5f * zb.y, zQ = 0.5f * zb.x + (1.0f / 3.0f) * zb.y;
+            float const yP = yb.x + 0.5f * yb.y, yQ = 0.5f * yb.x + (1.0f / 3.0f) * yb.y;
+            float cx[NK], cy[NK], cz_[NK];
+#pragma unroll
+            for(int k = 0; k < NK; ++k)
             {
-                v0 = (k0 == s) ? a0[s] : v0;
-                v1 = (k1 == s) ? a1[s] : v1;
+                cx[k] = cxp[k];
+                cy[k] = cyp[k];
+                cz_[k] = czp[k];
             }
-            float const ds = v1 - v0;
-            sd[n] = make_float2(v0, ds);
-            if(n < W::WN - 1)
+#pragma unroll
+            for(int j = 0; j < AW; ++j)
             {
-                run += ds; // accumulated_J recursion of Esirkepov.hpp:223-236, factored
-                cpre[n] = run * factor;
+                float2 const xa = rx[a0 + j], ya = ry[a0 + j];
+                float const xP = xa.x + 0.5f * xa.y, xQ = 0.5f * xa.x + (1.0f / 3.0f) * xa.y;
+                // Jx: (i,j) = (y,z) at node (a,b);  Jy: (z,x) at (x=a, z=b);  Jz: (x,y) at (a,b)
+                float const tX = ya.x * zP + ya.y * zQ;
+                float const tY = zb.x * xP + zb.y * xQ;
+                float const tZ = xa.x * yP + xa.y * yQ;
+#pragma unroll
+                for(int k = 0; k < NK; ++k)
+                {
+                    accX[j][k] += cx[k] * tX;
+                    accY[j][k] += cy[k] * tY;
+                    accZ[j][k] += cz_[k] * tZ;
+                }
+            }
+        }
+        // combine the PP record slots (butterfly over the slot bits of the lane id)
+#pragma unroll
+        for(int o = G; o < 32; o <<= 1)
+#pragma unroll
+            for(int j = 0; j < AW; ++j)
+#pragma unroll
+                for(int k = 0; k < NK; ++k)
+                {
+                    accX[j][k] += __shfl_xor_sync(0xffffffffu, accX[j][k], o);
+                    accY[j][k] += __shfl_xor_sync(0xffffffffu, accY[j][k], o);
+                    accZ[j][k] += __shfl_xor_sync(0xffffffffu, accZ[j][k], o);
+                }
+        // add to the warp-private tile: plain read-modify-write, no atomics (within one instruction all active lanes
+        // address distinct nodes, no other warp touches this tile); entry e is written by record slot e % PP.
+        // window index n <-> private tile coordinate (cxl + n + OFF, n + OFF, cz + n + OFF) per axis
+        if(valid)
+        {
+            int const tb = b + OFF;
+#pragma unroll
+            for(int j = 0; j < AW; ++j)
+            {
+                int const ta = a0 + j + OFF;
+#pragma unroll
+                for(int k = 0; k < NK; ++k)
+                {
+                    int const e = j * NK + k;
+                    if(e % PP == slot)
+                    {
+                        int const tk = k + OFF;
+                        myTile[(cxl + tk) + W::PX * (ta + W::PY * (cz + tb))] += accX[j][k]; // Jx: x=k, y=a, z=b
+                        myTile[W::PV + (cxl + ta) + W::PX * (tk + W::PY * (cz + tb))] += accY[j][k]; // Jy: x=a, y=k, z=b
+                        myTile[2 * W::PV + (cxl + ta) + W::PX * (tb + W::PY * (cz + tk))] += accZ[j][k]; // Jz: x=a, y=b, z=k
+                    }
+                }
             }
         }
     }
@@ -330,65 +426,43 @@ namespace picstep
         using Sh = Shape<SHAPE>;
         using T = JTile<SHAPE>;
         using W = Win<SHAPE>;
-        static_assert(WARPS == SCY, "one warp per y-row of the supercell");
+        static_assert(SCY % WARPS == 0, "a CTA owns WARPS consecutive y-rows of one supercell");
+        constexpr int PARTS = SCY / WARPS; // CTAs per supercell
         constexpr bool even = (Sh::SUPP % 2) == 0;
         constexpr int WN = W::WN;
         constexpr int NSEG = SOLVER == 0 ? 1 : 2; // EmZ: up to two on-support segments per particle
-        static_assert(WN * WN <= 64, "transverse window must fit two nodes per lane");
-        constexpr int NPL = (WN * WN + 31) / 32; // transverse nodes per lane
-
-        extern __shared__ float smem[];
-        float* tiles = smem; // WARPS * 3 * PV warp-private tiles
-        float* recs = smem + WARPS * 3 * W::PV; // WARPS * 32 * RECP
         constexpr int CHUNK = 32 / NSEG; // particles per phase-1 pass: 32 records per warp
+        constexpr int FR = SOLVER == 0 ? Sh::SUPP + 1 : Sh::SUPP; // frame entries per axis
 
-        int const sc = blockIdx.x;
+        extern __shared__ __align__(16) float smem[];
+        float* tiles = smem; // WARPS * 3 * PV warp-private tiles
+        float* recs = smem + WARPS * 3 * W::PV; // WARPS * NREC * RECP (16-byte aligned: PV*3*WARPS*4 bytes offset)
+
+        int const sc = blockIdx.x / PARTS, part = blockIdx.x % PARTS;
         int const scx = sc % P.nsc[0], scy = (sc / P.nsc[0]) % P.nsc[1], scz = sc / (P.nsc[0] * P.nsc[1]);
-        uint32_t const s0 = cellOff[sc * SCVOL], s1 = cellOff[(sc + 1) * SCVOL];
-        if(s0 == s1)
-            return;
+        int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        int const ly = part * WARPS + warp;
         for(int i = threadIdx.x; i < WARPS * 3 * W::PV; i += blockDim.x)
             tiles[i] = 0.0f;
+        float* const myTile = tiles + warp * 3 * W::PV;
+        float* const myRecs = recs + warp * W::NREC * W::RECP;
+        for(int i = lane; i < W::RECP; i += 32)
+            myRecs[32 * W::RECP + i] = 0.0f;
         __syncthreads();
 
-        int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        float* const myTile = tiles + warp * 3 * W::PV;
-        float* const myRecs = recs + warp * 32 * W::RECP;
         float const rc2 = float(1.0 / double(P.c) / double(P.c));
         float const vol = P.cell[0] * P.cell[1] * P.cell[2];
 
-        // transverse nodes owned by this lane
-        int na[NPL], nb[NPL];
-        bool nv[NPL];
-#pragma unroll
-        for(int q = 0; q < NPL; ++q)
-        {
-            int const node = lane + 32 * q;
-            nv[q] = node < WN * WN;
-            na[q] = nv[q] ? node % WN : 0;
-            nb[q] = nv[q] ? node / WN : 0;
-        }
-
-        int const ly = warp;
         for(int cz = 0; cz < SCZ; ++cz)
             for(int cxl = 0; cxl < SCX; ++cxl)
             {
                 int const lc = cxl + SCX * (ly + SCY * cz);
                 uint32_t const c0 = cellOff[sc * SCVOL + lc], c1 = cellOff[sc * SCVOL + lc + 1];
-                if(c0 == c1)
-                    continue;
-                // register accumulators: per owned transverse node WN-1 values along the current axis, 3 components
-                float accX[NPL][WN - 1], accY[NPL][WN - 1], accZ[NPL][WN - 1];
-#pragma unroll
-                for(int q = 0; q < NPL; ++q)
-#pragma unroll
-                    for(int k = 0; k < WN - 1; ++k)
-                        accX[q][k] = accY[q][k] = accZ[q][k] = 0.0f;
-
                 for(uint32_t chunk = c0; chunk < c1; chunk += CHUNK)
                 {
                     uint32_t const i = chunk + lane;
                     int const nIn = int(min(uint32_t(CHUNK), c1 - chunk));
+                    bool narrowOk = true;
                     __syncwarp();
                     // ---- phase 1: lane = particle --------------------------------------------------------------
                     if(lane < CHUNK && i < c1)
@@ -401,6 +475,13 @@ namespace picstep
                         float const t = ps_rsqrt(mass * mass + norm2d(ux, uy, uz) * rc2);
                         float const vel[3] = {t * ux, t * uy, t * uz};
                         float* rec = myRecs + lane * NSEG * W::RECP;
+                        // zero the record(s), then place the frames at their window offset
+                        {
+                            float4* z4 = reinterpret_cast<float4*>(rec);
+#pragma unroll
+                            for(int q = 0; q < NSEG * W::RECP / 4; ++q)
+                                z4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                         if constexpr(SOLVER == 0)
                         {
                             float const csd = charge * (1.0f / float(vol * P.dt));
@@ -411,20 +492,18 @@ namespace picstep
                                 float const x0 = pos[d] - dp, x1 = pos[d];
                                 int iS, iE;
                                 relay<even>(iS, iE, x0, x1);
-                                // Esirkepov shifts both points by gridShift = min(iS,iE) and evaluates the
-                                // off-support array, which is the on-support array of each point in its own
-                                // assignment cell (shapeOff): same arithmetic, same bits.
+                                // Esirkepov.hpp:84-103: both points in the frame of gridShift = min(iS,iE), off-support
+                                // arrays of SUPP+1 entries (same arithmetic, same bits as the reference)
                                 int const gs = iS < iE ? iS : iE;
                                 float const y0 = x0 - float(gs), y1 = x1 - float(gs);
+                                float s0[FR], s1[FR];
+                                shapeOff<SHAPE>(y0, gs != iS, s0);
+                                shapeOff<SHAPE>(y1, gs != iE, s1);
                                 float const f = (y0 == y1) ? 0.0f : -(csd * P.cell[d]);
-                                windowArrays<SHAPE>(
-                                    reinterpret_cast<float2*>(rec) + WN * d,
-                                    rec + 6 * WN + (WN - 1) * d,
-                                    gs != iS ? y0 - 1.0f : y0,
-                                    gs != iE ? y1 - 1.0f : y1,
-                                    iS,
-                                    iE,
-                                    f);
+                                int const leave = iS != iE ? 1 : 0;
+                                placeFrame<FR>(reinterpret_cast<float2*>(rec) + WN * d, rec + 6 * WN + (WN - 1) * d, gs + Sh::BEGIN + W::WLO, s0, s1, Sh::SUPP - 1 + leave, f);
+                                if(W::HAS_NARROW && (iS < 0 || iS > 1))
+                                    narrowOk = false;
                             }
                         }
                         else
@@ -437,6 +516,8 @@ namespace picstep
                                 float const dp = (vel[d] * P.dt) / P.cell[d];
                                 pS[d] = pos[d] - dp;
                                 rl[d] = relay<even>(sS[d], sE[d], pS[d], pos[d]);
+                                if(W::HAS_NARROW && (sS[d] < 0 || sS[d] > 1))
+                                    narrowOk = false;
                             }
                             float const cd = charge / vol;
                             bool const two = sS[0] != sE[0] || sS[1] != sE[1] || sS[2] != sE[2];
@@ -446,88 +527,44 @@ namespace picstep
                             {
                                 float const fd = -(P.cell[d] * cd / P.dt);
                                 float const a0 = pS[d] - float(sS[d]), a1 = rl[d] - float(sS[d]);
-                                windowArrays<SHAPE>(reinterpret_cast<float2*>(rec) + WN * d, rec + 6 * WN + (WN - 1) * d, a0, a1, sS[d], sS[d], (a0 == a1) ? 0.0f : fd);
+                                float s0[FR], s1[FR];
+                                Sh::on(a0, s0);
+                                Sh::on(a1, s1);
+                                placeFrame<FR>(reinterpret_cast<float2*>(rec) + WN * d, rec + 6 * WN + (WN - 1) * d, sS[d] + Sh::BEGIN + W::WLO, s0, s1, Sh::SUPP - 1, (a0 == a1) ? 0.0f : fd);
                                 float const b0 = rl[d] - float(sE[d]), b1 = pos[d] - float(sE[d]);
-                                windowArrays<SHAPE>(reinterpret_cast<float2*>(rec2) + WN * d, rec2 + 6 * WN + (WN - 1) * d, b0, b1, sE[d], sE[d], (!two || b0 == b1) ? 0.0f : fd);
+                                Sh::on(b0, s0);
+                                Sh::on(b1, s1);
+                                placeFrame<FR>(reinterpret_cast<float2*>(rec2) + WN * d, rec2 + 6 * WN + (WN - 1) * d, sE[d] + Sh::BEGIN + W::WLO, s0, s1, Sh::SUPP - 1, (!two || b0 == b1) ? 0.0f : fd);
                             }
                         }
                     }
+                    bool const allNarrow = W::HAS_NARROW && __all_sync(0xffffffffu, narrowOk);
                     __syncwarp();
-                    // ---- phase 2: lane = transverse node, loop over the particles of this chunk --------------------
-                    for(int p = 0; p < nIn * NSEG; ++p)
-                    {
-                        float const* r = myRecs + p * W::RECP;
-                        float2 const* rx = reinterpret_cast<float2 const*>(r);
-                        float2 const* ry = rx + WN;
-                        float2 const* rz = rx + 2 * WN;
-                        float cx[WN - 1], cy[WN - 1], cz_[WN - 1];
-#pragma unroll
-                        for(int k = 0; k < WN - 1; ++k)
-                        {
-                            cx[k] = r[6 * WN + k];
-                            cy[k] = r[6 * WN + (WN - 1) + k];
-                            cz_[k] = r[6 * WN + 2 * (WN - 1) + k];
-                        }
-#pragma unroll
-                        for(int q = 0; q < NPL; ++q)
-                        {
-                            int const a = na[q], b = nb[q];
-                            float2 const xa = rx[a], ya = ry[a], yb = ry[b], zb = rz[b];
-                            // transverse weights S0i*S0j + 1/2 (DSi*S0j + S0i*DSj) + 1/3 DSi*DSj, factored as
-                            // S0i*(S0j + DSj/2) + DSi*(S0j/2 + DSj/3)
-                            // Jx: (i,j) = (y,z) at node (a,b);  Jy: (z,x) at (x=a, z=b);  Jz: (x,y) at (a,b)
-                            float const zP = zb.x + 0.5f * zb.y, zQ = 0.5f * zb.x + (1.0f / 3.0f) * zb.y;
-                            float const xP = xa.x + 0.5f * xa.y, xQ = 0.5f * xa.x + (1.0f / 3.0f) * xa.y;
-                            float const yP = yb.x + 0.5f * yb.y, yQ = 0.5f * yb.x + (1.0f / 3.0f) * yb.y;
-                            float const tX = ya.x * zP + ya.y * zQ;
-                            float const tY = zb.x * xP + zb.y * xQ;
-                            float const tZ = xa.x * yP + xa.y * yQ;
-#pragma unroll
-                            for(int k = 0; k < WN - 1; ++k)
-                            {
-                                accX[q][k] += cx[k] * tX;
-                                accY[q][k] += cy[k] * tY;
-                                accZ[q][k] += cz_[k] * tZ;
-                            }
-                        }
-                    }
+                    // ---- phase 2: lane groups = records, lanes = transverse nodes, registers = current axis ----------
+                    if(allNarrow)
+                        accumulateAndFlush<SHAPE, W::WN_N, W::OFF_N>(myRecs, nIn * NSEG, myTile, cxl, cz, lane);
+                    else
+                        accumulateAndFlush<SHAPE, WN, 0>(myRecs, nIn * NSEG, myTile, cxl, cz, lane);
                 }
-                // ---- per cell: add the register window to the warp-private tile (no atomics needed: within one
-                // instruction all lanes address distinct nodes and no other warp touches this tile) ----------------
-                __syncwarp();
-#pragma unroll
-                for(int q = 0; q < NPL; ++q)
-                {
-                    if(!nv[q])
-                        continue;
-                    int const a = na[q], b = nb[q];
-#pragma unroll
-                    for(int k = 0; k < WN - 1; ++k)
-                    {
-                        // window index n <-> private tile coordinate (cxl + n, n, cz + n) per axis
-                        myTile[(cxl + k) + W::PX * (a + W::PY * (cz + b))] += accX[q][k]; // Jx: x=k, y=a, z=b
-                        myTile[W::PV + (cxl + a) + W::PX * (k + W::PY * (cz + b))] += accY[q][k]; // Jy: x=a, y=k, z=b
-                        myTile[2 * W::PV + (cxl + a) + W::PX * (b + W::PY * (cz + k))] += accZ[q][k]; // Jz: x=a, y=b, z=k
-                    }
-                }
-                __syncwarp();
             }
         __syncthreads();
         // ---- combine the warp-private tiles and flush once to global J (red.global.add.f32) --------------------------
         {
-            int const ox = scx * SCX + P.g[0] - T::LO, oy = scy * SCY + P.g[1] - T::LO, oz = scz * SCZ + P.g[2] - T::LO;
-            for(int i = threadIdx.x; i < 3 * T::TV; i += blockDim.x)
+            int const ox = scx * SCX + P.g[0] - T::LO, oy = scy * SCY + P.g[1] - T::LO + part * WARPS, oz = scz * SCZ + P.g[2] - T::LO;
+            constexpr int CY = WARPS + WN - 1; // y extent covered by this CTA
+            constexpr int CV = T::TX * CY * T::TZ;
+            for(int i = threadIdx.x; i < 3 * CV; i += blockDim.x)
             {
-                int const comp = i / T::TV;
-                int const r = i % T::TV;
-                int const x = r % T::TX, y = (r / T::TX) % T::TY, z = r / (T::TX * T::TY);
-                // block tile y = row + n  with row = warp index, n = window index in [0, WN)
+                int const comp = i / CV;
+                int const r = i % CV;
+                int const x = r % T::TX, y = (r / T::TX) % CY, z = r / (T::TX * CY);
+                // CTA tile y = row + n  with row = warp index, n = window index in [0, WN)
                 float v = 0.0f;
 #pragma unroll
                 for(int n = 0; n < WN; ++n)
                 {
                     int const row = y - n;
-                    if(row >= 0 && row < SCY)
+                    if(row >= 0 && row < WARPS)
                         v += tiles[row * 3 * W::PV + comp * W::PV + x + W::PX * (n + W::PY * z)];
                 }
                 if(v != 0.0f)
@@ -550,12 +587,13 @@ namespace picstep
         }
         else
         {
-            constexpr int WARPS = SCY;
-            size_t const smem = sizeof(float) * (WARPS * 3 * Win<SHAPE>::PV + WARPS * 32 * Win<SHAPE>::RECP);
+            constexpr int WARPS = 4;
+            static_assert((WARPS * 3 * Win<SHAPE>::PV) % 4 == 0, "records must stay 16-byte aligned");
+            size_t const smem = sizeof(float) * (WARPS * 3 * Win<SHAPE>::PV + WARPS * Win<SHAPE>::NREC * Win<SHAPE>::RECP);
             cudaError_t e = cudaFuncSetAttribute(depositCellKernel<SHAPE, SOLVER, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
             if(e != cudaSuccess)
                 return e;
-            depositCellKernel<SHAPE, SOLVER, WARPS><<<nscTot, WARPS * 32, smem, st>>>(P, S, J, cellOff);
+            depositCellKernel<SHAPE, SOLVER, WARPS><<<nscTot * (SCY / WARPS), WARPS * 32, smem, st>>>(P, S, J, cellOff);
         }
         return cudaGetLastError();
     }
