@@ -98,7 +98,9 @@ extern "C"
         int32_t devices[3]; /* -d : ranks per axis (one axis may be > 1) */
         int32_t rank_pos[3]; /* this rank's coordinate in the device grid */
         int32_t device; /* CUDA device ordinal */
-        int32_t flags; /* bit0: deposit with the simple per-particle atomic kernel (debug / cross-check) */
+        int32_t flags; /* bit0: deposit with the reference-strategy per-particle atomic kernel (cross-check);
+                        * bit1: deposit with the warp-per-cell kernel (all shapes, EmZ) instead of the run kernel;
+                        * bit2: picstep_step() runs push and deposit as separate kernels (no fusion) */
     } picstep_params;
 
     /* library / build information: returns e.g. "picstep sm_100a fmad=on" */

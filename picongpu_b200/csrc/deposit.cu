@@ -16,6 +16,7 @@
 //    particle, loop bounds and summation order exactly as Esirkepov.hpp:204-241, shared atomics, atomic flush.
 //    Kept as cross-check and as the baseline the ncu profiles compare against.
 #include "common.cuh"
+#include "esirkepov.cuh"
 #include "shapes.cuh"
 
 namespace picstep
@@ -35,24 +36,6 @@ namespace picstep
         static constexpr int TX = SCX + LO + UP, TY = SCY + LO + UP, TZ = SCZ + LO + UP;
         static constexpr int TV = TX * TY * TZ;
     };
-
-    // relayPoint.hpp:48-63 (only the two assignment-cell indices are needed by Esirkepov)
-    template<bool EVEN>
-    __device__ __forceinline__ float relay(int& i1, int& i2, float x1, float x2)
-    {
-        if constexpr(EVEN)
-        {
-            i1 = __float2int_rd(x1);
-            i2 = __float2int_rd(x2);
-            return i1 == i2 ? x2 : float(max(i1, i2));
-        }
-        else
-        {
-            i1 = __float2int_rd(x1 + 0.5f);
-            i2 = __float2int_rd(x2 + 0.5f);
-            return i1 == i2 ? x2 : float(i1 + i2) / 2.0f;
-        }
-    }
 
     // ------------------------------------------------------------------------------------------------------------
     // Reference-strategy kernel (thread per particle, shared atomics)

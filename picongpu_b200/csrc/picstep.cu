@@ -17,6 +17,9 @@ namespace picstep
     cudaError_t launchPush(int, int, DevParams const&, SpeciesDev const&, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, cudaStream_t);
     cudaError_t launchGather(int, DevParams const&, SpeciesDev const&, Field3, Field3, uint32_t const*, float*, long long, cudaStream_t);
     cudaError_t launchDeposit(int, int, bool, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
+    bool runKernelSupports(int, int);
+    cudaError_t launchDepositRun(int, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
+    cudaError_t launchPushDeposit(int, int, DevParams const&, SpeciesDev const&, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, cudaStream_t);
     cudaError_t launchScan(uint32_t const*, uint32_t*, uint32_t*, uint32_t*, int, uint32_t*, uint32_t, int*, cudaStream_t);
     cudaError_t launchScatter(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t*, cudaStream_t);
     cudaError_t launchCountRecords(MigRecord const*, uint32_t, uint32_t*, cudaStream_t);
@@ -937,7 +940,22 @@ extern "C"
         SpeciesHost& s = c->species[sp];
         if(s.capacity == 0)
             return PICSTEP_OK;
-        KL(c, 1, launchDeposit(c->prm.shape, c->prm.current_solver, (c->prm.flags & 1) != 0, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
+        if(runKernelSupports(c->prm.shape, c->prm.current_solver) && !(c->prm.flags & 3))
+            KL(c, 1, launchDepositRun(c->prm.shape, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
+        else
+            KL(c, 1, launchDeposit(c->prm.shape, c->prm.current_solver, (c->prm.flags & 1) != 0, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
+        return PICSTEP_OK;
+    }
+
+    /* fused ParticlePush + CurrentDeposition of one species (fast path of picstep_step): the current of the move
+     * is deposited by the kernel that performs the move, from the cell the particle started in */
+    static int pushDepositFused(picstep_ctx* c, int32_t sp)
+    {
+        StageTimer t(c, 1);
+        SpeciesHost& s = c->species[sp];
+        if(s.capacity == 0)
+            return PICSTEP_OK;
+        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.key, c->stream));
         return PICSTEP_OK;
     }
 
@@ -972,19 +990,21 @@ extern "C"
             return PICSTEP_ERR_INVALID;
         CU(c, cudaSetDevice(c->device));
         int const ns = int(c->species.size());
+        // fast path: the deposition does not depend on the field update, so it is fused into the push kernel
+        bool const fused = runKernelSupports(c->prm.shape, c->prm.current_solver) && !(c->prm.flags & 7);
         for(uint32_t it = 0; it < n; ++it)
         {
             uint32_t const step = first + it;
             int rc = picstep_current_reset(c);
             for(int s = 0; s < ns && !rc; ++s)
             {
-                rc = picstep_push(c, s, step);
+                rc = fused ? pushDepositFused(c, s) : picstep_push(c, s, step);
                 if(!rc)
                     rc = picstep_migrate(c, s);
             }
             if(!rc)
                 rc = picstep_field_update_before_current(c, step);
-            for(int s = 0; s < ns && !rc; ++s)
+            for(int s = 0; s < ns && !rc && !fused; ++s)
                 rc = picstep_deposit(c, s);
             if(!rc)
                 rc = picstep_add_current(c);

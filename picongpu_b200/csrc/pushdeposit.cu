@@ -1,0 +1,487 @@
+// pushdeposit.cu — the run kernel: charge conserving Esirkepov deposition over cell-sorted frame runs, optionally
+// fused with gather + push + move (reference kernels K1 + K7: KernelMoveAndMarkParticles,
+// include/picongpu/particles/Particles.kernel:170-316, and KernelComputeCurrent + Esirkepov,
+// include/picongpu/fields/FieldJ.kernel:52-142, fields/currentDeposition/Esirkepov/Esirkepov.hpp:62-242).
+//
+// Why it looks the way it does (numbers measured on B200, see profiles/ and tools/microbench/lds_bcast.cu):
+//   * shared-memory fp32 atomicAdd is a CAS loop (ATOMS.CAST.SPIN) and ATOMS costs ~2 cycles per lane, so the
+//     reference's 54..144 shared atomics per particle cannot be the design.  Particles are cell sorted, so all
+//     particles of a cell add to the same 4x4x4 node window: the sum over the particles of a cell is kept in
+//     REGISTERS and written once per cell to a warp-private tile with plain LDS/FADD/STS.
+//   * the shared memory return path delivers 256 B/cycle/SM (LDS.32 = 1, LDS.64 = 1, LDS.128 = 2 cycles per warp
+//     instruction, independent of broadcast), so the per-particle record that phase 2 reads is laid out such that
+//     a lane needs three 16-byte loads per record for twelve FMAs.
+//
+// One CTA (8 warps) per supercell; warp w owns the 32 consecutive cells [32w, 32w+32) of the supercell, i.e. a
+// contiguous piece of the frame run.  It walks that piece in chunks of 32 particles, regardless of cell borders:
+//   phase 1 (lane = particle): [FUSED: interpolate E,B from the shared tile, Boris/Vay push, move, emit the re-sort
+//     key] then the 1-D assignment arrays of start and end point (same arithmetic as Esirkepov.hpp:84-103) are
+//     turned into a 60-word record on the window [-1,2] around the anchor cell: per axis {S0,DS}[4],
+//     {P,Q}[4] = {S0+DS/2, S0/2+DS/3}[4] and C[3] = scaled prefix sums of DS (the accumulated_J recursion of
+//     Esirkepov.hpp:223-236, factored out: J_k = C_k * transverse weight).
+//   phase 2 (lane = (component, a-half, b-half), two records per pass): t(a,b) = S0_i(a) P_j(b) + DS_i(a) Q_j(b),
+//     acc(a,b,k) += C_k t(a,b).  When the cell changes the two record slots are combined with six SHFL and the
+//     144 window values are added to the warp-private tile.
+// The eight private tiles are summed and flushed once per supercell with red.global.add.f32.
+// Trajectories that do not fit the narrow window (more than half a cell per step for odd supports, any cell
+// crossing for PQS) are deposited by their own thread with global atomics, in the reference's loop order.
+// Anchor cell: the particle's cell (stand-alone deposit after the re-sort) or, FUSED, the cell it started in.
+#include "common.cuh"
+#include "esirkepov.cuh"
+#include "pusher.cuh"
+#include "shapes.cuh"
+
+namespace picstep
+{
+    template<int SHAPE>
+    struct RunCfg
+    {
+        using Sh = Shape<SHAPE>;
+        static constexpr int WN = 4; // narrow window: grid offsets -1..2 relative to the anchor cell
+        static constexpr int WLO = 1;
+        static constexpr int NK = WN - 1;
+        static constexpr int FR = Sh::SUPP + 1; // entries of the off-support assignment arrays
+        static constexpr int NMAX0 = WN - Sh::SUPP; // largest window index of frame entry 0 in a narrow record
+        static constexpr int AXW = 20, RECW = 3 * AXW, NREC = 33; // record 32 stays all zero
+        static constexpr int WARPS = 8, CELLS_PER_WARP = SCVOL / WARPS; // 32 cells: 8 x, 4 y, 1 z
+        static constexpr int PX = SCX + WN - 1, PY = SCY / 2 + WN - 1, PZ = 1 + WN - 1, PV = PX * PY * PZ;
+        static constexpr int TX = SCX + WN - 1, TY = SCY + WN - 1, TZ = SCZ + WN - 1, TV = TX * TY * TZ;
+        static constexpr int EBW = (6 * Tile<SHAPE>::TV + 3) / 4 * 4; // E/B tile words (FUSED), 16-byte padded
+        static_assert(Sh::SUPP <= 4, "narrow window of 4 nodes needs a support of at most 4");
+        static_assert((3 * PV * WARPS) % 4 == 0 && RECW % 4 == 0, "records must stay 16-byte aligned");
+    };
+
+    template<int SHAPE, bool FUSED>
+    constexpr size_t runSmemBytes()
+    {
+        using C = RunCfg<SHAPE>;
+        return sizeof(float) * ((FUSED ? C::EBW : 0) + C::WARPS * 3 * C::PV + C::WARPS * C::NREC * C::RECW);
+    }
+
+    template<int SHAPE, int PUSHER, bool FUSED>
+    __global__ void __launch_bounds__(256, 2) runKernel(
+        DevParams P,
+        SpeciesDev S,
+        Field3 E,
+        Field3 B,
+        Field3 J,
+        uint32_t const* __restrict__ cellOff,
+        uint32_t* __restrict__ cellCnt,
+        uint32_t* __restrict__ key)
+    {
+        using Sh = Shape<SHAPE>;
+        using C = RunCfg<SHAPE>;
+        using T = Tile<SHAPE>;
+        constexpr bool even = (Sh::SUPP % 2) == 0;
+        constexpr uint32_t FULL = 0xffffffffu;
+
+        extern __shared__ __align__(16) float smem[];
+        float* const ebTile = smem;
+        float* const tiles = smem + (FUSED ? C::EBW : 0);
+        float* const recs = tiles + C::WARPS * 3 * C::PV;
+
+        int const sc = blockIdx.x;
+        int const scx = sc % P.nsc[0], scy = (sc / P.nsc[0]) % P.nsc[1], scz = sc / (P.nsc[0] * P.nsc[1]);
+        uint32_t const scBeg = cellOff[sc * SCVOL], scEnd = cellOff[(sc + 1) * SCVOL];
+        if(scBeg == scEnd)
+            return;
+        int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        float* const myTile = tiles + warp * 3 * C::PV;
+        float* const myRecs = recs + warp * C::NREC * C::RECW;
+
+        for(int i = threadIdx.x; i < C::WARPS * 3 * C::PV; i += blockDim.x)
+            tiles[i] = 0.0f;
+        for(int i = lane; i < C::RECW; i += 32)
+            myRecs[32 * C::RECW + i] = 0.0f;
+        if constexpr(FUSED)
+        {
+            // stage the six E/B component tiles: rows of TX consecutive floats, coalesced per row
+            int const ox = scx * SCX + P.g[0] - T::LO, oy = scy * SCY + P.g[1] - T::LO, oz = scz * SCZ + P.g[2] - T::LO;
+            constexpr int ROWS = T::TY * T::TZ;
+            for(int i = threadIdx.x; i < 6 * ROWS * T::TX; i += blockDim.x)
+            {
+                int const x = i % T::TX;
+                int const row = (i / T::TX) % ROWS;
+                int const comp = i / (T::TX * ROWS);
+                int const y = row % T::TY, z = row / T::TY;
+                float const* src = comp < 3 ? B.c[comp] : E.c[comp - 3];
+                ebTile[comp * T::TV + row * T::PX + x] = __ldg(src + fidx(P, ox + x, oy + y, oz + z));
+            }
+        }
+        __syncthreads();
+
+        float const rc2 = float(1.0 / double(P.c) / double(P.c));
+        float const vol = P.cell[0] * P.cell[1] * P.cell[2];
+        float const* const tB = ebTile;
+        float const* const tE = ebTile + 3 * T::TV;
+
+        // ---- phase 2 lane constants ------------------------------------------------------------------------------
+        int const slot = lane >> 4, g = lane & 15;
+        bool const p2active = g < 12;
+        int const comp = p2active ? (g >> 2) : 0;
+        int const ah = (g >> 1) & 1, bh = g & 1;
+        int const ai = (comp + 1) % 3, aj = (comp + 2) % 3; // Jx: (i,j) = (y,z); Jy: (z,x); Jz: (x,y)
+        int const offSD = ai * C::AXW + 4 * ah;
+        int const offPQ = aj * C::AXW + 8 + 4 * bh;
+        int const offC = comp * C::AXW + 16;
+        auto strideOf = [](int a) { return a == 0 ? 1 : (a == 1 ? C::PX : C::PX * C::PY); };
+        int const sC = strideOf(comp), sJ = strideOf(aj);
+        int const laneTile = comp * C::PV + (2 * ah + slot) * strideOf(ai) + 2 * bh * sJ;
+
+        float acc[2][2][C::NK];
+#pragma unroll
+        for(int a = 0; a < 2; ++a)
+#pragma unroll
+            for(int b = 0; b < 2; ++b)
+#pragma unroll
+                for(int k = 0; k < C::NK; ++k)
+                    acc[a][b][k] = 0.0f;
+
+        int curCell = -1; // local cell index (0..255) the accumulators belong to
+        uint32_t stayCount = 0; // FUSED: particles of curCell that stay in their cell
+
+        // adds the accumulators to the private tile and clears them
+        auto flushCell = [&]()
+        {
+            __syncwarp();
+            int const cx = curCell & (SCX - 1), cyl = (curCell >> 3) & (SCY / 2 - 1);
+            int const cellBase = cx + C::PX * cyl + laneTile;
+#pragma unroll
+            for(int b = 0; b < 2; ++b)
+#pragma unroll
+                for(int k = 0; k < C::NK; ++k)
+                {
+                    float const keep = slot ? acc[1][b][k] : acc[0][b][k];
+                    float const send = slot ? acc[0][b][k] : acc[1][b][k];
+                    float const v = keep + __shfl_xor_sync(FULL, send, 16);
+                    if(p2active)
+                        myTile[cellBase + b * sJ + k * sC] += v;
+                    acc[0][b][k] = 0.0f;
+                    acc[1][b][k] = 0.0f;
+                }
+            if constexpr(FUSED)
+            {
+                if(lane == 0 && stayCount)
+                    atomicAdd(&cellCnt[sc * SCVOL + curCell], stayCount);
+                stayCount = 0;
+            }
+        };
+
+        uint32_t const pBeg = cellOff[sc * SCVOL + warp * C::CELLS_PER_WARP];
+        uint32_t const pEnd = cellOff[sc * SCVOL + (warp + 1) * C::CELLS_PER_WARP];
+
+        for(uint32_t chunk = pBeg; chunk < pEnd; chunk += 32)
+        {
+            uint32_t const i = chunk + lane;
+            bool const valid = i < pEnd;
+            int lc = -2;
+            bool useRec = false; // this lane wrote a record phase 2 has to add
+            bool stays = false;
+            __syncwarp(); // phase 2 of the previous chunk has finished reading the records
+            // ---- phase 1: lane = particle -----------------------------------------------------------------------
+            if(valid)
+            {
+                float x1[3] = {S.pos[0][i], S.pos[1][i], S.pos[2][i]};
+                float u[3] = {S.mom[0][i], S.mom[1][i], S.mom[2][i]};
+                float const w = S.w[i];
+                lc = S.cell[i];
+                int const lx = lc % SCX, ly = (lc / SCX) % SCY, lz = lc / (SCX * SCY);
+                float const mass = S.mass_per_w * w;
+                float const charge = S.charge_per_w * w;
+                int dir[3] = {0, 0, 0};
+                bool deposit = true;
+                float vel[3];
+                if constexpr(FUSED)
+                {
+                    float Bf[3], Ef[3];
+#pragma unroll
+                    for(int k = 0; k < 3; ++k)
+                    {
+                        Bf[k] = gatherComp<SHAPE, true>(tB + k * T::TV, k, lx, ly, lz, x1[0], x1[1], x1[2]);
+                        Ef[k] = gatherComp<SHAPE, false>(tE + k * T::TV, k, lx, ly, lz, x1[0], x1[1], x1[2]);
+                    }
+                    if constexpr(PUSHER == 0)
+                        boris(P, mass, charge, Ef, Bf, u);
+                    else
+                        vay(P, rc2, mass, charge, Ef, Bf, u);
+                    velocityOf(rc2, mass, u[0], u[1], u[2], vel[0], vel[1], vel[2]);
+                    // moveParticle (MoveParticle.hpp:48-160)
+#pragma unroll
+                    for(int d = 0; d < 3; ++d)
+                    {
+                        float q = (x1[d] + (vel[d] * P.dt) / P.cell[d]) - 0.5f;
+                        float mv = 0.0f;
+                        if(q < -0.5f)
+                            mv = -1.0f;
+                        if(q >= 0.5f)
+                            mv = 1.0f;
+                        q -= mv;
+                        x1[d] = q + 0.5f;
+                        dir[d] = int(mv);
+                        S.pos[d][i] = x1[d];
+                        S.mom[d][i] = u[d];
+                    }
+                    // re-sort key (see pushKernel)
+                    int const nl[3] = {lx + dir[0], ly + dir[1], lz + dir[2]};
+                    int gc[3] = {scx * SCX + nl[0], scy * SCY + nl[1], scz * SCZ + nl[2]};
+                    uint32_t flag = 0u;
+                    bool drop = false;
+#pragma unroll
+                    for(int d = 0; d < 3; ++d)
+                    {
+                        if(gc[d] < 0 || gc[d] >= P.n[d])
+                        {
+                            bool const up = gc[d] >= P.n[d];
+                            if(P.wrap[d])
+                                gc[d] += up ? -P.n[d] : P.n[d];
+                            else if(d == P.split_axis && (up ? P.has_upper : P.has_lower))
+                            {
+                                flag = KEY_LEAVE | (up ? KEY_UPPER : 0u);
+                                gc[d] += up ? -P.n[d] : P.n[d]; // coordinate in the receiver's local grid
+                            }
+                            else
+                                drop = true;
+                        }
+                    }
+                    uint32_t k;
+                    if(drop)
+                    {
+                        k = KEY_DROP;
+                        deposit = false; // absorbed particles are deleted before the current deposition
+                    }
+                    else
+                    {
+                        int const dsc = (gc[0] >> 3) + P.nsc[0] * ((gc[1] >> 3) + P.nsc[1] * (gc[2] >> 2));
+                        int const dlc = (gc[0] & 7) + SCX * ((gc[1] & 7) + SCY * (gc[2] & 3));
+                        k = uint32_t(dsc) * SCVOL + uint32_t(dlc);
+                        if(flag)
+                            k |= flag;
+                        else if((dir[0] | dir[1] | dir[2]) == 0)
+                            stays = true; // counted per cell by ballot in phase 2
+                        else
+                            atomicAdd(&cellCnt[k], 1u);
+                    }
+                    key[i] = k;
+                }
+                else
+                    velocityOf(rc2, mass, u[0], u[1], u[2], vel[0], vel[1], vel[2]);
+
+                if(deposit)
+                {
+                    // Esirkepov.hpp:84-103: both points in the frame of gridShift = min(iS,iE), off-support arrays
+                    float const csd = charge * (1.0f / float(vol * P.dt));
+                    float s0[3][C::FR], s1[3][C::FR], f[3], p0[3], p1[3];
+                    int n0[3], gs3[3], status[3];
+                    bool narrow = true;
+#pragma unroll
+                    for(int d = 0; d < 3; ++d)
+                    {
+                        float const dp = vel[d] * P.dt / P.cell[d];
+                        float const xe = x1[d], xs = xe - dp;
+                        int iS, iE;
+                        relay<even>(iS, iE, xs, xe);
+                        int const gs = iS < iE ? iS : iE;
+                        float const y0 = xs - float(gs), y1 = xe - float(gs);
+                        shapeOff<SHAPE>(y0, gs != iS, s0[d]);
+                        shapeOff<SHAPE>(y1, gs != iE, s1[d]);
+                        f[d] = (y0 == y1) ? 0.0f : -(csd * P.cell[d]);
+                        int const leave = iS != iE ? 1 : 0;
+                        n0[d] = gs + Sh::BEGIN + C::WLO + dir[d];
+                        if(n0[d] < 0 || n0[d] + Sh::SUPP - 1 + leave > C::WN - 1)
+                            narrow = false;
+                        p0[d] = y0;
+                        p1[d] = y1;
+                        gs3[d] = gs;
+                        status[d] = (gs == iS ? 2 : 0) | (gs == iE ? 4 : 0) | leave;
+                    }
+                    if(narrow)
+                    {
+                        useRec = true;
+                        float* const rec = myRecs + lane * C::RECW;
+#pragma unroll
+                        for(int d = 0; d < 3; ++d)
+                        {
+                            float S0[C::WN], DS[C::WN];
+#pragma unroll
+                            for(int n = 0; n < C::WN; ++n)
+                            {
+                                float v0 = 0.0f, v1 = 0.0f;
+#pragma unroll
+                                for(int m = 0; m <= C::NMAX0; ++m)
+                                {
+                                    int const s = n - m;
+                                    if(s >= 0 && s < C::FR)
+                                    {
+                                        v0 = (n0[d] == m) ? s0[d][s] : v0;
+                                        v1 = (n0[d] == m) ? s1[d][s] : v1;
+                                    }
+                                }
+                                S0[n] = v0;
+                                DS[n] = v1 - v0;
+                            }
+                            float4* r4 = reinterpret_cast<float4*>(rec + d * C::AXW);
+                            r4[0] = make_float4(S0[0], DS[0], S0[1], DS[1]);
+                            r4[1] = make_float4(S0[2], DS[2], S0[3], DS[3]);
+                            float Pn[C::WN], Qn[C::WN];
+#pragma unroll
+                            for(int n = 0; n < C::WN; ++n)
+                            {
+                                Pn[n] = S0[n] + 0.5f * DS[n];
+                                Qn[n] = 0.5f * S0[n] + (1.0f / 3.0f) * DS[n];
+                            }
+                            r4[2] = make_float4(Pn[0], Qn[0], Pn[1], Qn[1]);
+                            r4[3] = make_float4(Pn[2], Qn[2], Pn[3], Qn[3]);
+                            float const c0 = DS[0], c1 = c0 + DS[1], c2 = c1 + DS[2];
+                            r4[4] = make_float4(c0 * f[d], c1 * f[d], c2 * f[d], 0.0f);
+                        }
+                    }
+                    else
+                    {
+                        // wide trajectory: reference loop with global atomics, in the frame of the particle's new cell
+                        long long const strideG[3] = {1, P.N[0], (long long) P.N[0] * P.N[1]};
+                        int const baseG[3]
+                            = {scx * SCX + P.g[0] + lx + dir[0] + gs3[0], scy * SCY + P.g[1] + ly + dir[1] + gs3[1], scz * SCZ + P.g[2] + lz + dir[2] + gs3[2]};
+                        long long const origin = fidx(P, baseG[0], baseG[1], baseG[2]);
+                        esirkepov1DGlobal<SHAPE, 1, 2, 0>(J.c[0] + origin, strideG, status, p0, p1, csd * P.cell[0]);
+                        esirkepov1DGlobal<SHAPE, 2, 0, 1>(J.c[1] + origin, strideG, status, p0, p1, csd * P.cell[1]);
+                        esirkepov1DGlobal<SHAPE, 0, 1, 2>(J.c[2] + origin, strideG, status, p0, p1, csd * P.cell[2]);
+                    }
+                }
+            }
+            // ---- phase 2: segments of equal cell, two records per pass ----------------------------------------------
+            uint32_t const validMask = __ballot_sync(FULL, valid);
+            int const n = __popc(validMask);
+            uint32_t const useMask = __ballot_sync(FULL, useRec);
+            uint32_t const stayMask = FUSED ? __ballot_sync(FULL, stays) : 0u;
+            int prev = __shfl_up_sync(FULL, lc, 1);
+            if(lane == 0)
+                prev = curCell;
+            uint32_t const startMask = __ballot_sync(FULL, valid && lc != prev);
+            __syncwarp(); // records are visible
+            int r = 0;
+            while(r < n)
+            {
+                uint32_t const later = r < 31 ? (startMask & (0xfffffffeu << r)) : 0u;
+                int const e = later ? __ffs(later) - 1 : n;
+                if((startMask >> r) & 1u)
+                {
+                    if(curCell >= 0)
+                        flushCell();
+                    curCell = __shfl_sync(FULL, lc, r);
+                }
+                if constexpr(FUSED)
+                {
+                    uint32_t const seg = (e < 32 ? ((1u << e) - 1u) : FULL) & ~((1u << r) - 1u);
+                    stayCount += __popc(stayMask & seg);
+                }
+                for(int q = r; q < e; q += 2)
+                {
+                    int const idx = q + slot;
+                    bool const use = idx < e && ((useMask >> idx) & 1u);
+                    float const* rec = myRecs + (use ? idx : 32) * C::RECW;
+                    float4 const sd = *reinterpret_cast<float4 const*>(rec + offSD);
+                    float4 const pq = *reinterpret_cast<float4 const*>(rec + offPQ);
+                    float4 const c4 = *reinterpret_cast<float4 const*>(rec + offC);
+                    float const t00 = sd.x * pq.x + sd.y * pq.y;
+                    float const t01 = sd.x * pq.z + sd.y * pq.w;
+                    float const t10 = sd.z * pq.x + sd.w * pq.y;
+                    float const t11 = sd.z * pq.z + sd.w * pq.w;
+                    acc[0][0][0] += c4.x * t00;
+                    acc[0][0][1] += c4.y * t00;
+                    acc[0][0][2] += c4.z * t00;
+                    acc[0][1][0] += c4.x * t01;
+                    acc[0][1][1] += c4.y * t01;
+                    acc[0][1][2] += c4.z * t01;
+                    acc[1][0][0] += c4.x * t10;
+                    acc[1][0][1] += c4.y * t10;
+                    acc[1][0][2] += c4.z * t10;
+                    acc[1][1][0] += c4.x * t11;
+                    acc[1][1][1] += c4.y * t11;
+                    acc[1][1][2] += c4.z * t11;
+                }
+                r = e;
+            }
+        }
+        if(curCell >= 0)
+            flushCell();
+        __syncthreads();
+        // ---- combine the warp-private tiles and flush once to global J (red.global.add.f32) --------------------------
+        {
+            int const ox = scx * SCX + P.g[0] - C::WLO, oy = scy * SCY + P.g[1] - C::WLO, oz = scz * SCZ + P.g[2] - C::WLO;
+            for(int i = threadIdx.x; i < 3 * C::TV; i += blockDim.x)
+            {
+                int const cmp = i / C::TV;
+                int const rr = i % C::TV;
+                int const x = rr % C::TX, y = (rr / C::TX) % C::TY, z = rr / (C::TX * C::TY);
+                float v = 0.0f;
+#pragma unroll
+                for(int zc = 0; zc < SCZ; ++zc)
+                {
+                    int const tz = z - zc;
+                    if(tz < 0 || tz >= C::PZ)
+                        continue;
+#pragma unroll
+                    for(int h = 0; h < 2; ++h)
+                    {
+                        int const ty = y - h * (SCY / 2);
+                        if(ty < 0 || ty >= C::PY)
+                            continue;
+                        v += tiles[(zc * 2 + h) * 3 * C::PV + cmp * C::PV + x + C::PX * (ty + C::PY * tz)];
+                    }
+                }
+                if(v != 0.0f)
+                    atomicAdd(J.c[cmp] + fidx(P, ox + x, oy + y, oz + z), v);
+            }
+        }
+    }
+
+    template<int SHAPE, int PUSHER, bool FUSED>
+    cudaError_t launchRunT(DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* key, cudaStream_t st)
+    {
+        int const nscTot = P.nsc[0] * P.nsc[1] * P.nsc[2];
+        constexpr size_t smem = runSmemBytes<SHAPE, FUSED>();
+        cudaError_t e = cudaFuncSetAttribute(runKernel<SHAPE, PUSHER, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if(e != cudaSuccess)
+            return e;
+        runKernel<SHAPE, PUSHER, FUSED><<<nscTot, 256, smem, st>>>(P, S, E, B, J, cellOff, cellCnt, key);
+        return cudaGetLastError();
+    }
+
+    bool runKernelSupports(int shape, int solver)
+    {
+        return solver == 0 && shape >= 0 && shape <= 3;
+    }
+
+    /** stand-alone deposition of one species (picstep_deposit) */
+    cudaError_t launchDepositRun(int shape, DevParams const& P, SpeciesDev const& S, Field3 J, uint32_t const* cellOff, cudaStream_t st)
+    {
+        Field3 none{};
+#define PS_CASE(SH)                                                                                                   \
+    if(shape == SH)                                                                                                   \
+        return launchRunT<SH, 0, false>(P, S, none, none, J, cellOff, nullptr, nullptr, st);
+        PS_CASE(0)
+        PS_CASE(1)
+        PS_CASE(2)
+        PS_CASE(3)
+#undef PS_CASE
+        return cudaErrorInvalidValue;
+    }
+
+    /** fused gather + push + move + deposit of one species (picstep_step fast path) */
+    cudaError_t launchPushDeposit(int shape, int pusher, DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* key, cudaStream_t st)
+    {
+#define PS_CASE(SH, PU)                                                                                               \
+    if(shape == SH && pusher == PU)                                                                                   \
+        return launchRunT<SH, PU, true>(P, S, E, B, J, cellOff, cellCnt, key, st);
+        PS_CASE(0, 0)
+        PS_CASE(1, 0)
+        PS_CASE(2, 0)
+        PS_CASE(3, 0)
+        PS_CASE(0, 1)
+        PS_CASE(1, 1)
+        PS_CASE(2, 1)
+        PS_CASE(3, 1)
+#undef PS_CASE
+        return cudaErrorInvalidValue;
+    }
+} // namespace picstep

@@ -1,0 +1,186 @@
+// pusher.cuh — device functions shared by the push kernels: field-to-particle interpolation on the Yee grid
+// (FieldToParticleInterpolation.hpp:97-124), Boris / Vay pushers (particlePusherBoris.hpp:42-91,
+// particlePusherVay.hpp:43-112), Gamma / Velocity (Gamma.hpp:30-38, Velocity.hpp:28-38).
+#pragma once
+#include "common.cuh"
+#include "shapes.cuh"
+
+namespace picstep
+{
+    // Yee stagger (include/picongpu/fields/YeeCell.hpp:70-130); component c of E sits at +0.5 along c,
+    // component c of B at +0.5 along the two other axes.
+    __device__ __forceinline__ float stagE(int comp, int d)
+    {
+        return comp == d ? 0.5f : 0.0f;
+    }
+    __device__ __forceinline__ float stagB(int comp, int d)
+    {
+        return comp == d ? 0.0f : 0.5f;
+    }
+
+    template<int SHAPE>
+    struct Tile
+    {
+        static constexpr int LO = GatherMargin<SHAPE>::LO, UP = GatherMargin<SHAPE>::UP;
+        static constexpr int TX = SCX + LO + UP, TY = SCY + LO + UP, TZ = SCZ + LO + UP;
+        // odd row pitch keeps the y/z neighbours of a cell on different banks
+        static constexpr int PX = (TX % 2 == 0) ? TX + 1 : TX;
+        static constexpr int TV = PX * TY * TZ;
+    };
+
+    /** Interpolate one field component to the particle (FieldToParticleInterpolation.hpp:97-124 +
+     * ShiftCoordinateSystem.hpp:54-79 + AssignedTrilinearInterpolation.hpp:54-86; x innermost). */
+    template<int SHAPE, bool IS_B>
+    __device__ __forceinline__ float gatherComp(float const* __restrict__ t, int comp, int lx, int ly, int lz, float px, float py, float pz)
+    {
+        using S = Shape<SHAPE>;
+        using T = Tile<SHAPE>;
+        constexpr bool even = (S::SUPP % 2) == 0;
+        constexpr int begin = -S::SUPP / 2 + (S::SUPP + 1) % 2;
+        float sx[S::SUPP], sy[S::SUPP], sz[S::SUPP];
+        int base;
+        {
+            float const p[3] = {px, py, pz};
+            int const l[3] = {lx, ly, lz};
+            int sh[3];
+            float q[3];
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+            {
+                float const fp = IS_B ? stagB(comp, d) : stagE(comp, d);
+                float const v = p[d] - fp - 0.5f;
+                if constexpr(even)
+                    sh[d] = v >= -0.5f ? 0 : -1;
+                else
+                    sh[d] = v >= 0.0f ? 1 : 0;
+                q[d] = v - float(sh[d]) + 0.5f;
+                sh[d] += l[d] + T::LO + begin;
+            }
+            S::on(q[0], sx);
+            S::on(q[1], sy);
+            S::on(q[2], sz);
+            base = (sh[2] * T::TY + sh[1]) * T::PX + sh[0];
+        }
+        float rz = 0.0f;
+#pragma unroll
+        for(int z = 0; z < S::SUPP; ++z)
+        {
+            float ry = 0.0f;
+#pragma unroll
+            for(int y = 0; y < S::SUPP; ++y)
+            {
+                float rx = 0.0f;
+#pragma unroll
+                for(int x = 0; x < S::SUPP; ++x)
+                    rx += t[base + (z * T::TY + y) * T::PX + x] * sx[x];
+                ry += rx * sy[y];
+            }
+            rz += ry * sz[z];
+        }
+        return rz;
+    }
+
+    __device__ __forceinline__ float norm2(float x, float y, float z)
+    {
+        float t = x * x;
+        t += y * y;
+        t += z * z;
+        return t;
+    }
+
+    // Gamma.hpp:30-38
+    __device__ __forceinline__ float gammaOf(float c, float ux, float uy, float uz, float mass)
+    {
+        float const c2 = c * c;
+        float const r = 1.0f / (mass * mass * c2);
+        return sqrtf(1.0f + norm2(ux, uy, uz) * r);
+    }
+
+    // Velocity.hpp:28-38: v = p * rsqrt(m^2 + p^2/c^2)
+    __device__ __forceinline__ void velocityOf(float rc2, float mass, float ux, float uy, float uz, float& vx, float& vy, float& vz)
+    {
+        float const t = ps_rsqrt(mass * mass + norm2(ux, uy, uz) * rc2);
+        vx = t * ux;
+        vy = t * uy;
+        vz = t * uz;
+    }
+
+    // particlePusherBoris.hpp:42-91
+    __device__ __forceinline__ void boris(DevParams const& P, float mass, float charge, float const E[3], float const B[3], float u[3])
+    {
+        float const QoM = charge / mass;
+        float const dt = P.dt;
+        float m[3], t[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            m[d] = u[d] + 0.5f * charge * E[d] * dt;
+        float const gr = 1.0f / gammaOf(P.c, m[0], m[1], m[2], mass);
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            t[d] = 0.5f * QoM * B[d] * gr * dt;
+        float const sf = 1.0f / (1.0f + norm2(t[0], t[1], t[2]));
+        float s[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            s[d] = 2.0f * t[d] * sf;
+        float pr[3];
+        pr[0] = m[0] + (m[1] * t[2] - m[2] * t[1]);
+        pr[1] = m[1] + (m[2] * t[0] - m[0] * t[2]);
+        pr[2] = m[2] + (m[0] * t[1] - m[1] * t[0]);
+        float pl[3];
+        pl[0] = m[0] + (pr[1] * s[2] - pr[2] * s[1]);
+        pl[1] = m[1] + (pr[2] * s[0] - pr[0] * s[2]);
+        pl[2] = m[2] + (pr[0] * s[1] - pr[1] * s[0]);
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            u[d] = pl[d] + 0.5f * charge * E[d] * dt;
+    }
+
+    // particlePusherVay.hpp:43-112 (sqrt section in fp64: sqrt_Vay = precision64Bit, param/pusher.param:62)
+    __device__ __forceinline__ void vay(DevParams const& P, float rc2, float mass, float charge, float const E[3], float const B[3], float u[3])
+    {
+        float const factor = float(0.5 * double(charge) * double(P.dt));
+        float v0[3];
+        velocityOf(rc2, mass, u[0], u[1], u[2], v0[0], v0[1], v0[2]);
+        float cr[3];
+        cr[0] = v0[1] * B[2] - v0[2] * B[1];
+        cr[1] = v0[2] * B[0] - v0[0] * B[2];
+        cr[2] = v0[0] * B[1] - v0[1] * B[0];
+        float mp[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+        {
+            float const m0 = u[d] + factor * (E[d] + cr[d]);
+            mp[d] = m0 + factor * E[d];
+        }
+        float const gp = gammaOf(P.c, mp[0], mp[1], mp[2], mass);
+        double tau[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            tau[d] = double(factor / mass * B[d]);
+        double dpt = double(mp[0]) * tau[0];
+        dpt += double(mp[1]) * tau[1];
+        dpt += double(mp[2]) * tau[2];
+        double const ustar = dpt / double(P.c * mass);
+        double tau2 = tau[0] * tau[0];
+        tau2 += tau[1] * tau[1];
+        tau2 += tau[2] * tau[2];
+        double const sigma = double(gp * gp) - tau2;
+        double const gplus = sqrt(0.5 * (sigma + sqrt(sigma * sigma + 4.0 * (tau2 + ustar * ustar))));
+        float t[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            t[d] = float(tau[d] * (1.0 / gplus));
+        float const s = 1.0f / (1.0f + norm2(t[0], t[1], t[2]));
+        float dp = mp[0] * t[0];
+        dp += mp[1] * t[1];
+        dp += mp[2] * t[2];
+        cr[0] = mp[1] * t[2] - mp[2] * t[1];
+        cr[1] = mp[2] * t[0] - mp[0] * t[2];
+        cr[2] = mp[0] * t[1] - mp[1] * t[0];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            u[d] = s * (mp[d] + dp * t[d] + cr[d]);
+    }
+
+} // namespace picstep

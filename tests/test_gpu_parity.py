@@ -216,14 +216,15 @@ def test_resort_many_steps_keeps_invariants(orc):
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [prm.SHAPE_CIC, prm.SHAPE_TSC, prm.SHAPE_PQS, prm.SHAPE_PCS])
 @pytest.mark.parametrize("solver", [prm.CURRENT_ESIRKEPOV, prm.CURRENT_EMZ])
-@pytest.mark.parametrize("atomic", [False, True])
-def test_deposit(orc, shape, solver, atomic):
+@pytest.mark.parametrize("kernel", ["run", "cell", "atomic"])
+def test_deposit(orc, shape, solver, kernel):
     p = util.make_params((16, 16, 8), shape=shape, current_solver=solver)
     pos, mom, w, cell = util.random_particles(p, ppc=12, seed=40 + shape, thermal=1.5)
     # a few particles exactly at rest and some at cell faces
     mom[:, :100] = 0
     pos[0, 100:200] = 0.0
-    s = _sim(p, False, atomic_deposit=atomic)
+    # "run": the chunked run kernel (default where supported: Esirkepov, NGP..PQS; otherwise falls back to "cell")
+    s = _sim(p, False, atomic_deposit=kernel == "atomic", cell_deposit=kernel == "cell")
     s.upload_particles("e", pos, mom, w, cell)
     s.current_reset()
     s.deposit("e")
@@ -244,11 +245,11 @@ def test_deposit(orc, shape, solver, atomic):
     s.close()
 
 
-@pytest.mark.parametrize("atomic", [False, True])
-def test_deposit_ngp(orc, atomic):
+@pytest.mark.parametrize("kernel", ["run", "cell", "atomic"])
+def test_deposit_ngp(orc, kernel):
     p = util.make_params((16, 16, 8), shape=prm.SHAPE_NGP)
     pos, mom, w, cell = util.random_particles(p, ppc=8, seed=47, thermal=1.0)
-    s = _sim(p, False, atomic_deposit=atomic)
+    s = _sim(p, False, atomic_deposit=kernel == "atomic", cell_deposit=kernel == "cell")
     s.upload_particles("e", pos, mom, w, cell)
     s.current_reset()
     s.deposit("e")
@@ -258,6 +259,26 @@ def test_deposit_ngp(orc, atomic):
     Jo = o.field()
     o.deposit(1.0, 1.0, Jo, dp, dm, dw, dc)
     assert _relerr(J, Jo) < 2e-5
+    s.close()
+
+
+@pytest.mark.parametrize("thermal", [0.05, 0.4])
+def test_deposit_run_kernel_slow_particles(orc, thermal):
+    """Run kernel with non-relativistic particles: (almost) every trajectory takes the narrow-window register path
+    (the relativistic cases above mostly exercise the per-thread wide-trajectory path)."""
+    p = util.make_params((16, 16, 8))
+    pos, mom, w, cell = util.random_particles(p, ppc=25, seed=77, thermal=thermal)
+    s = _sim(p, False)
+    s.upload_particles("e", pos, mom, w, cell)
+    s.current_reset()
+    s.deposit("e")
+    J = s.download_field(FJ)
+    dp, dm, dw, dc = s.download_particles("e")
+    o = orc.Oracle(p)
+    Jo = o.field()
+    o.deposit(1.0, 1.0, Jo, dp, dm, dw, dc)
+    assert np.abs(Jo).max() > 0
+    assert _relerr(J, Jo) < 2e-5, _relerr(J, Jo)
     s.close()
 
 
@@ -355,9 +376,9 @@ def test_plane_wave_dispersion():
 # ---------------------------------------------------------------------------------------------------------------
 # coupled steps
 # ---------------------------------------------------------------------------------------------------------------
-def _run_pair(orc, p, steps, exact, fused):
+def _run_pair(orc, p, steps, exact, fused, **kw):
     o, e, i = util.khi_ic(orc, p)
-    s = _sim(p, exact)
+    s = _sim(p, exact, **kw)
     for name, sp in (("e", e), ("i", i)):
         s.upload_particles(name, sp["pos"], sp["mom"], sp["w"], sp["cell"])
     E, B, J = o.field(), o.field(), o.field()
@@ -381,8 +402,42 @@ def test_khi_step_stage_calls_equal_fused_step(orc):
         a, b = s1.download_field(f), s2.download_field(f)
         assert np.abs(o.interior(a) - o.interior(b)).max() / sc < 1e-5
     assert s1.launch_count() > 0
+    # picstep_step with separate push / deposit kernels (flags bit2) against the fused push+deposit kernel
+    s3, _, _, _ = _run_pair(orc, p, 3, True, fused=True, unfused=True)
+    for f, sc in ((FE, escale), (FB, escale), (FJ, jscale)):
+        a, b = s1.download_field(f), s3.download_field(f)
+        assert np.abs(o.interior(a) - o.interior(b)).max() / sc < 1e-5
     s1.close()
     s2.close()
+    s3.close()
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("shape,pusher", [(prm.SHAPE_TSC, prm.PUSHER_BORIS), (prm.SHAPE_CIC, prm.PUSHER_VAY), (prm.SHAPE_PQS, prm.PUSHER_BORIS)])
+def test_fused_push_equals_separate_kernels(orc, exact, shape, pusher):
+    """One step from identical fields and particles: the fused push+deposit kernel must move every particle exactly
+    like the stand-alone push kernel (bit-identical positions, momenta, cells) and deposit the same current."""
+    p = util.make_params((16, 16, 8), shape=shape, pusher=pusher)
+    E, B = util.smooth_fields(p, seed=5, amp=0.05)
+    pos, mom, w, cell = util.random_particles(p, ppc=6, seed=9, thermal=0.4)
+    res = []
+    for unfused in (False, True):
+        s = _sim(p, exact, unfused=unfused)
+        s.upload_field(FE, E)
+        s.upload_field(FB, B)
+        s.upload_particles("e", pos, mom, w, cell)
+        s.step(1)
+        res.append((util.order_by_weight(*s.download_particles("e")), s.download_field(FJ), s.supercell_counts("e")))
+        s.close()
+    (pa, Ja, ca), (pb, Jb, cb) = res
+    for x, y in zip(pa, pb):
+        assert np.array_equal(x, y)
+    assert np.array_equal(ca, cb)
+    # interior only: the guard cells hold the un-folded contributions, which depend on the anchor cell of the window
+    g, n = p.guard_cells, p.grid
+    Ja, Jb = (x[:, g[2]:g[2] + n[2], g[1]:g[1] + n[1], g[0]:g[0] + n[0]] for x in (Ja, Jb))
+    assert np.abs(Ja).max() > 0
+    assert _relerr(Ja, Jb) < 2e-5, _relerr(Ja, Jb)
 
 
 @pytest.mark.parametrize("exact", [True, False])
