@@ -18,16 +18,36 @@ namespace picstep
     constexpr uint32_t KEY_DROP = 0xFFFFFFFFu;
 
 #ifdef PICSTEP_EXACT
-    // bit-exact build (-fmad=false): the reference's CPU backend computes rsqrt as 1/sqrt
+    // bit-exact build (-fmad=false): the reference's CPU backend computes rsqrt as 1/sqrt; IEEE division and sqrt
     __device__ __forceinline__ float ps_rsqrt(float x)
     {
         return 1.0f / sqrtf(x);
     }
+    __device__ __forceinline__ float ps_div(float a, float b)
+    {
+        return a / b;
+    }
+    __device__ __forceinline__ float ps_sqrt(float x)
+    {
+        return sqrtf(x);
+    }
 #else
-    // production build: same as the reference's CUDA backend (alpaka rsqrt -> ::rsqrtf)
+    // production build: rsqrt as the reference's CUDA backend (alpaka rsqrt -> ::rsqrtf); division and sqrt through
+    // the SFU approximations (2 ulp) instead of the IEEE sequences with their slow-path calls -- the kernels are
+    // issue bound and the error is far inside the 1e-5 parity tolerance (tests/test_gpu_parity.py)
     __device__ __forceinline__ float ps_rsqrt(float x)
     {
         return rsqrtf(x);
+    }
+    __device__ __forceinline__ float ps_div(float a, float b)
+    {
+        return __fdividef(a, b);
+    }
+    __device__ __forceinline__ float ps_sqrt(float x)
+    {
+        float r;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
     }
 #endif
 

@@ -24,12 +24,19 @@ namespace picstep
         }
     }
 
+    /** red.global.add.f32 on a pointer that is known to be global memory (atomicAdd on a generic pointer compiles to
+     * an address-space test plus both the shared CAS loop and the global atomic) */
+    __device__ __forceinline__ void redGlobal(float* p, float v)
+    {
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    }
+
     /** One rotated 1-D pass of Esirkepov (Esirkepov.hpp:147-242) for a single particle with global atomics
      * (red.global.add.f32); loop bounds and summation order are the reference's.  R0,R1,R2: original axes of the
      * rotated i,j,k.  `origin` points at the node of the particle's cell shifted by gridShift, `stride` are the
      * element strides of the three grid axes, p0/p1 the start/end point in that frame. */
     template<int SHAPE, int R0, int R1, int R2>
-    __device__ __noinline__ void esirkepov1DGlobal(
+    __device__ __forceinline__ void esirkepov1DGlobal(
         float* __restrict__ origin,
         long long const stride[3],
         int const status[3],
@@ -69,9 +76,21 @@ namespace picstep
                             {
                                 float const W = (s1k[k - begin] - s0k[k - begin]) * tmp;
                                 acc += W;
-                                atomicAdd(origin + i * stride[R0] + j * stride[R1] + k * stride[R2], acc);
+                                redGlobal(origin + i * stride[R0] + j * stride[R1] + k * stride[R2], acc);
                             }
                     }
             }
+    }
+    /** Slow path of the run kernel: one particle, all three components, arguments by value so that the caller keeps
+     * nothing in local memory.  status = status[0] | status[1] << 3 | status[2] << 6. */
+    template<int SHAPE>
+    __device__ __noinline__ void esirkepovParticleGlobal(float* jx, float* jy, float* jz, long long strideY, long long strideZ, int statusPacked, float p0x, float p0y, float p0z, float p1x, float p1y, float p1z, float csdx, float csdy, float csdz)
+    {
+        long long const stride[3] = {1, strideY, strideZ};
+        int const status[3] = {statusPacked & 7, (statusPacked >> 3) & 7, (statusPacked >> 6) & 7};
+        float const p0[3] = {p0x, p0y, p0z}, p1[3] = {p1x, p1y, p1z};
+        esirkepov1DGlobal<SHAPE, 1, 2, 0>(jx, stride, status, p0, p1, csdx);
+        esirkepov1DGlobal<SHAPE, 2, 0, 1>(jy, stride, status, p0, p1, csdy);
+        esirkepov1DGlobal<SHAPE, 0, 1, 2>(jz, stride, status, p0, p1, csdz);
     }
 } // namespace picstep

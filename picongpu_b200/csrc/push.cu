@@ -64,12 +64,7 @@ namespace picstep
             int const lx = lc % SCX, ly = (lc / SCX) % SCY, lz = lc / (SCX * SCY);
 
             float Bf[3], Ef[3];
-#pragma unroll
-            for(int k = 0; k < 3; ++k)
-            {
-                Bf[k] = gatherComp<SHAPE, true>(tB + k * T::TV, k, lx, ly, lz, px, py, pz);
-                Ef[k] = gatherComp<SHAPE, false>(tE + k * T::TV, k, lx, ly, lz, px, py, pz);
-            }
+            gatherEB<SHAPE>(tB, tE, lx, ly, lz, px, py, pz, Ef, Bf);
             float const mass = S.mass_per_w * w;
             float const charge = S.charge_per_w * w;
             if constexpr(PUSHER == 0)
@@ -78,7 +73,7 @@ namespace picstep
                 vay(P, rc2, mass, charge, Ef, Bf, u);
             float vx, vy, vz;
             velocityOf(rc2, mass, u[0], u[1], u[2], vx, vy, vz);
-            float np[3] = {px + (vx * P.dt) / P.cell[0], py + (vy * P.dt) / P.cell[1], pz + (vz * P.dt) / P.cell[2]};
+            float np[3] = {px + ps_div(vx * P.dt, P.cell[0]), py + ps_div(vy * P.dt, P.cell[1]), pz + ps_div(vz * P.dt, P.cell[2])};
 
             // moveParticle (MoveParticle.hpp:48-160): wrap to [0,1) with the +-0.5 shift trick, cell crossing
             int dir[3];
@@ -226,11 +221,13 @@ namespace picstep
             float const px = S.pos[0][i], py = S.pos[1][i], pz = S.pos[2][i];
             int const lc = S.cell[i];
             int const lx = lc % SCX, ly = (lc / SCX) % SCY, lz = lc / (SCX * SCY);
+            float Ef[3], Bf[3];
+            gatherEB<SHAPE>(tile, tile + 3 * T::TV, lx, ly, lz, px, py, pz, Ef, Bf);
 #pragma unroll
             for(int k = 0; k < 3; ++k)
             {
-                out[(long long) k * np + i] = gatherComp<SHAPE, false>(tile + (3 + k) * T::TV, k, lx, ly, lz, px, py, pz);
-                out[(long long) (3 + k) * np + i] = gatherComp<SHAPE, true>(tile + k * T::TV, k, lx, ly, lz, px, py, pz);
+                out[(long long) k * np + i] = Ef[k];
+                out[(long long) (3 + k) * np + i] = Bf[k];
             }
         }
     }

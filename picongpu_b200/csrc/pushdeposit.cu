@@ -121,9 +121,13 @@ namespace picstep
         int const comp = p2active ? (g >> 2) : 0;
         int const ah = (g >> 1) & 1, bh = g & 1;
         int const ai = (comp + 1) % 3, aj = (comp + 2) % 3; // Jx: (i,j) = (y,z); Jy: (z,x); Jz: (x,y)
+        // a lane reads {S0,DS} of axis i at nodes 2ah,2ah+1, {P,Q} of axis j at nodes 2bh,2bh+1 and C of its component;
+        // the three addresses share one base register: rec + {0, offPQ - offSD, offC - offSD}
         int const offSD = ai * C::AXW + 4 * ah;
         int const offPQ = aj * C::AXW + 8 + 4 * bh;
         int const offC = comp * C::AXW + 16;
+        float const* const recLane = myRecs;
+        float const* const recZero = myRecs + 32 * C::RECW;
         auto strideOf = [](int a) { return a == 0 ? 1 : (a == 1 ? C::PX : C::PX * C::PY); };
         int const sC = strideOf(comp), sJ = strideOf(aj);
         int const laneTile = comp * C::PV + (2 * ah + slot) * strideOf(ai) + 2 * bh * sJ;
@@ -138,7 +142,6 @@ namespace picstep
                     acc[a][b][k] = 0.0f;
 
         int curCell = -1; // local cell index (0..255) the accumulators belong to
-        uint32_t stayCount = 0; // FUSED: particles of curCell that stay in their cell
 
         // adds the accumulators to the private tile and clears them
         auto flushCell = [&]()
@@ -159,12 +162,6 @@ namespace picstep
                     acc[0][b][k] = 0.0f;
                     acc[1][b][k] = 0.0f;
                 }
-            if constexpr(FUSED)
-            {
-                if(lane == 0 && stayCount)
-                    atomicAdd(&cellCnt[sc * SCVOL + curCell], stayCount);
-                stayCount = 0;
-            }
         };
 
         uint32_t const pBeg = cellOff[sc * SCVOL + warp * C::CELLS_PER_WARP];
@@ -194,12 +191,7 @@ namespace picstep
                 if constexpr(FUSED)
                 {
                     float Bf[3], Ef[3];
-#pragma unroll
-                    for(int k = 0; k < 3; ++k)
-                    {
-                        Bf[k] = gatherComp<SHAPE, true>(tB + k * T::TV, k, lx, ly, lz, x1[0], x1[1], x1[2]);
-                        Ef[k] = gatherComp<SHAPE, false>(tE + k * T::TV, k, lx, ly, lz, x1[0], x1[1], x1[2]);
-                    }
+                    gatherEB<SHAPE>(tB, tE, lx, ly, lz, x1[0], x1[1], x1[2], Ef, Bf);
                     if constexpr(PUSHER == 0)
                         boris(P, mass, charge, Ef, Bf, u);
                     else
@@ -209,7 +201,7 @@ namespace picstep
 #pragma unroll
                     for(int d = 0; d < 3; ++d)
                     {
-                        float q = (x1[d] + (vel[d] * P.dt) / P.cell[d]) - 0.5f;
+                        float q = (x1[d] + ps_div(vel[d] * P.dt, P.cell[d])) - 0.5f;
                         float mv = 0.0f;
                         if(q < -0.5f)
                             mv = -1.0f;
@@ -221,45 +213,54 @@ namespace picstep
                         S.pos[d][i] = x1[d];
                         S.mom[d][i] = u[d];
                     }
-                    // re-sort key (see pushKernel)
+                    // re-sort key (see pushKernel); fast path: the particle stays inside this supercell
                     int const nl[3] = {lx + dir[0], ly + dir[1], lz + dir[2]};
-                    int gc[3] = {scx * SCX + nl[0], scy * SCY + nl[1], scz * SCZ + nl[2]};
-                    uint32_t flag = 0u;
-                    bool drop = false;
-#pragma unroll
-                    for(int d = 0; d < 3; ++d)
-                    {
-                        if(gc[d] < 0 || gc[d] >= P.n[d])
-                        {
-                            bool const up = gc[d] >= P.n[d];
-                            if(P.wrap[d])
-                                gc[d] += up ? -P.n[d] : P.n[d];
-                            else if(d == P.split_axis && (up ? P.has_upper : P.has_lower))
-                            {
-                                flag = KEY_LEAVE | (up ? KEY_UPPER : 0u);
-                                gc[d] += up ? -P.n[d] : P.n[d]; // coordinate in the receiver's local grid
-                            }
-                            else
-                                drop = true;
-                        }
-                    }
                     uint32_t k;
-                    if(drop)
+                    if(unsigned(nl[0]) < unsigned(SCX) && unsigned(nl[1]) < unsigned(SCY) && unsigned(nl[2]) < unsigned(SCZ))
                     {
-                        k = KEY_DROP;
-                        deposit = false; // absorbed particles are deleted before the current deposition
+                        k = uint32_t(sc) * SCVOL + uint32_t(nl[0] + SCX * (nl[1] + SCY * nl[2]));
+                        if((dir[0] | dir[1] | dir[2]) == 0)
+                            stays = true; // counted once per run of equal cells, see below
+                        else
+                            atomicAdd(&cellCnt[k], 1u);
                     }
                     else
                     {
-                        int const dsc = (gc[0] >> 3) + P.nsc[0] * ((gc[1] >> 3) + P.nsc[1] * (gc[2] >> 2));
-                        int const dlc = (gc[0] & 7) + SCX * ((gc[1] & 7) + SCY * (gc[2] & 3));
-                        k = uint32_t(dsc) * SCVOL + uint32_t(dlc);
-                        if(flag)
-                            k |= flag;
-                        else if((dir[0] | dir[1] | dir[2]) == 0)
-                            stays = true; // counted per cell by ballot in phase 2
+                        int gc[3] = {scx * SCX + nl[0], scy * SCY + nl[1], scz * SCZ + nl[2]};
+                        uint32_t flag = 0u;
+                        bool drop = false;
+#pragma unroll
+                        for(int d = 0; d < 3; ++d)
+                        {
+                            if(gc[d] < 0 || gc[d] >= P.n[d])
+                            {
+                                bool const up = gc[d] >= P.n[d];
+                                if(P.wrap[d])
+                                    gc[d] += up ? -P.n[d] : P.n[d];
+                                else if(d == P.split_axis && (up ? P.has_upper : P.has_lower))
+                                {
+                                    flag = KEY_LEAVE | (up ? KEY_UPPER : 0u);
+                                    gc[d] += up ? -P.n[d] : P.n[d]; // coordinate in the receiver's local grid
+                                }
+                                else
+                                    drop = true;
+                            }
+                        }
+                        if(drop)
+                        {
+                            k = KEY_DROP;
+                            deposit = false; // absorbed particles are deleted before the current deposition
+                        }
                         else
-                            atomicAdd(&cellCnt[k], 1u);
+                        {
+                            int const dsc = (gc[0] >> 3) + P.nsc[0] * ((gc[1] >> 3) + P.nsc[1] * (gc[2] >> 2));
+                            int const dlc = (gc[0] & 7) + SCX * ((gc[1] & 7) + SCY * (gc[2] & 3));
+                            k = uint32_t(dsc) * SCVOL + uint32_t(dlc);
+                            if(flag)
+                                k |= flag;
+                            else
+                                atomicAdd(&cellCnt[k], 1u);
+                        }
                     }
                     key[i] = k;
                 }
@@ -276,7 +277,7 @@ namespace picstep
 #pragma unroll
                     for(int d = 0; d < 3; ++d)
                     {
-                        float const dp = vel[d] * P.dt / P.cell[d];
+                        float const dp = ps_div(vel[d] * P.dt, P.cell[d]);
                         float const xe = x1[d], xs = xe - dp;
                         int iS, iE;
                         relay<even>(iS, iE, xs, xe);
@@ -338,47 +339,57 @@ namespace picstep
                     else
                     {
                         // wide trajectory: reference loop with global atomics, in the frame of the particle's new cell
-                        long long const strideG[3] = {1, P.N[0], (long long) P.N[0] * P.N[1]};
                         int const baseG[3]
                             = {scx * SCX + P.g[0] + lx + dir[0] + gs3[0], scy * SCY + P.g[1] + ly + dir[1] + gs3[1], scz * SCZ + P.g[2] + lz + dir[2] + gs3[2]};
                         long long const origin = fidx(P, baseG[0], baseG[1], baseG[2]);
-                        esirkepov1DGlobal<SHAPE, 1, 2, 0>(J.c[0] + origin, strideG, status, p0, p1, csd * P.cell[0]);
-                        esirkepov1DGlobal<SHAPE, 2, 0, 1>(J.c[1] + origin, strideG, status, p0, p1, csd * P.cell[1]);
-                        esirkepov1DGlobal<SHAPE, 0, 1, 2>(J.c[2] + origin, strideG, status, p0, p1, csd * P.cell[2]);
+                        esirkepovParticleGlobal<SHAPE>(J.c[0] + origin, J.c[1] + origin, J.c[2] + origin, P.N[0], (long long) P.N[0] * P.N[1], status[0] | (status[1] << 3) | (status[2] << 6), p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], csd * P.cell[0], csd * P.cell[1], csd * P.cell[2]);
                     }
                 }
             }
-            // ---- phase 2: segments of equal cell, two records per pass ----------------------------------------------
+            // ---- phase 2: runs of equal cell, two records per pass ------------------------------------------------
             uint32_t const validMask = __ballot_sync(FULL, valid);
             int const n = __popc(validMask);
             uint32_t const useMask = __ballot_sync(FULL, useRec);
-            uint32_t const stayMask = FUSED ? __ballot_sync(FULL, stays) : 0u;
             int prev = __shfl_up_sync(FULL, lc, 1);
             if(lane == 0)
                 prev = curCell;
-            uint32_t const startMask = __ballot_sync(FULL, valid && lc != prev);
-            __syncwarp(); // records are visible
-            int r = 0;
-            while(r < n)
+            uint32_t const startMask = __ballot_sync(FULL, valid && lc != prev); // a new cell starts at this record
+            // end of the run of equal cells that contains record x
+            auto runEnd = [&](int x)
             {
-                uint32_t const later = r < 31 ? (startMask & (0xfffffffeu << r)) : 0u;
-                int const e = later ? __ffs(later) - 1 : n;
+                uint32_t const later = x < 31 ? (startMask & (0xfffffffeu << x)) : 0u;
+                return later ? __ffs(later) - 1 : n;
+            };
+            if constexpr(FUSED)
+            {
+                // re-sort histogram: particles that stay in their cell are counted once per run by its first stayer
+                uint32_t const stayMask = __ballot_sync(FULL, stays);
+                if(stays)
+                {
+                    uint32_t const below = (startMask | 1u) & (FULL >> (31 - lane));
+                    int const rs = 31 - __clz(below), re = runEnd(lane);
+                    uint32_t const run = (re < 32 ? ((1u << re) - 1u) : FULL) & ~((1u << rs) - 1u);
+                    uint32_t const st = stayMask & run;
+                    if((st & ((1u << lane) - 1u)) == 0u)
+                        atomicAdd(&cellCnt[sc * SCVOL + lc], uint32_t(__popc(st)));
+                }
+            }
+            __syncwarp(); // records are visible
+            for(int r = 0; r < n;)
+            {
+                int const e = runEnd(r);
                 if((startMask >> r) & 1u)
                 {
                     if(curCell >= 0)
                         flushCell();
                     curCell = __shfl_sync(FULL, lc, r);
                 }
-                if constexpr(FUSED)
-                {
-                    uint32_t const seg = (e < 32 ? ((1u << e) - 1u) : FULL) & ~((1u << r) - 1u);
-                    stayCount += __popc(stayMask & seg);
-                }
+                // records of this run that phase 2 has to add, as a bit mask seen from this lane's slot
+                uint32_t const runUse = (useMask & (e < 32 ? ((1u << e) - 1u) : FULL)) >> slot;
+#pragma unroll 1
                 for(int q = r; q < e; q += 2)
                 {
-                    int const idx = q + slot;
-                    bool const use = idx < e && ((useMask >> idx) & 1u);
-                    float const* rec = myRecs + (use ? idx : 32) * C::RECW;
+                    float const* rec = ((runUse >> q) & 1u) ? recLane + (q + slot) * C::RECW : recZero;
                     float4 const sd = *reinterpret_cast<float4 const*>(rec + offSD);
                     float4 const pq = *reinterpret_cast<float4 const*>(rec + offPQ);
                     float4 const c4 = *reinterpret_cast<float4 const*>(rec + offC);

@@ -80,6 +80,86 @@ namespace picstep
         return rz;
     }
 
+    /** All six components at once.  Production build: the components are interpolated in the pairs (B_c, E_c),
+     * whose Yee staggers are complementary on every axis, with packed FFMA2 — the weights of the un-staggered and the
+     * staggered frame of an axis are evaluated together as the register pairs {u,s} and {s,u}.  Same operations per
+     * component as gatherComp (x innermost), half the issue slots.  Exact build: gatherComp per component. */
+    template<int SHAPE>
+    __device__ __forceinline__ void gatherEB(float const* __restrict__ tB, float const* __restrict__ tE, int lx, int ly, int lz, float px, float py, float pz, float Ef[3], float Bf[3])
+    {
+        using S = Shape<SHAPE>;
+        using T = Tile<SHAPE>;
+#ifdef PICSTEP_EXACT
+#pragma unroll
+        for(int k = 0; k < 3; ++k)
+        {
+            Bf[k] = gatherComp<SHAPE, true>(tB + k * T::TV, k, lx, ly, lz, px, py, pz);
+            Ef[k] = gatherComp<SHAPE, false>(tE + k * T::TV, k, lx, ly, lz, px, py, pz);
+        }
+#else
+        constexpr bool even = (S::SUPP % 2) == 0;
+        constexpr int begin = -S::SUPP / 2 + (S::SUPP + 1) % 2;
+        float const p[3] = {px, py, pz};
+        int const l[3] = {lx, ly, lz};
+        F2 wUS[3][S::SUPP], wSU[3][S::SUPP];
+        int bU[3], bS[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+        {
+            float const vu = p[d] - 0.0f - 0.5f, vs = p[d] - 0.5f - 0.5f;
+            int shu, shs;
+            if constexpr(even)
+            {
+                shu = vu >= -0.5f ? 0 : -1;
+                shs = vs >= -0.5f ? 0 : -1;
+            }
+            else
+            {
+                shu = vu >= 0.0f ? 1 : 0;
+                shs = vs >= 0.0f ? 1 : 0;
+            }
+            float const qu = vu - float(shu) + 0.5f, qs = vs - float(shs) + 0.5f;
+            bU[d] = shu + l[d] + T::LO + begin;
+            bS[d] = shs + l[d] + T::LO + begin;
+            S::on(F2(qu, qs), wUS[d]);
+            S::on(F2(qs, qu), wSU[d]);
+        }
+#pragma unroll
+        for(int c = 0; c < 3; ++c)
+        {
+            // B_c is staggered on the axes != c, E_c on axis c: pair {B,E} uses {u,s} weights on axis c, {s,u} elsewhere
+            int const bx = c == 0 ? bU[0] : bS[0], by = c == 1 ? bU[1] : bS[1], bz = c == 2 ? bU[2] : bS[2];
+            int const ex = c == 0 ? bS[0] : bU[0], ey = c == 1 ? bS[1] : bU[1], ez = c == 2 ? bS[2] : bU[2];
+            float const* __restrict__ pb = tB + c * T::TV + (bz * T::TY + by) * T::PX + bx;
+            float const* __restrict__ pe = tE + c * T::TV + (ez * T::TY + ey) * T::PX + ex;
+            F2 const* wx = c == 0 ? wUS[0] : wSU[0];
+            F2 const* wy = c == 1 ? wUS[1] : wSU[1];
+            F2 const* wz = c == 2 ? wUS[2] : wSU[2];
+            F2 rz(0.0f);
+#pragma unroll
+            for(int z = 0; z < S::SUPP; ++z)
+            {
+                F2 ry(0.0f);
+#pragma unroll
+                for(int y = 0; y < S::SUPP; ++y)
+                {
+                    F2 rx(0.0f);
+#pragma unroll
+                    for(int x = 0; x < S::SUPP; ++x)
+                    {
+                        int const o = (z * T::TY + y) * T::PX + x;
+                        rx = fma2(F2(pb[o], pe[o]), wx[x], rx);
+                    }
+                    ry = fma2(rx, wy[y], ry);
+                }
+                rz = fma2(ry, wz[z], rz);
+            }
+            Bf[c] = rz.x;
+            Ef[c] = rz.y;
+        }
+#endif
+    }
+
     __device__ __forceinline__ float norm2(float x, float y, float z)
     {
         float t = x * x;
@@ -92,8 +172,8 @@ namespace picstep
     __device__ __forceinline__ float gammaOf(float c, float ux, float uy, float uz, float mass)
     {
         float const c2 = c * c;
-        float const r = 1.0f / (mass * mass * c2);
-        return sqrtf(1.0f + norm2(ux, uy, uz) * r);
+        float const r = ps_div(1.0f, mass * mass * c2);
+        return ps_sqrt(1.0f + norm2(ux, uy, uz) * r);
     }
 
     // Velocity.hpp:28-38: v = p * rsqrt(m^2 + p^2/c^2)
@@ -108,17 +188,17 @@ namespace picstep
     // particlePusherBoris.hpp:42-91
     __device__ __forceinline__ void boris(DevParams const& P, float mass, float charge, float const E[3], float const B[3], float u[3])
     {
-        float const QoM = charge / mass;
+        float const QoM = ps_div(charge, mass);
         float const dt = P.dt;
         float m[3], t[3];
 #pragma unroll
         for(int d = 0; d < 3; ++d)
             m[d] = u[d] + 0.5f * charge * E[d] * dt;
-        float const gr = 1.0f / gammaOf(P.c, m[0], m[1], m[2], mass);
+        float const gr = ps_div(1.0f, gammaOf(P.c, m[0], m[1], m[2], mass));
 #pragma unroll
         for(int d = 0; d < 3; ++d)
             t[d] = 0.5f * QoM * B[d] * gr * dt;
-        float const sf = 1.0f / (1.0f + norm2(t[0], t[1], t[2]));
+        float const sf = ps_div(1.0f, 1.0f + norm2(t[0], t[1], t[2]));
         float s[3];
 #pragma unroll
         for(int d = 0; d < 3; ++d)
@@ -171,7 +251,7 @@ namespace picstep
 #pragma unroll
         for(int d = 0; d < 3; ++d)
             t[d] = float(tau[d] * (1.0 / gplus));
-        float const s = 1.0f / (1.0f + norm2(t[0], t[1], t[2]));
+        float const s = ps_div(1.0f, 1.0f + norm2(t[0], t[1], t[2]));
         float dp = mp[0] * t[0];
         dp += mp[1] * t[1];
         dp += mp[2] * t[2];

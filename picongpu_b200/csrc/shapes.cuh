@@ -3,51 +3,59 @@
 // computed as 1 - sum(others), e.g. TSC.hpp:85) so that the exact build reproduces the reference bit for bit.
 #pragma once
 #include "common.cuh"
+#include "f2.cuh"
 
 namespace picstep
 {
     template<int SHAPE>
     struct Shape;
 
-    // ---- polynomial pieces -------------------------------------------------------------------------------
-    __device__ __forceinline__ float tsc_inner(float a)
+    // ---- polynomial pieces (T = float or F2: two evaluations in packed registers) -------------------------------
+    template<class T>
+    __device__ __forceinline__ T tsc_inner(T a)
     {
-        float const sq = a * a;
-        return 0.75f - sq;
+        T const sq = a * a;
+        return T(0.75f) - sq;
     }
-    __device__ __forceinline__ float tsc_outer(float a)
+    template<class T>
+    __device__ __forceinline__ T tsc_outer(T a)
     {
-        float const t = 3.0f / 2.0f - a;
-        float const sq = t * t;
-        return 0.5f * sq;
+        T const t = T(3.0f / 2.0f) - a;
+        T const sq = t * t;
+        return T(0.5f) * sq;
     }
-    __device__ __forceinline__ float pqs_inner(float a)
+    template<class T>
+    __device__ __forceinline__ T pqs_inner(T a)
     {
-        float const sq = a * a;
-        float const cu = sq * a;
-        return 1.0f / 6.0f * (4.0f - 6.0f * sq + 3.0f * cu);
+        T const sq = a * a;
+        T const cu = sq * a;
+        return T(1.0f / 6.0f) * (T(4.0f) - T(6.0f) * sq + T(3.0f) * cu);
     }
-    __device__ __forceinline__ float pqs_outer(float a)
+    template<class T>
+    __device__ __forceinline__ T pqs_outer(T a)
     {
-        float const t = 2.0f - a;
-        float const cu = t * t * t;
-        return 1.0f / 6.0f * cu;
+        T const t = T(2.0f) - a;
+        T const cu = t * t * t;
+        return T(1.0f / 6.0f) * cu;
     }
-    __device__ __forceinline__ float pcs_inner(float a)
+    template<class T>
+    __device__ __forceinline__ T pcs_inner(T a)
     {
-        float const sq = a * a;
-        return 115.f / 192.f + sq * (-5.f / 8.f + 1.0f / 4.0f * sq);
+        T const sq = a * a;
+        return T(115.f / 192.f) + sq * (T(-5.f / 8.f) + T(1.0f / 4.0f) * sq);
     }
-    __device__ __forceinline__ float pcs_mid(float a)
+    template<class T>
+    __device__ __forceinline__ T pcs_mid(T a)
     {
-        return 1.f / 96.f * (55.f + 4.f * a * (5.f - 2.f * a * (15.f + 2.f * a * (-5.f + a))));
+        return T(1.f / 96.f) * (T(55.f) + T(4.f) * a * (T(5.f) - T(2.f) * a * (T(15.f) + T(2.f) * a * (T(-5.f) + a))));
     }
-    __device__ __forceinline__ float pcs_outer(float a)
+    template<class T>
+    __device__ __forceinline__ T pcs_outer(T a)
     {
-        float const t = 5.f - 2.f * a;
-        float const sq = t * t;
-        float const q = sq * sq;
-        return 1.f / 384.f * q;
+        T const t = T(5.f) - T(2.f) * a;
+        T const sq = t * t;
+        T const q = sq * sq;
+        return T(1.f / 384.f) * q;
     }
 
     // SUPP = support in cells, BEGIN = lowest grid offset.  on(x, v): values at BEGIN..BEGIN+SUPP-1 for a particle
@@ -56,18 +64,20 @@ namespace picstep
     struct Shape<0>
     {
         static constexpr int SUPP = 1, BEGIN = 0;
-        __device__ __forceinline__ static void on(float, float* v)
+        template<class T>
+        __device__ __forceinline__ static void on(T, T* v)
         {
-            v[0] = 1.0f;
+            v[0] = T(1.0f);
         }
     };
     template<>
     struct Shape<1>
     {
         static constexpr int SUPP = 2, BEGIN = 0;
-        __device__ __forceinline__ static void on(float x, float* v)
+        template<class T>
+        __device__ __forceinline__ static void on(T x, T* v)
         {
-            v[0] = 1.0f - x;
+            v[0] = T(1.0f) - x;
             v[1] = x;
         }
     };
@@ -75,36 +85,39 @@ namespace picstep
     struct Shape<2>
     {
         static constexpr int SUPP = 3, BEGIN = -1;
-        __device__ __forceinline__ static void on(float x, float* v)
+        template<class T>
+        __device__ __forceinline__ static void on(T x, T* v)
         {
-            v[0] = tsc_outer(fabsf(-1.f - x));
-            v[1] = tsc_inner(fabsf(x));
-            v[2] = 1.0f - (v[0] + v[1]);
+            v[0] = tsc_outer(absT(T(-1.f) - x));
+            v[1] = tsc_inner(absT(x));
+            v[2] = T(1.0f) - (v[0] + v[1]);
         }
     };
     template<>
     struct Shape<3>
     {
         static constexpr int SUPP = 4, BEGIN = -1;
-        __device__ __forceinline__ static void on(float x, float* v)
+        template<class T>
+        __device__ __forceinline__ static void on(T x, T* v)
         {
-            v[0] = pqs_outer(fabsf(-1.f - x));
+            v[0] = pqs_outer(absT(T(-1.f) - x));
             v[1] = pqs_inner(x);
-            v[3] = pqs_outer(2.f - x);
-            v[2] = 1.0f - (v[0] + v[1] + v[3]);
+            v[3] = pqs_outer(T(2.f) - x);
+            v[2] = T(1.0f) - (v[0] + v[1] + v[3]);
         }
     };
     template<>
     struct Shape<4>
     {
         static constexpr int SUPP = 5, BEGIN = -2;
-        __device__ __forceinline__ static void on(float x, float* v)
+        template<class T>
+        __device__ __forceinline__ static void on(T x, T* v)
         {
-            v[0] = pcs_outer(fabsf(-2.f - x));
-            v[1] = pcs_mid(fabsf(-1.f - x));
-            v[2] = pcs_inner(fabsf(x));
-            v[4] = pcs_outer(2.f - x);
-            v[3] = 1.0f - (v[0] + v[1] + v[2] + v[4]);
+            v[0] = pcs_outer(absT(T(-2.f) - x));
+            v[1] = pcs_mid(absT(T(-1.f) - x));
+            v[2] = pcs_inner(absT(x));
+            v[4] = pcs_outer(T(2.f) - x);
+            v[3] = T(1.0f) - (v[0] + v[1] + v[2] + v[4]);
         }
     };
 
