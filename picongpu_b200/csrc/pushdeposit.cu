@@ -121,13 +121,10 @@ namespace picstep
         int const comp = p2active ? (g >> 2) : 0;
         int const ah = (g >> 1) & 1, bh = g & 1;
         int const ai = (comp + 1) % 3, aj = (comp + 2) % 3; // Jx: (i,j) = (y,z); Jy: (z,x); Jz: (x,y)
-        // a lane reads {S0,DS} of axis i at nodes 2ah,2ah+1, {P,Q} of axis j at nodes 2bh,2bh+1 and C of its component;
-        // the three addresses share one base register: rec + {0, offPQ - offSD, offC - offSD}
+        // a lane reads {S0,DS} of axis i at nodes 2ah,2ah+1, {P,Q} of axis j at nodes 2bh,2bh+1 and C of its component
         int const offSD = ai * C::AXW + 4 * ah;
         int const offPQ = aj * C::AXW + 8 + 4 * bh;
         int const offC = comp * C::AXW + 16;
-        float const* const recLane = myRecs;
-        float const* const recZero = myRecs + 32 * C::RECW;
         auto strideOf = [](int a) { return a == 0 ? 1 : (a == 1 ? C::PX : C::PX * C::PY); };
         int const sC = strideOf(comp), sJ = strideOf(aj);
         int const laneTile = comp * C::PV + (2 * ah + slot) * strideOf(ai) + 2 * bh * sJ;
@@ -269,10 +266,13 @@ namespace picstep
 
                 if(deposit)
                 {
-                    // Esirkepov.hpp:84-103: both points in the frame of gridShift = min(iS,iE), off-support arrays
+                    // Esirkepov.hpp:84-103: start and end point in the frame of gridShift = min(iS,iE); the on-support
+                    // assignment values of both points are evaluated together (packed: .x start, .y end) and placed
+                    // on the window: value s of the start point sits at window index o0 + s, o0 = iS + BEGIN + WLO + dir
                     float const csd = charge * (1.0f / float(vol * P.dt));
-                    float s0[3][C::FR], s1[3][C::FR], f[3], p0[3], p1[3];
-                    int n0[3], gs3[3], status[3];
+                    F2 t[3][Sh::SUPP];
+                    float f[3], p0[3], p1[3];
+                    int o0[3], o1[3], gs3[3], status[3];
                     bool narrow = true;
 #pragma unroll
                     for(int d = 0; d < 3; ++d)
@@ -283,26 +283,25 @@ namespace picstep
                         relay<even>(iS, iE, xs, xe);
                         int const gs = iS < iE ? iS : iE;
                         float const y0 = xs - float(gs), y1 = xe - float(gs);
-                        shapeOff<SHAPE>(y0, gs != iS, s0[d]);
-                        shapeOff<SHAPE>(y1, gs != iE, s1[d]);
+                        Sh::on(F2(gs != iS ? y0 - 1.0f : y0, gs != iE ? y1 - 1.0f : y1), t[d]);
                         f[d] = (y0 == y1) ? 0.0f : -(csd * P.cell[d]);
-                        int const leave = iS != iE ? 1 : 0;
-                        n0[d] = gs + Sh::BEGIN + C::WLO + dir[d];
-                        if(n0[d] < 0 || n0[d] + Sh::SUPP - 1 + leave > C::WN - 1)
+                        o0[d] = iS + Sh::BEGIN + C::WLO + dir[d];
+                        o1[d] = iE + Sh::BEGIN + C::WLO + dir[d];
+                        if(o0[d] < 0 || o0[d] > C::NMAX0 || o1[d] < 0 || o1[d] > C::NMAX0)
                             narrow = false;
                         p0[d] = y0;
                         p1[d] = y1;
                         gs3[d] = gs;
-                        status[d] = (gs == iS ? 2 : 0) | (gs == iE ? 4 : 0) | leave;
+                        status[d] = (gs == iS ? 2 : 0) | (gs == iE ? 4 : 0) | (iS != iE ? 1 : 0);
                     }
+                    float* const rec = myRecs + lane * C::RECW;
                     if(narrow)
                     {
                         useRec = true;
-                        float* const rec = myRecs + lane * C::RECW;
 #pragma unroll
                         for(int d = 0; d < 3; ++d)
                         {
-                            float S0[C::WN], DS[C::WN];
+                            float S0[C::WN], S1[C::WN];
 #pragma unroll
                             for(int n = 0; n < C::WN; ++n)
                             {
@@ -311,28 +310,28 @@ namespace picstep
                                 for(int m = 0; m <= C::NMAX0; ++m)
                                 {
                                     int const s = n - m;
-                                    if(s >= 0 && s < C::FR)
+                                    if(s >= 0 && s < Sh::SUPP)
                                     {
-                                        v0 = (n0[d] == m) ? s0[d][s] : v0;
-                                        v1 = (n0[d] == m) ? s1[d][s] : v1;
+                                        v0 = (o0[d] == m) ? t[d][s].x : v0;
+                                        v1 = (o1[d] == m) ? t[d][s].y : v1;
                                     }
                                 }
                                 S0[n] = v0;
-                                DS[n] = v1 - v0;
+                                S1[n] = v1;
                             }
                             float4* r4 = reinterpret_cast<float4*>(rec + d * C::AXW);
-                            r4[0] = make_float4(S0[0], DS[0], S0[1], DS[1]);
-                            r4[1] = make_float4(S0[2], DS[2], S0[3], DS[3]);
-                            float Pn[C::WN], Qn[C::WN];
+                            F2 DS[2];
 #pragma unroll
-                            for(int n = 0; n < C::WN; ++n)
+                            for(int j = 0; j < 2; ++j)
                             {
-                                Pn[n] = S0[n] + 0.5f * DS[n];
-                                Qn[n] = 0.5f * S0[n] + (1.0f / 3.0f) * DS[n];
+                                F2 const s0p(S0[2 * j], S0[2 * j + 1]);
+                                DS[j] = F2(S1[2 * j], S1[2 * j + 1]) - s0p;
+                                F2 const Pp = fma2(DS[j], F2(0.5f), s0p);
+                                F2 const Qp = fma2(DS[j], F2(1.0f / 3.0f), s0p * F2(0.5f));
+                                r4[j] = make_float4(s0p.x, s0p.y, DS[j].x, DS[j].y);
+                                r4[2 + j] = make_float4(Pp.x, Pp.y, Qp.x, Qp.y);
                             }
-                            r4[2] = make_float4(Pn[0], Qn[0], Pn[1], Qn[1]);
-                            r4[3] = make_float4(Pn[2], Qn[2], Pn[3], Qn[3]);
-                            float const c0 = DS[0], c1 = c0 + DS[1], c2 = c1 + DS[2];
+                            float const c0 = DS[0].x, c1 = c0 + DS[0].y, c2 = c1 + DS[1].x;
                             r4[4] = make_float4(c0 * f[d], c1 * f[d], c2 * f[d], 0.0f);
                         }
                     }
@@ -345,11 +344,18 @@ namespace picstep
                         esirkepovParticleGlobal<SHAPE>(J.c[0] + origin, J.c[1] + origin, J.c[2] + origin, P.N[0], (long long) P.N[0] * P.N[1], status[0] | (status[1] << 3) | (status[2] << 6), p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], csd * P.cell[0], csd * P.cell[1], csd * P.cell[2]);
                     }
                 }
+                if(!useRec)
+                {
+                    // nothing to add for this particle in phase 2: C = 0 (stale S0/DS/P/Q values are finite)
+                    float* const rec = myRecs + lane * C::RECW;
+#pragma unroll
+                    for(int d = 0; d < 3; ++d)
+                        *reinterpret_cast<float4*>(rec + d * C::AXW + 16) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
             }
             // ---- phase 2: runs of equal cell, two records per pass ------------------------------------------------
             uint32_t const validMask = __ballot_sync(FULL, valid);
             int const n = __popc(validMask);
-            uint32_t const useMask = __ballot_sync(FULL, useRec);
             int prev = __shfl_up_sync(FULL, lc, 1);
             if(lane == 0)
                 prev = curCell;
@@ -384,19 +390,16 @@ namespace picstep
                         flushCell();
                     curCell = __shfl_sync(FULL, lc, r);
                 }
-                // records of this run that phase 2 has to add, as a bit mask seen from this lane's slot
-                uint32_t const runUse = (useMask & (e < 32 ? ((1u << e) - 1u) : FULL)) >> slot;
-#pragma unroll 1
-                for(int q = r; q < e; q += 2)
+                // one pass = two records (one per half warp): operands at pSD/pPQ/pC + off words
+                auto pass = [&](float const* pSD, float const* pPQ, float const* pC, int off)
                 {
-                    float const* rec = ((runUse >> q) & 1u) ? recLane + (q + slot) * C::RECW : recZero;
-                    float4 const sd = *reinterpret_cast<float4 const*>(rec + offSD);
-                    float4 const pq = *reinterpret_cast<float4 const*>(rec + offPQ);
-                    float4 const c4 = *reinterpret_cast<float4 const*>(rec + offC);
-                    float const t00 = sd.x * pq.x + sd.y * pq.y;
-                    float const t01 = sd.x * pq.z + sd.y * pq.w;
-                    float const t10 = sd.z * pq.x + sd.w * pq.y;
-                    float const t11 = sd.z * pq.z + sd.w * pq.w;
+                    float4 const sd = *reinterpret_cast<float4 const*>(pSD + off); // {S0[a0], S0[a0+1], DS[a0], DS[a0+1]}
+                    float4 const pq = *reinterpret_cast<float4 const*>(pPQ + off); // {P[b0], P[b0+1], Q[b0], Q[b0+1]}
+                    float4 const c4 = *reinterpret_cast<float4 const*>(pC + off);
+                    float const t00 = sd.x * pq.x + sd.z * pq.z;
+                    float const t01 = sd.x * pq.y + sd.z * pq.w;
+                    float const t10 = sd.y * pq.x + sd.w * pq.z;
+                    float const t11 = sd.y * pq.y + sd.w * pq.w;
                     acc[0][0][0] += c4.x * t00;
                     acc[0][0][1] += c4.y * t00;
                     acc[0][0][2] += c4.z * t00;
@@ -409,6 +412,31 @@ namespace picstep
                     acc[1][1][0] += c4.x * t11;
                     acc[1][1][1] += c4.y * t11;
                     acc[1][1][2] += c4.z * t11;
+                };
+                int const len = e - r;
+                float const* rec = myRecs + (r + slot) * C::RECW;
+                float const *pSD = rec + offSD, *pPQ = rec + offPQ, *pC = rec + offC;
+#pragma unroll 1
+                for(int it = len >> 2; it > 0; --it)
+                {
+                    pass(pSD, pPQ, pC, 0);
+                    pass(pSD, pPQ, pC, 2 * C::RECW);
+                    pSD += 4 * C::RECW;
+                    pPQ += 4 * C::RECW;
+                    pC += 4 * C::RECW;
+                }
+                if(len & 2)
+                {
+                    pass(pSD, pPQ, pC, 0);
+                    pSD += 2 * C::RECW;
+                    pPQ += 2 * C::RECW;
+                    pC += 2 * C::RECW;
+                }
+                if(len & 1)
+                {
+                    // last record of the run in slot 0; slot 1 would read the first record of the next cell
+                    float const* z = myRecs + 32 * C::RECW;
+                    pass(slot ? z + offSD : pSD, slot ? z + offPQ : pPQ, slot ? z + offC : pC, 0);
                 }
                 r = e;
             }
