@@ -19,8 +19,11 @@ namespace picstep
     cudaError_t launchDeposit(int, int, bool, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
     bool runKernelSupports(int, int);
     cudaError_t launchDepositRun(int, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
-    cudaError_t launchPushDeposit(int, int, DevParams const&, SpeciesDev const&, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, cudaStream_t);
-    cudaError_t launchScan(uint32_t const*, uint32_t*, uint32_t*, uint32_t*, int, uint32_t*, uint32_t, int*, cudaStream_t);
+    cudaError_t launchPushDeposit(int, int, DevParams const&, SpeciesDev const&, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, cudaStream_t);
+    cudaError_t launchScan(uint32_t const*, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, int, uint32_t*, uint32_t, int*, cudaStream_t);
+    cudaError_t launchScatterRanked(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t const*, cudaStream_t);
+    cudaError_t launchScatterRecordsBack(MigRecord const*, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, cudaStream_t);
+    cudaError_t launchClearRecordCounts(MigRecord const*, uint32_t, uint32_t*, cudaStream_t);
     cudaError_t launchScatter(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t*, cudaStream_t);
     cudaError_t launchCountRecords(MigRecord const*, uint32_t, uint32_t*, cudaStream_t);
     cudaError_t launchScatterRecords(MigRecord const*, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, cudaStream_t);
@@ -60,7 +63,10 @@ namespace picstep
         int cur = 0;
         uint32_t* key = nullptr;
         uint32_t* cellOff[2] = {};
-        uint32_t* cellCnt = nullptr;
+        uint32_t* cellCnt = nullptr; // per destination cell: histogram of the re-sort keys (ranked mode: arrivals only)
+        uint32_t* stayCnt = nullptr; // per cell: particles that stay (written by the fused kernel, zero otherwise)
+        uint32_t* rank = nullptr; // per particle: slot inside the destination cell (fused kernel)
+        bool ranked = false; // key/rank/stayCnt come from the fused kernel -> atomics-free scatter
         uint32_t *scSum = nullptr, *scOff = nullptr;
         uint32_t* nDev = nullptr; // [2], indexed like cur
         uint32_t nUpper = 0; // host side upper bound of the particle count
@@ -181,6 +187,8 @@ namespace
         }
         cudaFree(s.key);
         s.key = nullptr;
+        cudaFree(s.rank);
+        s.rank = nullptr;
         cudaFree(s.sendLo);
         cudaFree(s.sendHi);
         cudaFree(s.recvLo);
@@ -203,6 +211,7 @@ namespace
             CU(c, cudaMalloc(&s.cell[b], sizeof(uint16_t) * capacity));
         }
         CU(c, cudaMalloc(&s.key, sizeof(uint32_t) * capacity));
+        CU(c, cudaMalloc(&s.rank, sizeof(uint32_t) * capacity));
         if(c->P.split_axis >= 0)
         {
             // exchange capacity: particles of one border supercell layer could at most all leave; reserve a
@@ -388,12 +397,33 @@ namespace
             KL(c, 1, launchCountRecords(s.recvLo, nRecLo, s.cellCnt, c->stream));
         if(nRecHi)
             KL(c, 1, launchCountRecords(s.recvHi, nRecHi, s.cellCnt, c->stream));
-        KL(c, 3, launchScan(s.cellCnt, s.scSum, s.scOff, s.cellOff[nxt], nscTot, s.nDev + nxt, uint32_t(s.capacity), c->flags, c->stream));
-        KL(c, 1, launchScatter(devOf(c, s, s.cur), devOf(c, s, nxt), s.key, s.nDev + s.cur, s.nUpper, s.cellOff[nxt], s.cellCnt, c->stream));
-        if(nRecLo)
-            KL(c, 1, launchScatterRecords(s.recvLo, nRecLo, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
-        if(nRecHi)
-            KL(c, 1, launchScatterRecords(s.recvHi, nRecHi, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+        KL(c, 3, launchScan(s.cellCnt, s.stayCnt, s.scSum, s.scOff, s.cellOff[nxt], nscTot, s.nDev + nxt, uint32_t(s.capacity), c->flags, c->stream));
+        if(s.ranked)
+        {
+            // slots were assigned by the fused kernel: streaming permutation, then reset both histograms
+            size_t const cntBytes = sizeof(uint32_t) * size_t(nscTot) * SCVOL;
+            KL(c, 1, launchScatterRanked(devOf(c, s, s.cur), devOf(c, s, nxt), s.key, s.rank, s.nDev + s.cur, s.nUpper, s.cellOff[nxt], s.stayCnt, c->stream));
+            CU(c, cudaMemsetAsync(s.cellCnt, 0, cntBytes, c->stream));
+            CU(c, cudaMemsetAsync(s.stayCnt, 0, cntBytes, c->stream));
+            c->launches += 2;
+            if(nRecLo)
+                KL(c, 1, launchScatterRecordsBack(s.recvLo, nRecLo, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+            if(nRecHi)
+                KL(c, 1, launchScatterRecordsBack(s.recvHi, nRecHi, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+            if(nRecLo)
+                KL(c, 1, launchClearRecordCounts(s.recvLo, nRecLo, s.cellCnt, c->stream));
+            if(nRecHi)
+                KL(c, 1, launchClearRecordCounts(s.recvHi, nRecHi, s.cellCnt, c->stream));
+            s.ranked = false;
+        }
+        else
+        {
+            KL(c, 1, launchScatter(devOf(c, s, s.cur), devOf(c, s, nxt), s.key, s.nDev + s.cur, s.nUpper, s.cellOff[nxt], s.cellCnt, c->stream));
+            if(nRecLo)
+                KL(c, 1, launchScatterRecords(s.recvLo, nRecLo, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+            if(nRecHi)
+                KL(c, 1, launchScatterRecords(s.recvHi, nRecHi, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+        }
         s.cur = nxt;
         s.nUpper = uint32_t(std::min<int64_t>(s.capacity, int64_t(s.nUpper) + nRecLo + nRecHi));
         return PICSTEP_OK;
@@ -590,6 +620,7 @@ extern "C"
             cudaFree(s.cellOff[0]);
             cudaFree(s.cellOff[1]);
             cudaFree(s.cellCnt);
+            cudaFree(s.stayCnt);
             cudaFree(s.scSum);
             cudaFree(s.scOff);
             cudaFree(s.nDev);
@@ -638,6 +669,8 @@ extern "C"
         }
         CU(c, cudaMalloc(&s.cellCnt, sizeof(uint32_t) * ncell));
         CU(c, cudaMemsetAsync(s.cellCnt, 0, sizeof(uint32_t) * ncell, c->stream));
+        CU(c, cudaMalloc(&s.stayCnt, sizeof(uint32_t) * ncell));
+        CU(c, cudaMemsetAsync(s.stayCnt, 0, sizeof(uint32_t) * ncell, c->stream));
         CU(c, cudaMalloc(&s.scSum, sizeof(uint32_t) * nsc));
         CU(c, cudaMalloc(&s.scOff, sizeof(uint32_t) * (nsc + 1)));
         CU(c, cudaMalloc(&s.nDev, sizeof(uint32_t) * 2));
@@ -728,6 +761,7 @@ extern "C"
         // the int32 host cell indices travel through the (not yet used) key array of the active buffer's pos.x
         int32_t* cellIn = reinterpret_cast<int32_t*>(s.attr[s.cur][0]);
         CU(c, cudaMemcpyAsync(cellIn, cell, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        s.ranked = false;
         KL(c, 1, launchKeysFromCells(c->P, cellIn, n32, s.key, s.cellCnt, c->flags + 1, c->stream));
         s.cur = stage; // resortSpecies reads from `cur` and writes to the other one
         s.nUpper = n32;
@@ -872,6 +906,7 @@ extern "C"
         SpeciesHost& s = c->species[sp];
         if(s.capacity == 0)
             return PICSTEP_OK;
+        s.ranked = false;
         KL(c, 1, launchPush(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], s.cellCnt, s.key, c->stream));
         return PICSTEP_OK;
     }
@@ -955,7 +990,8 @@ extern "C"
         SpeciesHost& s = c->species[sp];
         if(s.capacity == 0)
             return PICSTEP_OK;
-        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.key, c->stream));
+        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, c->stream));
+        s.ranked = true;
         return PICSTEP_OK;
     }
 

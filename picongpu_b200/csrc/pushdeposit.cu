@@ -66,8 +66,10 @@ namespace picstep
         Field3 B,
         Field3 J,
         uint32_t const* __restrict__ cellOff,
-        uint32_t* __restrict__ cellCnt,
-        uint32_t* __restrict__ key)
+        uint32_t* __restrict__ cellCnt, // FUSED: per destination cell, number of particles arriving from other cells
+        uint32_t* __restrict__ stayCnt, // FUSED: per cell, number of particles that stay in it
+        uint32_t* __restrict__ key, // FUSED: destination supercell * 256 + cell (+ leave flags)
+        uint32_t* __restrict__ rank) // FUSED: slot inside the destination cell: stayers first, then arrivals (bit 31)
     {
         using Sh = Shape<SHAPE>;
         using C = RunCfg<SHAPE>;
@@ -139,6 +141,7 @@ namespace picstep
                     acc[a][b][k] = 0.0f;
 
         int curCell = -1; // local cell index (0..255) the accumulators belong to
+        uint32_t stayBase = 0; // FUSED: stayers of curCell seen so far (their rank in the re-sorted cell run)
 
         // adds the accumulators to the private tile and clears them
         auto flushCell = [&]()
@@ -171,6 +174,7 @@ namespace picstep
             int lc = -2;
             bool useRec = false; // this lane wrote a record phase 2 has to add
             bool stays = false;
+            uint32_t myRank = 0;
             __syncwarp(); // phase 2 of the previous chunk has finished reading the records
             // ---- phase 1: lane = particle -----------------------------------------------------------------------
             if(valid)
@@ -217,9 +221,9 @@ namespace picstep
                     {
                         k = uint32_t(sc) * SCVOL + uint32_t(nl[0] + SCX * (nl[1] + SCY * nl[2]));
                         if((dir[0] | dir[1] | dir[2]) == 0)
-                            stays = true; // counted once per run of equal cells, see below
+                            stays = true; // ranked per run of equal cells in phase 2
                         else
-                            atomicAdd(&cellCnt[k], 1u);
+                            myRank = 0x80000000u | atomicAdd(&cellCnt[k], 1u);
                     }
                     else
                     {
@@ -256,7 +260,7 @@ namespace picstep
                             if(flag)
                                 k |= flag;
                             else
-                                atomicAdd(&cellCnt[k], 1u);
+                                myRank = 0x80000000u | atomicAdd(&cellCnt[k], 1u);
                         }
                     }
                     key[i] = k;
@@ -366,20 +370,7 @@ namespace picstep
                 uint32_t const later = x < 31 ? (startMask & (0xfffffffeu << x)) : 0u;
                 return later ? __ffs(later) - 1 : n;
             };
-            if constexpr(FUSED)
-            {
-                // re-sort histogram: particles that stay in their cell are counted once per run by its first stayer
-                uint32_t const stayMask = __ballot_sync(FULL, stays);
-                if(stays)
-                {
-                    uint32_t const below = (startMask | 1u) & (FULL >> (31 - lane));
-                    int const rs = 31 - __clz(below), re = runEnd(lane);
-                    uint32_t const run = (re < 32 ? ((1u << re) - 1u) : FULL) & ~((1u << rs) - 1u);
-                    uint32_t const st = stayMask & run;
-                    if((st & ((1u << lane) - 1u)) == 0u)
-                        atomicAdd(&cellCnt[sc * SCVOL + lc], uint32_t(__popc(st)));
-                }
-            }
+            uint32_t const stayMask = FUSED ? __ballot_sync(FULL, stays) : 0u;
             __syncwarp(); // records are visible
             for(int r = 0; r < n;)
             {
@@ -387,8 +378,21 @@ namespace picstep
                 if((startMask >> r) & 1u)
                 {
                     if(curCell >= 0)
+                    {
                         flushCell();
+                        if(FUSED && lane == 0)
+                            stayCnt[sc * SCVOL + curCell] = stayBase;
+                    }
+                    stayBase = 0;
                     curCell = __shfl_sync(FULL, lc, r);
+                }
+                if constexpr(FUSED)
+                {
+                    // stayers keep their relative order: rank = stayers of this cell before me
+                    uint32_t const st = stayMask & (e < 32 ? ((1u << e) - 1u) : FULL) & ~((1u << r) - 1u);
+                    if(stays && lane >= r && lane < e)
+                        myRank = stayBase + __popc(st & ((1u << lane) - 1u));
+                    stayBase += __popc(st);
                 }
                 // one pass = two records (one per half warp): operands at pSD/pPQ/pC + off words
                 auto pass = [&](float const* pSD, float const* pPQ, float const* pC, int off)
@@ -440,9 +444,15 @@ namespace picstep
                 }
                 r = e;
             }
+            if(FUSED && valid)
+                rank[i] = myRank;
         }
         if(curCell >= 0)
+        {
             flushCell();
+            if(FUSED && lane == 0)
+                stayCnt[sc * SCVOL + curCell] = stayBase;
+        }
         __syncthreads();
         // ---- combine the warp-private tiles and flush once to global J (red.global.add.f32) --------------------------
         {
@@ -475,14 +485,14 @@ namespace picstep
     }
 
     template<int SHAPE, int PUSHER, bool FUSED>
-    cudaError_t launchRunT(DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* key, cudaStream_t st)
+    cudaError_t launchRunT(DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, cudaStream_t st)
     {
         int const nscTot = P.nsc[0] * P.nsc[1] * P.nsc[2];
         constexpr size_t smem = runSmemBytes<SHAPE, FUSED>();
         cudaError_t e = cudaFuncSetAttribute(runKernel<SHAPE, PUSHER, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if(e != cudaSuccess)
             return e;
-        runKernel<SHAPE, PUSHER, FUSED><<<nscTot, 256, smem, st>>>(P, S, E, B, J, cellOff, cellCnt, key);
+        runKernel<SHAPE, PUSHER, FUSED><<<nscTot, 256, smem, st>>>(P, S, E, B, J, cellOff, cellCnt, stayCnt, key, rank);
         return cudaGetLastError();
     }
 
@@ -497,7 +507,7 @@ namespace picstep
         Field3 none{};
 #define PS_CASE(SH)                                                                                                   \
     if(shape == SH)                                                                                                   \
-        return launchRunT<SH, 0, false>(P, S, none, none, J, cellOff, nullptr, nullptr, st);
+        return launchRunT<SH, 0, false>(P, S, none, none, J, cellOff, nullptr, nullptr, nullptr, nullptr, st);
         PS_CASE(0)
         PS_CASE(1)
         PS_CASE(2)
@@ -507,11 +517,11 @@ namespace picstep
     }
 
     /** fused gather + push + move + deposit of one species (picstep_step fast path) */
-    cudaError_t launchPushDeposit(int shape, int pusher, DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* key, cudaStream_t st)
+    cudaError_t launchPushDeposit(int shape, int pusher, DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, cudaStream_t st)
     {
 #define PS_CASE(SH, PU)                                                                                               \
     if(shape == SH && pusher == PU)                                                                                   \
-        return launchRunT<SH, PU, true>(P, S, E, B, J, cellOff, cellCnt, key, st);
+        return launchRunT<SH, PU, true>(P, S, E, B, J, cellOff, cellCnt, stayCnt, key, rank, st);
         PS_CASE(0, 0)
         PS_CASE(1, 0)
         PS_CASE(2, 0)

@@ -13,10 +13,11 @@ namespace picstep
 {
     // ---- two level exclusive scan over cell counts --------------------------------------------------------------
     // level 1: one CTA per supercell sums its 256 cell counters
-    __global__ void __launch_bounds__(256) supercellSumKernel(uint32_t const* __restrict__ cnt, uint32_t* __restrict__ scSum)
+    // (cnt2: second histogram that is added in, e.g. the stayers of the fused push kernel; all zero otherwise)
+    __global__ void __launch_bounds__(256) supercellSumKernel(uint32_t const* __restrict__ cnt, uint32_t const* __restrict__ cnt2, uint32_t* __restrict__ scSum)
     {
         __shared__ uint32_t ws[8];
-        uint32_t v = cnt[blockIdx.x * SCVOL + threadIdx.x];
+        uint32_t v = cnt[blockIdx.x * SCVOL + threadIdx.x] + cnt2[blockIdx.x * SCVOL + threadIdx.x];
 #pragma unroll
         for(int o = 16; o > 0; o >>= 1)
             v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -88,10 +89,10 @@ namespace picstep
     }
 
     // level 3: per supercell exclusive scan of its 256 counters + supercell base
-    __global__ void __launch_bounds__(256) cellScanKernel(uint32_t const* __restrict__ cnt, uint32_t const* __restrict__ scOff, uint32_t* __restrict__ cellOff, int nsc)
+    __global__ void __launch_bounds__(256) cellScanKernel(uint32_t const* __restrict__ cnt, uint32_t const* __restrict__ cnt2, uint32_t const* __restrict__ scOff, uint32_t* __restrict__ cellOff, int nsc)
     {
         __shared__ uint32_t ws[8];
-        uint32_t const v = cnt[blockIdx.x * SCVOL + threadIdx.x];
+        uint32_t const v = cnt[blockIdx.x * SCVOL + threadIdx.x] + cnt2[blockIdx.x * SCVOL + threadIdx.x];
         uint32_t x = v;
 #pragma unroll
         for(int o = 1; o < 32; o <<= 1)
@@ -162,6 +163,88 @@ namespace picstep
                 dst.cell[d] = uint16_t(k & (SCVOL - 1));
             }
         }
+    }
+
+    // Ranked scatter (after the fused push+deposit kernel): every particle already knows its slot inside the
+    // destination cell -- stayers keep their order (rank), arrivals follow them (bit 31: rank among the arrivals) --
+    // so the permutation needs no atomics and no inter-thread communication: pure streaming with UNROLL
+    // independent particles per thread in flight.
+    template<int UNROLL>
+    __global__ void __launch_bounds__(256) scatterRankedKernel(
+        SpeciesDev src,
+        SpeciesDev dst,
+        uint32_t const* __restrict__ key,
+        uint32_t const* __restrict__ rank,
+        uint32_t const* __restrict__ nOld,
+        uint32_t const* __restrict__ newOff,
+        uint32_t const* __restrict__ stayCnt)
+    {
+        uint32_t const n = *nOld;
+        for(uint32_t base = blockIdx.x * (256u * UNROLL); base < n; base += gridDim.x * (256u * UNROLL))
+        {
+            uint32_t k[UNROLL], r[UNROLL], d[UNROLL];
+            bool ok[UNROLL];
+#pragma unroll
+            for(int u = 0; u < UNROLL; ++u)
+            {
+                uint32_t const i = base + u * 256u + threadIdx.x;
+                k[u] = i < n ? __ldcs(key + i) : KEY_DROP;
+                r[u] = i < n ? __ldcs(rank + i) : 0u;
+                ok[u] = !(k[u] & KEY_LEAVE);
+            }
+#pragma unroll
+            for(int u = 0; u < UNROLL; ++u)
+                if(ok[u])
+                {
+                    d[u] = newOff[k[u]] + (r[u] & 0x7fffffffu);
+                    if(r[u] >> 31)
+                        d[u] += stayCnt[k[u]];
+                }
+#pragma unroll
+            for(int a = 0; a < 7; ++a)
+            {
+                float v[UNROLL];
+                float const* __restrict__ sp = a < 3 ? src.pos[a] : (a < 6 ? src.mom[a - 3] : src.w);
+                float* __restrict__ dp = a < 3 ? dst.pos[a] : (a < 6 ? dst.mom[a - 3] : dst.w);
+#pragma unroll
+                for(int u = 0; u < UNROLL; ++u)
+                    if(ok[u])
+                        v[u] = __ldcs(sp + base + u * 256u + threadIdx.x);
+#pragma unroll
+                for(int u = 0; u < UNROLL; ++u)
+                    if(ok[u])
+                        dp[d[u]] = v[u];
+            }
+#pragma unroll
+            for(int u = 0; u < UNROLL; ++u)
+                if(ok[u])
+                    dst.cell[d[u]] = uint16_t(k[u] & (SCVOL - 1));
+        }
+    }
+
+    // ranked mode: received records fill their cell's run from the END (the local particles occupy the front);
+    // cnt was cleared after the scan and is cleared again afterwards by clearRecordCountsKernel
+    __global__ void __launch_bounds__(256) scatterRecordsBackKernel(MigRecord const* __restrict__ rec, uint32_t nRec, SpeciesDev dst, uint32_t const* __restrict__ newOff, uint32_t* __restrict__ cnt)
+    {
+        for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nRec; i += gridDim.x * blockDim.x)
+        {
+            MigRecord const r = rec[i];
+            uint32_t const k = r.key & KEY_MASK;
+            uint32_t const d = newOff[k + 1] - 1u - atomicAdd(&cnt[k], 1u);
+            dst.pos[0][d] = r.px;
+            dst.pos[1][d] = r.py;
+            dst.pos[2][d] = r.pz;
+            dst.mom[0][d] = r.ux;
+            dst.mom[1][d] = r.uy;
+            dst.mom[2][d] = r.uz;
+            dst.w[d] = r.w;
+            dst.cell[d] = uint16_t(k & (SCVOL - 1));
+        }
+    }
+    __global__ void __launch_bounds__(256) clearRecordCountsKernel(MigRecord const* __restrict__ rec, uint32_t nRec, uint32_t* __restrict__ cnt)
+    {
+        for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nRec; i += gridDim.x * blockDim.x)
+            cnt[rec[i].key & KEY_MASK] = 0u;
     }
 
     // received migration records -> new runs (KernelInsertParticles, ParticlesBase.kernel:846-938)
@@ -323,17 +406,45 @@ namespace picstep
         return int(b);
     }
 
-    cudaError_t launchScan(uint32_t const* cnt, uint32_t* scSum, uint32_t* scOff, uint32_t* cellOff, int nsc, uint32_t* total, uint32_t capacity, int* overflow, cudaStream_t st)
+    cudaError_t launchScan(uint32_t const* cnt, uint32_t const* cnt2, uint32_t* scSum, uint32_t* scOff, uint32_t* cellOff, int nsc, uint32_t* total, uint32_t capacity, int* overflow, cudaStream_t st)
     {
-        supercellSumKernel<<<nsc, 256, 0, st>>>(cnt, scSum);
+        supercellSumKernel<<<nsc, 256, 0, st>>>(cnt, cnt2, scSum);
         supercellScanKernel<<<1, 1024, 0, st>>>(scSum, scOff, nsc, total, capacity, overflow);
-        cellScanKernel<<<nsc, 256, 0, st>>>(cnt, scOff, cellOff, nsc);
+        cellScanKernel<<<nsc, 256, 0, st>>>(cnt, cnt2, scOff, cellOff, nsc);
         return cudaGetLastError();
     }
 
     cudaError_t launchScatter(SpeciesDev src, SpeciesDev dst, uint32_t const* key, uint32_t const* nOld, uint32_t nOldUpper, uint32_t const* newOff, uint32_t* cnt, cudaStream_t st)
     {
         scatterKernel<<<gridFor(nOldUpper), 256, 0, st>>>(src, dst, key, nOld, newOff, cnt);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchScatterRanked(SpeciesDev src, SpeciesDev dst, uint32_t const* key, uint32_t const* rank, uint32_t const* nOld, uint32_t nOldUpper, uint32_t const* newOff, uint32_t const* stayCnt, cudaStream_t st)
+    {
+        constexpr int UNROLL = 4;
+        long long blocks = (nOldUpper + 256ll * UNROLL - 1) / (256ll * UNROLL);
+        if(blocks < 1)
+            blocks = 1;
+        if(blocks > 148 * 32)
+            blocks = 148 * 32;
+        scatterRankedKernel<UNROLL><<<int(blocks), 256, 0, st>>>(src, dst, key, rank, nOld, newOff, stayCnt);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchScatterRecordsBack(MigRecord const* rec, uint32_t nRec, SpeciesDev dst, uint32_t const* newOff, uint32_t* cnt, cudaStream_t st)
+    {
+        if(nRec == 0)
+            return cudaSuccess;
+        scatterRecordsBackKernel<<<gridFor(nRec), 256, 0, st>>>(rec, nRec, dst, newOff, cnt);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchClearRecordCounts(MigRecord const* rec, uint32_t nRec, uint32_t* cnt, cudaStream_t st)
+    {
+        if(nRec == 0)
+            return cudaSuccess;
+        clearRecordCountsKernel<<<gridFor(nRec), 256, 0, st>>>(rec, nRec, cnt);
         return cudaGetLastError();
     }
 
