@@ -67,6 +67,7 @@ namespace picstep
         uint32_t* stayCnt = nullptr; // per cell: particles that stay (written by the fused kernel, zero otherwise)
         uint32_t* rank = nullptr; // per particle: slot inside the destination cell (fused kernel)
         bool ranked = false; // key/rank/stayCnt come from the fused kernel -> atomics-free scatter
+        std::vector<void*> raw; // cudaMalloc'ed blocks behind the skewed per-particle arrays
         uint32_t *scSum = nullptr, *scOff = nullptr;
         uint32_t* nDev = nullptr; // [2], indexed like cur
         uint32_t nUpper = 0; // host side upper bound of the particle count
@@ -175,25 +176,39 @@ namespace
 
     void freeSpeciesBuffers(SpeciesHost& s)
     {
+        for(void* p : s.raw)
+            cudaFree(p);
+        s.raw.clear();
         for(int b = 0; b < 2; ++b)
         {
             for(int k = 0; k < 7; ++k)
-            {
-                cudaFree(s.attr[b][k]);
                 s.attr[b][k] = nullptr;
-            }
-            cudaFree(s.cell[b]);
             s.cell[b] = nullptr;
         }
-        cudaFree(s.key);
         s.key = nullptr;
-        cudaFree(s.rank);
         s.rank = nullptr;
         cudaFree(s.sendLo);
         cudaFree(s.sendHi);
         cudaFree(s.recvLo);
         cudaFree(s.recvHi);
         s.sendLo = s.sendHi = s.recvLo = s.recvHi = nullptr;
+    }
+
+    // The push and scatter kernels walk all per-particle arrays of a species in lockstep (same element index in up
+    // to 18 streams).  cudaMalloc returns 2 MiB aligned blocks, so without a skew every stream would sit at the same
+    // offset inside its page and the streams would camp on the same DRAM channels/banks (measured: the scatter ran
+    // at 3.5 or 6.3 TB/s depending on the ping-pong direction).  Each array therefore starts at a different offset.
+    template<class T>
+    int allocSkewed(picstep_ctx* c, SpeciesHost& s, T** out, int64_t count)
+    {
+        size_t const skew = (size_t(s.raw.size()) * 37u % 61u + 1u) * 33u * 1024u; // multiples of 33 KiB, < 2 MiB
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, sizeof(T) * size_t(count) + skew);
+        if(e != cudaSuccess)
+            return fail(c, PICSTEP_ERR_CUDA, std::string("cudaMalloc(particle array): ") + cudaGetErrorString(e));
+        s.raw.push_back(p);
+        *out = reinterpret_cast<T*>(static_cast<char*>(p) + skew);
+        return PICSTEP_OK;
     }
 
     int allocSpeciesBuffers(picstep_ctx* c, SpeciesHost& s, int64_t capacity)
@@ -207,11 +222,15 @@ namespace
         for(int b = 0; b < 2; ++b)
         {
             for(int k = 0; k < 7; ++k)
-                CU(c, cudaMalloc(&s.attr[b][k], sizeof(float) * capacity));
-            CU(c, cudaMalloc(&s.cell[b], sizeof(uint16_t) * capacity));
+                if(int rc = allocSkewed(c, s, &s.attr[b][k], capacity))
+                    return rc;
+            if(int rc = allocSkewed(c, s, &s.cell[b], capacity))
+                return rc;
         }
-        CU(c, cudaMalloc(&s.key, sizeof(uint32_t) * capacity));
-        CU(c, cudaMalloc(&s.rank, sizeof(uint32_t) * capacity));
+        if(int rc = allocSkewed(c, s, &s.key, capacity))
+            return rc;
+        if(int rc = allocSkewed(c, s, &s.rank, capacity))
+            return rc;
         if(c->P.split_axis >= 0)
         {
             // exchange capacity: particles of one border supercell layer could at most all leave; reserve a

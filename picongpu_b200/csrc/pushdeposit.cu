@@ -167,6 +167,27 @@ namespace picstep
         uint32_t const pBeg = cellOff[sc * SCVOL + warp * C::CELLS_PER_WARP];
         uint32_t const pEnd = cellOff[sc * SCVOL + (warp + 1) * C::CELLS_PER_WARP];
 
+        // The particle attributes of a chunk are loaded one chunk ahead: the loads are issued before phase 2 of the
+        // previous chunk, which does not touch global memory, so the HBM latency is hidden by it.
+        float pfx[3] = {0.f, 0.f, 0.f}, pfu[3] = {0.f, 0.f, 0.f}, pfw = 0.f;
+        int pfc = -2;
+        auto prefetch = [&](uint32_t chunk_)
+        {
+            uint32_t const j = chunk_ + lane;
+            if(j < pEnd)
+            {
+#pragma unroll
+                for(int d = 0; d < 3; ++d)
+                {
+                    pfx[d] = S.pos[d][j];
+                    pfu[d] = S.mom[d][j];
+                }
+                pfw = S.w[j];
+                pfc = S.cell[j];
+            }
+        };
+        prefetch(pBeg);
+
         for(uint32_t chunk = pBeg; chunk < pEnd; chunk += 32)
         {
             uint32_t const i = chunk + lane;
@@ -179,10 +200,10 @@ namespace picstep
             // ---- phase 1: lane = particle -----------------------------------------------------------------------
             if(valid)
             {
-                float x1[3] = {S.pos[0][i], S.pos[1][i], S.pos[2][i]};
-                float u[3] = {S.mom[0][i], S.mom[1][i], S.mom[2][i]};
-                float const w = S.w[i];
-                lc = S.cell[i];
+                float x1[3] = {pfx[0], pfx[1], pfx[2]};
+                float u[3] = {pfu[0], pfu[1], pfu[2]};
+                float const w = pfw;
+                lc = pfc;
                 int const lx = lc % SCX, ly = (lc / SCX) % SCY, lz = lc / (SCX * SCY);
                 float const mass = S.mass_per_w * w;
                 float const charge = S.charge_per_w * w;
@@ -371,6 +392,7 @@ namespace picstep
                 return later ? __ffs(later) - 1 : n;
             };
             uint32_t const stayMask = FUSED ? __ballot_sync(FULL, stays) : 0u;
+            prefetch(chunk + 32);
             __syncwarp(); // records are visible
             for(int r = 0; r < n;)
             {
