@@ -35,6 +35,7 @@ BYTES_PER_CELL = 168.0  # E,B gather 24 + J 36 + 2x B-half 72 + E update 36
 PUSH_BYTES_PER_PARTICLE = 30.0 + 24.0 + 4.0  # read pos,mom,w,cell; write pos,mom; write re-sort key
 DEPOSIT_BYTES_PER_PARTICLE = 30.0  # read pos,mom,w,cell
 DEPOSIT_BYTES_PER_CELL = 24.0  # J read-modify-write, 3 components
+FUSED_BYTES_PER_CELL = 24.0 + 24.0  # fused run kernel: E,B tile read + J read-modify-write
 
 
 def measured_peaks():
@@ -234,15 +235,28 @@ def run_ours(args):
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------
     peak, peak_kind = measured_peaks()
     nspec = 2
-    per_launch = {
-        "deposit": (stage["deposit"] / (args.steps * nspec), (npart / nspec) * DEPOSIT_BYTES_PER_PARTICLE + ncell * DEPOSIT_BYTES_PER_CELL, "depositCellKernel<TSC,Esirkepov>"),
-        "push": (stage["push"] / (args.steps * nspec), (npart / nspec) * PUSH_BYTES_PER_PARTICLE + ncell * 24.0, "pushKernel<TSC,Boris>"),
-    }
+    fused = stage["deposit"] == 0.0  # picstep_step fast path: gather+push+move+deposit in one kernel (runKernel)
+    if fused:
+        per_launch = {
+            "run": (stage["push"] / (args.steps * nspec), (npart / nspec) * BYTES_PER_UPDATE + ncell * FUSED_BYTES_PER_CELL, "runKernel<TSC,Boris,fused>"),
+        }
+    else:
+        per_launch = {
+            "deposit": (stage["deposit"] / (args.steps * nspec), (npart / nspec) * DEPOSIT_BYTES_PER_PARTICLE + ncell * DEPOSIT_BYTES_PER_CELL, "depositCellKernel<TSC,Esirkepov>"),
+            "push": (stage["push"] / (args.steps * nspec), (npart / nspec) * PUSH_BYTES_PER_PARTICLE + ncell * 24.0, "pushKernel<TSC,Boris>"),
+        }
     dom = max(per_launch, key=lambda k: per_launch[k][0])
     ms_k, bytes_k, kname = per_launch[dom]
     achieved = bytes_k / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel at the default workload, from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if kname in tj and grid == (256, 256, 256) and args.ppc == 25:
+            traffic = float(tj[kname]["dram_bytes_per_launch"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
+                "traffic": traffic, "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
                 "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": bytes_k,
                 "share_of_step": ms_k * nspec / ms_step if ms_step > 0 else None}
     step_bytes = npart * BYTES_PER_UPDATE + ncell * BYTES_PER_CELL
