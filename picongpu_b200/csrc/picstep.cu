@@ -19,7 +19,10 @@ namespace picstep
     cudaError_t launchDeposit(int, int, bool, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
     bool runKernelSupports(int, int);
     cudaError_t launchDepositRun(int, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
-    cudaError_t launchPushDeposit(int, int, DevParams const&, SpeciesDev const&, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, cudaStream_t);
+    cudaError_t launchPushDeposit(int, int, DevParams const&, SpeciesDev const&, SpeciesDev const&, uint32_t const*, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, cudaStream_t);
+    cudaError_t launchInvertRanked(uint32_t const*, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t const*, uint32_t*, uint16_t*, cudaStream_t);
+    cudaError_t launchAppendRecords(MigRecord const*, uint32_t, uint32_t const*, uint32_t, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, uint32_t*, int*, cudaStream_t);
+    cudaError_t launchGatherPerm(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t, cudaStream_t);
     cudaError_t launchScan(uint32_t const*, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, int, uint32_t*, uint32_t, int*, cudaStream_t);
     cudaError_t launchScatterRanked(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t const*, cudaStream_t);
     cudaError_t launchScatterRecordsBack(MigRecord const*, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, cudaStream_t);
@@ -66,7 +69,9 @@ namespace picstep
         uint32_t* cellCnt = nullptr; // per destination cell: histogram of the re-sort keys (ranked mode: arrivals only)
         uint32_t* stayCnt = nullptr; // per cell: particles that stay (written by the fused kernel, zero otherwise)
         uint32_t* rank = nullptr; // per particle: slot inside the destination cell (fused kernel)
-        bool ranked = false; // key/rank/stayCnt come from the fused kernel -> atomics-free scatter
+        bool ranked = false; // key/rank/stayCnt come from the fused kernel (which wrote the pushed attributes into buffer cur^1)
+        uint32_t* inv = nullptr; // lazy re-sort: attribute index of slot j of the run order
+        bool lazy = false; // attr[cur] is addressed through inv; cell[cur], cellOff[cur] are in run order
         std::vector<void*> raw; // cudaMalloc'ed blocks behind the skewed per-particle arrays
         uint32_t *scSum = nullptr, *scOff = nullptr;
         uint32_t* nDev = nullptr; // [2], indexed like cur
@@ -187,6 +192,9 @@ namespace
         }
         s.key = nullptr;
         s.rank = nullptr;
+        s.inv = nullptr;
+        s.lazy = false;
+        s.ranked = false;
         cudaFree(s.sendLo);
         cudaFree(s.sendHi);
         cudaFree(s.recvLo);
@@ -230,6 +238,8 @@ namespace
         if(int rc = allocSkewed(c, s, &s.key, capacity))
             return rc;
         if(int rc = allocSkewed(c, s, &s.rank, capacity))
+            return rc;
+        if(int rc = allocSkewed(c, s, &s.inv, capacity))
             return rc;
         if(c->P.split_axis >= 0)
         {
@@ -407,6 +417,22 @@ namespace
         return PICSTEP_OK;
     }
 
+    // lazy -> physical run order: gather the attributes through inv into the other buffer (API calls and the
+    // un-fused stage functions work on the sorted arrays themselves)
+    int ensureSorted(picstep_ctx* c, SpeciesHost& s)
+    {
+        if(!s.lazy || s.capacity == 0)
+            return PICSTEP_OK;
+        int const nxt = s.cur ^ 1;
+        int const nscTot = c->P.nsc[0] * c->P.nsc[1] * c->P.nsc[2];
+        KL(c, 1, launchGatherPerm(devOf(c, s, s.cur), devOf(c, s, nxt), s.inv, s.nDev + s.cur, uint32_t(s.capacity), c->stream));
+        CU(c, cudaMemcpyAsync(s.cellOff[nxt], s.cellOff[s.cur], sizeof(uint32_t) * (size_t(nscTot) * SCVOL + 1), cudaMemcpyDeviceToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(s.nDev + nxt, s.nDev + s.cur, sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+        s.cur = nxt;
+        s.lazy = false;
+        return PICSTEP_OK;
+    }
+
     // counting sort of species s from buffer `cur` (keys + histogram ready) into the other buffer
     int resortSpecies(picstep_ctx* c, SpeciesHost& s, uint32_t nRecLo, uint32_t nRecHi)
     {
@@ -419,20 +445,22 @@ namespace
         KL(c, 3, launchScan(s.cellCnt, s.stayCnt, s.scSum, s.scOff, s.cellOff[nxt], nscTot, s.nDev + nxt, uint32_t(s.capacity), c->flags, c->stream));
         if(s.ranked)
         {
-            // slots were assigned by the fused kernel: streaming permutation, then reset both histograms
+            // slots were assigned by the fused kernel, which also wrote the pushed attributes into buffer nxt in its
+            // processing order: only the permutation (inv) and the new localCellIdx are materialised (lazy re-sort)
             size_t const cntBytes = sizeof(uint32_t) * size_t(nscTot) * SCVOL;
-            KL(c, 1, launchScatterRanked(devOf(c, s, s.cur), devOf(c, s, nxt), s.key, s.rank, s.nDev + s.cur, s.nUpper, s.cellOff[nxt], s.stayCnt, c->stream));
+            KL(c, 1, launchInvertRanked(s.key, s.rank, s.nDev + s.cur, s.nUpper, s.cellOff[nxt], s.stayCnt, s.inv, s.cell[nxt], c->stream));
             CU(c, cudaMemsetAsync(s.cellCnt, 0, cntBytes, c->stream));
             CU(c, cudaMemsetAsync(s.stayCnt, 0, cntBytes, c->stream));
             c->launches += 2;
             if(nRecLo)
-                KL(c, 1, launchScatterRecordsBack(s.recvLo, nRecLo, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+                KL(c, 1, launchAppendRecords(s.recvLo, nRecLo, s.nDev + s.cur, 0u, uint32_t(s.capacity), devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, s.inv, c->flags, c->stream));
             if(nRecHi)
-                KL(c, 1, launchScatterRecordsBack(s.recvHi, nRecHi, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+                KL(c, 1, launchAppendRecords(s.recvHi, nRecHi, s.nDev + s.cur, nRecLo, uint32_t(s.capacity), devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, s.inv, c->flags, c->stream));
             if(nRecLo)
                 KL(c, 1, launchClearRecordCounts(s.recvLo, nRecLo, s.cellCnt, c->stream));
             if(nRecHi)
                 KL(c, 1, launchClearRecordCounts(s.recvHi, nRecHi, s.cellCnt, c->stream));
+            s.lazy = true;
             s.ranked = false;
         }
         else
@@ -766,6 +794,7 @@ extern "C"
                 return rc;
         }
         // stage the unsorted input in the inactive buffer, build keys + histogram, then scatter into the active one
+        s.lazy = false; // everything is overwritten
         int const stage = s.cur ^ 1;
         int const ncell = numCells(c);
         CU(c, cudaMemsetAsync(s.cellCnt, 0, sizeof(uint32_t) * ncell, c->stream));
@@ -824,6 +853,8 @@ extern "C"
         if(n == 0)
             return PICSTEP_OK;
         SpeciesHost& s = c->species[sp];
+        if(int rc2 = ensureSorted(c, s))
+            return rc2;
         for(int k = 0; k < 3; ++k)
         {
             if(pos)
@@ -876,6 +907,8 @@ extern "C"
                     return rc;
             }
             s.nUpper = uint32_t(n);
+            s.lazy = false;
+            s.ranked = false;
             uint32_t const n32 = uint32_t(n);
             CU(c, cudaMemcpyAsync(s.nDev + s.cur, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
         }
@@ -926,6 +959,8 @@ extern "C"
         if(s.capacity == 0)
             return PICSTEP_OK;
         s.ranked = false;
+        if(int rc = ensureSorted(c, s))
+            return rc;
         KL(c, 1, launchPush(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], s.cellCnt, s.key, c->stream));
         return PICSTEP_OK;
     }
@@ -944,7 +979,7 @@ extern "C"
             if(!c->comm)
                 return fail(c, PICSTEP_ERR_COMM, "devices > 1 but picstep_comm_init was not called");
             CU(c, cudaMemsetAsync(s.sendCnt, 0, sizeof(uint32_t) * 2, c->stream));
-            KL(c, 1, launchPackLeavers(c->P, devOf(c, s, s.cur), s.key, s.cellOff[s.cur], s.sendLo, s.sendHi, s.sendCnt, s.capRec, c->flags + 2, c->stream));
+            KL(c, 1, launchPackLeavers(c->P, devOf(c, s, s.ranked ? (s.cur ^ 1) : s.cur), s.key, s.cellOff[s.cur], s.sendLo, s.sendHi, s.sendCnt, s.capRec, c->flags + 2, c->stream));
             // counts first (fixed-size header), so receive buffers can never overflow silently
             CU(c, cudaMemcpyAsync(c->hostPinned, s.sendCnt, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
             uint32_t* cntDev = s.sendCnt; // reuse: [0],[1] send counts; receive counts land in scSum[0..1] scratch
@@ -994,6 +1029,8 @@ extern "C"
         SpeciesHost& s = c->species[sp];
         if(s.capacity == 0)
             return PICSTEP_OK;
+        if(int rc = ensureSorted(c, s))
+            return rc;
         if(runKernelSupports(c->prm.shape, c->prm.current_solver) && !(c->prm.flags & 3))
             KL(c, 1, launchDepositRun(c->prm.shape, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
         else
@@ -1009,7 +1046,7 @@ extern "C"
         SpeciesHost& s = c->species[sp];
         if(s.capacity == 0)
             return PICSTEP_OK;
-        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, c->stream));
+        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), devOf(c, s, s.cur ^ 1), s.lazy ? s.inv : nullptr, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, c->stream));
         s.ranked = true;
         return PICSTEP_OK;
     }
@@ -1141,6 +1178,8 @@ extern "C"
         {
             SpeciesHost& s = c->species[sp];
             CU(c, cudaMemsetAsync(c->redBuf, 0, sizeof(double) * 2, c->stream));
+            if(int rc = ensureSorted(c, s))
+                return rc;
             if(s.capacity)
                 KL(c, 1, launchParticleEnergy(P, devOf(c, s, s.cur), s.nDev + s.cur, c->redBuf, c->stream));
             CU(c, cudaMemcpyAsync(c->hostPinned, c->redBuf, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
@@ -1162,6 +1201,9 @@ extern "C"
             if(!c->rho)
                 CU(c, cudaMalloc(&c->rho, sizeof(float) * 3 * P.vol));
             CU(c, cudaMemsetAsync(c->rho, 0, sizeof(float) * 3 * P.vol, c->stream));
+            for(auto& s : c->species)
+                if(int rc = ensureSorted(c, s))
+                    return rc;
             for(auto& s : c->species)
                 if(s.capacity)
                     KL(c, 1, launchChargeDensity(c->prm.shape, P, devOf(c, s, s.cur), s.cellOff[s.cur], c->rho, c->stream));
@@ -1199,6 +1241,8 @@ extern "C"
         if(n > capacity)
             return fail(c, PICSTEP_ERR_CAPACITY, "gather buffer too small");
         SpeciesHost& s = c->species[sp];
+        if(int rc2 = ensureSorted(c, s))
+            return rc2;
         float* tmp = nullptr;
         CU(c, cudaMalloc(&tmp, sizeof(float) * 6 * std::max<int64_t>(n, 1)));
         KL(c, 1, launchGather(c->prm.shape, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], tmp, n, c->stream));

@@ -61,7 +61,9 @@ namespace picstep
     template<int SHAPE, int PUSHER, bool FUSED>
     __global__ void __launch_bounds__(256, 2) runKernel(
         DevParams P,
-        SpeciesDev S,
+        SpeciesDev S, // attributes are read from here: slot j of the cell-sorted order lives at index inv[j] (j if inv is null)
+        SpeciesDev D, // FUSED: the pushed attributes are written here at index j (the other buffer: lazy re-sort)
+        uint32_t const* __restrict__ inv,
         Field3 E,
         Field3 B,
         Field3 J,
@@ -169,24 +171,37 @@ namespace picstep
 
         // The particle attributes of a chunk are loaded one chunk ahead: the loads are issued before phase 2 of the
         // previous chunk, which does not touch global memory, so the HBM latency is hidden by it.
+        // The attributes are addressed through the permutation of the previous step's re-sort (inv), whose entries
+        // are loaded two chunks ahead.
         float pfx[3] = {0.f, 0.f, 0.f}, pfu[3] = {0.f, 0.f, 0.f}, pfw = 0.f;
         int pfc = -2;
+        uint32_t pfSrc = 0;
+        auto prefetchIdx = [&](uint32_t chunk_)
+        {
+            uint32_t const j = chunk_ + lane;
+            pfSrc = j;
+            if(inv != nullptr && j < pEnd)
+                pfSrc = __ldcs(inv + j);
+        };
         auto prefetch = [&](uint32_t chunk_)
         {
             uint32_t const j = chunk_ + lane;
             if(j < pEnd)
             {
+                uint32_t const src = pfSrc;
 #pragma unroll
                 for(int d = 0; d < 3; ++d)
                 {
-                    pfx[d] = S.pos[d][j];
-                    pfu[d] = S.mom[d][j];
+                    pfx[d] = S.pos[d][src];
+                    pfu[d] = S.mom[d][src];
                 }
-                pfw = S.w[j];
+                pfw = S.w[src];
                 pfc = S.cell[j];
             }
         };
+        prefetchIdx(pBeg);
         prefetch(pBeg);
+        prefetchIdx(pBeg + 32);
 
         for(uint32_t chunk = pBeg; chunk < pEnd; chunk += 32)
         {
@@ -232,9 +247,10 @@ namespace picstep
                         q -= mv;
                         x1[d] = q + 0.5f;
                         dir[d] = int(mv);
-                        S.pos[d][i] = x1[d];
-                        S.mom[d][i] = u[d];
+                        D.pos[d][i] = x1[d];
+                        D.mom[d][i] = u[d];
                     }
+                    D.w[i] = w;
                     // re-sort key (see pushKernel); fast path: the particle stays inside this supercell
                     int const nl[3] = {lx + dir[0], ly + dir[1], lz + dir[2]};
                     uint32_t k;
@@ -393,6 +409,7 @@ namespace picstep
             };
             uint32_t const stayMask = FUSED ? __ballot_sync(FULL, stays) : 0u;
             prefetch(chunk + 32);
+            prefetchIdx(chunk + 64);
             __syncwarp(); // records are visible
             for(int r = 0; r < n;)
             {
@@ -507,14 +524,14 @@ namespace picstep
     }
 
     template<int SHAPE, int PUSHER, bool FUSED>
-    cudaError_t launchRunT(DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, cudaStream_t st)
+    cudaError_t launchRunT(DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, cudaStream_t st)
     {
         int const nscTot = P.nsc[0] * P.nsc[1] * P.nsc[2];
         constexpr size_t smem = runSmemBytes<SHAPE, FUSED>();
         cudaError_t e = cudaFuncSetAttribute(runKernel<SHAPE, PUSHER, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if(e != cudaSuccess)
             return e;
-        runKernel<SHAPE, PUSHER, FUSED><<<nscTot, 256, smem, st>>>(P, S, E, B, J, cellOff, cellCnt, stayCnt, key, rank);
+        runKernel<SHAPE, PUSHER, FUSED><<<nscTot, 256, smem, st>>>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank);
         return cudaGetLastError();
     }
 
@@ -529,7 +546,7 @@ namespace picstep
         Field3 none{};
 #define PS_CASE(SH)                                                                                                   \
     if(shape == SH)                                                                                                   \
-        return launchRunT<SH, 0, false>(P, S, none, none, J, cellOff, nullptr, nullptr, nullptr, nullptr, st);
+        return launchRunT<SH, 0, false>(P, S, S, nullptr, none, none, J, cellOff, nullptr, nullptr, nullptr, nullptr, st);
         PS_CASE(0)
         PS_CASE(1)
         PS_CASE(2)
@@ -539,11 +556,11 @@ namespace picstep
     }
 
     /** fused gather + push + move + deposit of one species (picstep_step fast path) */
-    cudaError_t launchPushDeposit(int shape, int pusher, DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, cudaStream_t st)
+    cudaError_t launchPushDeposit(int shape, int pusher, DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, cudaStream_t st)
     {
 #define PS_CASE(SH, PU)                                                                                               \
     if(shape == SH && pusher == PU)                                                                                   \
-        return launchRunT<SH, PU, true>(P, S, E, B, J, cellOff, cellCnt, stayCnt, key, rank, st);
+        return launchRunT<SH, PU, true>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, st);
         PS_CASE(0, 0)
         PS_CASE(1, 0)
         PS_CASE(2, 0)
