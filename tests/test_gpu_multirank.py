@@ -1,0 +1,94 @@
+"""GPU test of the N>1 path through the C ABI (N-GPU result == 1-GPU result): two ranks, one
+B200 each, 1-D slab decomposition in y, guard exchange + particle migration over NCCL send/recv (comm.cu), must
+reproduce the single-domain oracle run on the same global grid.  Needs two GPUs (`gpurun --gpus 2`); skipped on a
+one-GPU box."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from picongpu_b200 import param as prm  # noqa: E402
+from picongpu_b200 import picstep  # noqa: E402
+
+import util  # noqa: E402
+from test_multirank_cpu import _kick  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+LOCAL = (16, 16, 8)
+
+
+def _worker(rank, world, port, steps, fused, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import nvidia.nccl as _n
+
+        os.environ.setdefault("PICSTEP_NCCL_LIB", os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so.2"))
+    except Exception:
+        pass
+    from oracle import picoracle as orc
+
+    orc.lib().orc_set_num_threads(2)
+    p = prm.khi_params(grid=LOCAL, devices=(1, world, 1), rank_pos=(0, rank, 0))
+    o, e, i = util.khi_ic(orc, p)
+    _kick(p, e)
+    _kick(p, i)
+    sim = picstep.Simulation(p, device=rank, exact=False, unfused=not fused)
+    box = [sim.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    sim.comm_init(box[0], rank, world)
+    for name, sp in (("e", e), ("i", i)):
+        sim.upload_particles(name, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+    n0 = sim.particle_count("e")
+    sim.step(steps)
+    sim.sync()
+    E, B = sim.download_field(picstep.FIELD_E), sim.download_field(picstep.FIELD_B)
+    pe = sim.download_particles("e")
+    pi = sim.download_particles("i")
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), E=o.interior(E), B=o.interior(B), ne=pe[2].shape[0], ni=pi[2].shape[0], n0=n0,
+             eux=np.sort(pe[1][0]), iux=np.sort(pi[1][0]), ecell=np.sort(pe[3]), gauss=sim.gauss_residual())
+    sim.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_two_gpu_slab_decomposition_equals_single_domain(orc, tmp_path, fused):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world, steps = 2, 6
+    port = 29500 + (os.getpid() % 2000) + (7 if fused else 0)
+    mp.spawn(_worker, args=(world, port, steps, fused, str(tmp_path)), nprocs=world, join=True)
+    p = prm.khi_params(grid=(LOCAL[0], LOCAL[1] * world, LOCAL[2]))
+    o, e, i = util.khi_ic(orc, p)
+    _kick(p, e)
+    _kick(p, i)
+    E, B, J = o.field(), o.field(), o.field()
+    for _ in range(steps):
+        o.step(E, B, J, [e, i])
+    r = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % k)) for k in range(world)]
+    Eg = np.concatenate([r[0]["E"], r[1]["E"]], axis=2)
+    Bg = np.concatenate([r[0]["B"], r[1]["B"]], axis=2)
+    _, escale = util.khi_scales(p, 1)
+    # production build vs oracle, tolerance as in test_khi_100_steps_vs_oracle (2e-5 of the per-species drive scale)
+    assert np.abs(Eg - o.interior(E)).max() / escale < 2e-5
+    assert np.abs(Bg - o.interior(B)).max() / escale < 2e-5
+    assert int(r[0]["ne"]) + int(r[1]["ne"]) == e["w"].shape[0]
+    assert int(r[0]["ni"]) + int(r[1]["ni"]) == i["w"].shape[0]
+    # particles really crossed the slab boundary
+    assert int(r[0]["ne"]) != int(r[0]["n0"]) or int(r[1]["ne"]) != int(r[1]["n0"])
+    for key, ref in (("eux", e["mom"][0]), ("iux", i["mom"][0])):
+        a, b = np.sort(np.concatenate([r[0][key], r[1][key]])), np.sort(ref)
+        assert np.abs(a - b).max() / np.abs(b).max() < 5e-6
+    # Gauss residual stays at round-off on both ranks (charge conserving deposition across the rank boundary)
+    q = 25.0 * abs(p.base_charge) * p.typical_num_particles_per_macro
+    assert max(float(r[0]["gauss"]), float(r[1]["gauss"])) / q < 1e-4
