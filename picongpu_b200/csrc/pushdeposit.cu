@@ -95,8 +95,8 @@ namespace picstep
 
         for(int i = threadIdx.x; i < C::WARPS * 3 * C::PV; i += blockDim.x)
             tiles[i] = 0.0f;
-        for(int i = lane; i < C::RECW; i += 32)
-            myRecs[32 * C::RECW + i] = 0.0f;
+        for(int i = lane; i < C::NREC * C::RECW; i += 32) // record 32 stays all zero
+            myRecs[i] = 0.0f;
         if constexpr(FUSED)
         {
             // stage the six E/B component tiles: rows of TX consecutive floats, coalesced per row
@@ -133,17 +133,16 @@ namespace picstep
         int const sC = strideOf(comp), sJ = strideOf(aj);
         int const laneTile = comp * C::PV + (2 * ah + slot) * strideOf(ai) + 2 * bh * sJ;
 
-        float acc[2][2][C::NK];
+        // accumulators of the lane's 2 x 2 x 3 nodes, packed over b: acc[a][k] = {J(a, b=0, k), J(a, b=1, k)}
+        F2 acc[2][C::NK];
 #pragma unroll
         for(int a = 0; a < 2; ++a)
 #pragma unroll
-            for(int b = 0; b < 2; ++b)
-#pragma unroll
-                for(int k = 0; k < C::NK; ++k)
-                    acc[a][b][k] = 0.0f;
+            for(int k = 0; k < C::NK; ++k)
+                acc[a][k] = F2(0.0f);
 
         int curCell = -1; // local cell index (0..255) the accumulators belong to
-        uint32_t stayBase = 0; // FUSED: stayers of curCell seen so far (their rank in the re-sorted cell run)
+        uint32_t stayCarry = 0; // FUSED: stayers of curCell seen in earlier chunks (their rank in the re-sorted cell run)
 
         // adds the accumulators to the private tile and clears them
         auto flushCell = [&]()
@@ -156,14 +155,18 @@ namespace picstep
 #pragma unroll
                 for(int k = 0; k < C::NK; ++k)
                 {
-                    float const keep = slot ? acc[1][b][k] : acc[0][b][k];
-                    float const send = slot ? acc[0][b][k] : acc[1][b][k];
+                    float const a0 = b ? acc[0][k].y : acc[0][k].x, a1 = b ? acc[1][k].y : acc[1][k].x;
+                    float const keep = slot ? a1 : a0;
+                    float const send = slot ? a0 : a1;
                     float const v = keep + __shfl_xor_sync(FULL, send, 16);
                     if(p2active)
                         myTile[cellBase + b * sJ + k * sC] += v;
-                    acc[0][b][k] = 0.0f;
-                    acc[1][b][k] = 0.0f;
                 }
+#pragma unroll
+            for(int a = 0; a < 2; ++a)
+#pragma unroll
+                for(int k = 0; k < C::NK; ++k)
+                    acc[a][k] = F2(0.0f);
         };
 
         uint32_t const pBeg = cellOff[sc * SCVOL + warp * C::CELLS_PER_WARP];
@@ -385,112 +388,109 @@ namespace picstep
                         esirkepovParticleGlobal<SHAPE>(J.c[0] + origin, J.c[1] + origin, J.c[2] + origin, P.N[0], (long long) P.N[0] * P.N[1], status[0] | (status[1] << 3) | (status[2] << 6), p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], csd * P.cell[0], csd * P.cell[1], csd * P.cell[2]);
                     }
                 }
-                if(!useRec)
-                {
-                    // nothing to add for this particle in phase 2: C = 0 (stale S0/DS/P/Q values are finite)
-                    float* const rec = myRecs + lane * C::RECW;
-#pragma unroll
-                    for(int d = 0; d < 3; ++d)
-                        *reinterpret_cast<float4*>(rec + d * C::AXW + 16) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                }
             }
-            // ---- phase 2: runs of equal cell, two records per pass ------------------------------------------------
+            if(!useRec)
+            {
+                // nothing to add for this record in phase 2 (absorbed / wide trajectory / slot beyond the end of the
+                // piece): C = 0; the S0/DS/P/Q words are stale but finite (the record area is zeroed at kernel start)
+                float* const rec = myRecs + lane * C::RECW;
+#pragma unroll
+                for(int d = 0; d < 3; ++d)
+                    *reinterpret_cast<float4*>(rec + d * C::AXW + 16) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+            // ---- phase 2: two records per pass (one per half warp), accumulators flushed when the cell changes ------
             uint32_t const validMask = __ballot_sync(FULL, valid);
             int const n = __popc(validMask);
             int prev = __shfl_up_sync(FULL, lc, 1);
             if(lane == 0)
                 prev = curCell;
             uint32_t const startMask = __ballot_sync(FULL, valid && lc != prev); // a new cell starts at this record
-            // end of the run of equal cells that contains record x
-            auto runEnd = [&](int x)
+            if constexpr(FUSED)
             {
-                uint32_t const later = x < 31 ? (startMask & (0xfffffffeu << x)) : 0u;
-                return later ? __ffs(later) - 1 : n;
-            };
-            uint32_t const stayMask = FUSED ? __ballot_sync(FULL, stays) : 0u;
+                // Stayers keep their relative order: rank = stayers of my cell before me.  Evaluated per lane from
+                // the ballots: my run of equal cells starts at the highest start bit at or below my lane, or in an
+                // earlier chunk (then stayCarry stayers precede this chunk).
+                uint32_t const stayMask = __ballot_sync(FULL, stays);
+                uint32_t const le = FULL >> (31 - lane); // bits 0..lane
+                uint32_t const sBelow = startMask & le;
+                int const lo = sBelow ? 31 - __clz(sBelow) : 0;
+                uint32_t const incl = (sBelow ? 0u : stayCarry) + __popc(stayMask & le & (FULL << lo));
+                if(stays)
+                    myRank = incl - 1u;
+                if(valid && lane < 31 && ((startMask >> (lane + 1)) & 1u)) // my cell ends with me
+                    stayCnt[sc * SCVOL + lc] = incl;
+                if(lane == 0 && (startMask & 1u) && curCell >= 0) // the cell left open by the previous chunk has ended
+                    stayCnt[sc * SCVOL + curCell] = stayCarry;
+                stayCarry = __shfl_sync(FULL, incl, n - 1);
+            }
             prefetch(chunk + 32);
             prefetchIdx(chunk + 64);
             __syncwarp(); // records are visible
-            for(int r = 0; r < n;)
+            // one pass: t(a,b) = S0_i(a) P_j(b) + DS_i(a) Q_j(b), acc(a,b,k) += C_k t(a,b); packed over b (FFMA2 with a
+            // broadcast scalar operand: 10 issue slots for 20 FMAs)
+            auto pass = [&](float const* pSD, float const* pPQ, float const* pC)
             {
-                int const e = runEnd(r);
-                if((startMask >> r) & 1u)
+                float4 const sd = *reinterpret_cast<float4 const*>(pSD); // {S0[a0], S0[a0+1], DS[a0], DS[a0+1]}
+                float4 const pq = *reinterpret_cast<float4 const*>(pPQ); // {P[b0], P[b0+1], Q[b0], Q[b0+1]}
+                float4 const c4 = *reinterpret_cast<float4 const*>(pC);
+                F2 const pp(pq.x, pq.y), qq(pq.z, pq.w);
+                F2 const t0 = fma2(F2(sd.z), qq, F2(sd.x) * pp);
+                F2 const t1 = fma2(F2(sd.w), qq, F2(sd.y) * pp);
+                acc[0][0] = fma2(F2(c4.x), t0, acc[0][0]);
+                acc[0][1] = fma2(F2(c4.y), t0, acc[0][1]);
+                acc[0][2] = fma2(F2(c4.z), t0, acc[0][2]);
+                acc[1][0] = fma2(F2(c4.x), t1, acc[1][0]);
+                acc[1][1] = fma2(F2(c4.y), t1, acc[1][1]);
+                acc[1][2] = fma2(F2(c4.z), t1, acc[1][2]);
+            };
+            float const* const zC = myRecs + 32 * C::RECW + offC; // C words of the all-zero record
+            // records q, q+1 with a cell change at q (bit 0) and / or at q+1 (bit 1)
+            auto passSlow = [&](float const* pSD, float const* pPQ, float const* pC, uint32_t bits, int q)
+            {
+                if(bits & 1u)
                 {
                     if(curCell >= 0)
-                    {
                         flushCell();
-                        if(FUSED && lane == 0)
-                            stayCnt[sc * SCVOL + curCell] = stayBase;
-                    }
-                    stayBase = 0;
-                    curCell = __shfl_sync(FULL, lc, r);
+                    curCell = __shfl_sync(FULL, lc, q);
                 }
-                if constexpr(FUSED)
+                if(bits & 2u)
                 {
-                    // stayers keep their relative order: rank = stayers of this cell before me
-                    uint32_t const st = stayMask & (e < 32 ? ((1u << e) - 1u) : FULL) & ~((1u << r) - 1u);
-                    if(stays && lane >= r && lane < e)
-                        myRank = stayBase + __popc(st & ((1u << lane) - 1u));
-                    stayBase += __popc(st);
+                    pass(pSD, pPQ, slot ? zC : pC); // record q closes its cell
+                    flushCell();
+                    curCell = __shfl_sync(FULL, lc, q + 1);
+                    pass(pSD, pPQ, slot ? pC : zC); // record q+1 opens the next one
                 }
-                // one pass = two records (one per half warp): operands at pSD/pPQ/pC + off words
-                auto pass = [&](float const* pSD, float const* pPQ, float const* pC, int off)
-                {
-                    float4 const sd = *reinterpret_cast<float4 const*>(pSD + off); // {S0[a0], S0[a0+1], DS[a0], DS[a0+1]}
-                    float4 const pq = *reinterpret_cast<float4 const*>(pPQ + off); // {P[b0], P[b0+1], Q[b0], Q[b0+1]}
-                    float4 const c4 = *reinterpret_cast<float4 const*>(pC + off);
-                    float const t00 = sd.x * pq.x + sd.z * pq.z;
-                    float const t01 = sd.x * pq.y + sd.z * pq.w;
-                    float const t10 = sd.y * pq.x + sd.w * pq.z;
-                    float const t11 = sd.y * pq.y + sd.w * pq.w;
-                    acc[0][0][0] += c4.x * t00;
-                    acc[0][0][1] += c4.y * t00;
-                    acc[0][0][2] += c4.z * t00;
-                    acc[0][1][0] += c4.x * t01;
-                    acc[0][1][1] += c4.y * t01;
-                    acc[0][1][2] += c4.z * t01;
-                    acc[1][0][0] += c4.x * t10;
-                    acc[1][0][1] += c4.y * t10;
-                    acc[1][0][2] += c4.z * t10;
-                    acc[1][1][0] += c4.x * t11;
-                    acc[1][1][1] += c4.y * t11;
-                    acc[1][1][2] += c4.z * t11;
-                };
-                int const len = e - r;
-                float const* rec = myRecs + (r + slot) * C::RECW;
-                float const *pSD = rec + offSD, *pPQ = rec + offPQ, *pC = rec + offC;
+                else
+                    pass(pSD, pPQ, pC);
+            };
+            float const* rec = myRecs + slot * C::RECW;
+            float const *pSD = rec + offSD, *pPQ = rec + offPQ, *pC = rec + offC;
 #pragma unroll 1
-                for(int it = len >> 2; it > 0; --it)
+            for(int r = 0; r < n; r += 4)
+            {
+                uint32_t const b4 = (startMask >> r) & 0xfu;
+                if(b4 == 0u)
                 {
-                    pass(pSD, pPQ, pC, 0);
-                    pass(pSD, pPQ, pC, 2 * C::RECW);
-                    pSD += 4 * C::RECW;
-                    pPQ += 4 * C::RECW;
-                    pC += 4 * C::RECW;
+                    pass(pSD, pPQ, pC);
+                    pass(pSD + 2 * C::RECW, pPQ + 2 * C::RECW, pC + 2 * C::RECW);
                 }
-                if(len & 2)
+                else
                 {
-                    pass(pSD, pPQ, pC, 0);
-                    pSD += 2 * C::RECW;
-                    pPQ += 2 * C::RECW;
-                    pC += 2 * C::RECW;
+                    passSlow(pSD, pPQ, pC, b4 & 3u, r);
+                    passSlow(pSD + 2 * C::RECW, pPQ + 2 * C::RECW, pC + 2 * C::RECW, b4 >> 2, r + 2);
                 }
-                if(len & 1)
-                {
-                    // last record of the run in slot 0; slot 1 would read the first record of the next cell
-                    float const* z = myRecs + 32 * C::RECW;
-                    pass(slot ? z + offSD : pSD, slot ? z + offPQ : pPQ, slot ? z + offC : pC, 0);
-                }
-                r = e;
+                pSD += 4 * C::RECW;
+                pPQ += 4 * C::RECW;
+                pC += 4 * C::RECW;
             }
             if(FUSED && valid)
-                rank[i] = myRank;
+                rank[i] = myRank; // last: the rank of an arrival is the return value of a global atomic
         }
         if(curCell >= 0)
         {
             flushCell();
             if(FUSED && lane == 0)
-                stayCnt[sc * SCVOL + curCell] = stayBase;
+                stayCnt[sc * SCVOL + curCell] = stayCarry;
         }
         __syncthreads();
         // ---- combine the warp-private tiles and flush once to global J (red.global.add.f32) --------------------------
