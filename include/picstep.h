@@ -41,11 +41,12 @@ extern "C"
         PICSTEP_SHAPE_PQS = 3,
         PICSTEP_SHAPE_PCS = 4
     };
-    /* particles::pusher::{Boris,Vay} (include/picongpu/unitless/pusher.unitless:43-86) */
+    /* particles::pusher::{Boris,Vay,HigueraCary} (include/picongpu/unitless/pusher.unitless:43-86) */
     enum picstep_pusher
     {
         PICSTEP_PUSHER_BORIS = 0,
-        PICSTEP_PUSHER_VAY = 1
+        PICSTEP_PUSHER_VAY = 1,
+        PICSTEP_PUSHER_HIGUERA_CARY = 2
     };
     /* currentSolver::{Esirkepov,EmZ} (include/picongpu/fields/currentDeposition/) */
     enum picstep_current_solver
@@ -58,6 +59,18 @@ extern "C"
     {
         PICSTEP_SOLVER_YEE = 0,
         PICSTEP_SOLVER_LEHE = 1
+    };
+    /* fields::currentInterpolation::{None,Binomial} (include/picongpu/fields/currentInterpolation/) */
+    enum picstep_current_interpolation
+    {
+        PICSTEP_CURRENT_INTERPOLATION_NONE = 0,
+        PICSTEP_CURRENT_INTERPOLATION_BINOMIAL = 1
+    };
+    /* fields::absorber::Absorber::Kind (include/picongpu/fields/absorber/Absorber.hpp); PML is not built */
+    enum picstep_absorber
+    {
+        PICSTEP_ABSORBER_NONE = 0,
+        PICSTEP_ABSORBER_EXPONENTIAL = 1
     };
     /* FieldE / FieldB / FieldJ, as named through DataConnector ("E","B","J") */
     enum picstep_field
@@ -101,6 +114,16 @@ extern "C"
         int32_t flags; /* bit0: deposit with the reference-strategy per-particle atomic kernel (cross-check);
                         * bit1: deposit with the warp-per-cell kernel (all shapes, EmZ) instead of the run kernel;
                         * bit2: picstep_step() runs push and deposit as separate kernels (no fusion) */
+        /* --currentInterpolation none|binomial (simulation/stage/CurrentInterpolationAndAdditionToEMF.hpp:60-92,
+         * fields/currentInterpolation/Binomial.hpp:41-112) */
+        int32_t current_interpolation; /* picstep_current_interpolation */
+        /* field absorber at non-periodic outer boundaries (param/fieldAbsorber.param:44-72,
+         * fields/absorber/exponential/Exponential.kernel:45-118): thickness in cells and strength per
+         * [axis][0 = negative side, 1 = positive side]; particles crossing such a boundary are absorbed
+         * (particles/boundary/Absorbing.hpp:50-92, offset 0) */
+        int32_t absorber_kind; /* picstep_absorber */
+        int32_t absorber_cells[3][2];
+        float absorber_strength[3][2];
     } picstep_params;
 
     /* library / build information: returns e.g. "picstep sm_100a fmad=on" */

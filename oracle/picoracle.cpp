@@ -46,11 +46,15 @@ extern "C"
         float base_mass; // sim.pic.getBaseMass()
         float base_charge; // sim.pic.getBaseCharge()
         int shape; // 0 NGP, 1 CIC, 2 TSC, 3 PQS, 4 PCS
-        int pusher; // 0 Boris, 1 Vay
+        int pusher; // 0 Boris, 1 Vay, 2 HigueraCary
         int current; // 0 Esirkepov, 1 EmZ
         int solver; // 0 Yee, 1 Lehe
         int lehe_dir; // Cherenkov-free direction for Lehe
         int wrap[3]; // 1: periodic wrap inside this domain; 0: leaving particles get cell coordinate -1 / n
+        int current_interp; // 0 None, 1 Binomial (--currentInterpolation)
+        int open[3][2]; // [axis][lower, upper]: face is a non-periodic outer boundary (no neighbour, no exchange)
+        int absorber_cells[3][2]; // exponential absorber thickness, NUM_CELLS (P/param/fieldAbsorber.param:53-57)
+        float absorber_strength[3][2]; // exponential::STRENGTH (fieldAbsorber.param:68-72)
     };
 }
 
@@ -422,6 +426,56 @@ namespace
         cross(momp, t, cr);
         for(int d = 0; d < 3; ++d)
             mom[d] = s * (momp[d] + dpt * t[d] + cr[d]);
+        f32 vel[3];
+        velocityF(P, mom, mass, vel);
+        for(int d = 0; d < 3; ++d)
+            pos[d] += (vel[d] * dt) / P.cell[d];
+    }
+
+    // P/particles/pusher/particlePusherHigueraCary.hpp:45-145 (sqrt_HigueraCary = precision64Bit, P/param/pusher.param:71;
+    // Gamma<> computes in float_X, P/unitless/pusher.unitless:55)
+    inline void pushHigueraCary(OrcParams const& P, f32 mass, f32 charge, f32 const E[3], f32 const B[3], f32 mom[3], f32 pos[3])
+    {
+        f32 const dt = P.dt;
+        f32 half_e[3], mm32[3];
+        double mom_minus[3], tau[3];
+        for(int d = 0; d < 3; ++d)
+        {
+            half_e[d] = 0.5f * charge * E[d] * dt;
+            mm32[d] = mom[d] + half_e[d];
+            mom_minus[d] = double(mm32[d]);
+            tau[d] = double(0.5f * B[d] * charge * dt / mass);
+        }
+        double const gamma_minus = double(gammaF(P, mm32, mass));
+        double tau2 = tau[0] * tau[0];
+        tau2 += tau[1] * tau[1];
+        tau2 += tau[2] * tau[2];
+        double const sigma = gamma_minus * gamma_minus - tau2;
+        double dotpt = mom_minus[0] * tau[0];
+        dotpt += mom_minus[1] * tau[1];
+        dotpt += mom_minus[2] * tau[2];
+        double const u_star = dotpt / double(mass * P.c);
+        double const gamma_plus = std::sqrt(0.5 * (sigma + std::sqrt(sigma * sigma + 4.0 * (tau2 + u_star * u_star))));
+        double t[3];
+        for(int d = 0; d < 3; ++d)
+            t[d] = tau[d] / gamma_plus;
+        double t2 = t[0] * t[0];
+        t2 += t[1] * t[1];
+        t2 += t[2] * t[2];
+        double const sfac = 1.0 / (1.0 + t2);
+        double dmt = mom_minus[0] * t[0];
+        dmt += mom_minus[1] * t[1];
+        dmt += mom_minus[2] * t[2];
+        double cr[3] = {mom_minus[1] * t[2] - mom_minus[2] * t[1], mom_minus[2] * t[0] - mom_minus[0] * t[2], mom_minus[0] * t[1] - mom_minus[1] * t[0]};
+        double mom_plus[3];
+        for(int d = 0; d < 3; ++d)
+            mom_plus[d] = sfac * (mom_minus[d] + dmt * t[d] + cr[d]);
+        double const cr2[3] = {mom_plus[1] * t[2] - mom_plus[2] * t[1], mom_plus[2] * t[0] - mom_plus[0] * t[2], mom_plus[0] * t[1] - mom_plus[1] * t[0]};
+        for(int d = 0; d < 3; ++d)
+        {
+            f32 const mom_diff = half_e[d] + f32(cr2[d]);
+            mom[d] = f32(mom_plus[d]) + mom_diff;
+        }
         f32 vel[3];
         velocityF(P, mom, mass, vel);
         for(int d = 0; d < 3; ++d)
@@ -939,8 +993,10 @@ extern "C"
         f32 const charge = (P->base_charge * chargeRatio) * w;
         if(P->pusher == 0)
             pushBoris(*P, mass, charge, E, B, mom, pos);
-        else
+        else if(P->pusher == 1)
             pushVay(*P, mass, charge, E, B, mom, pos);
+        else
+            pushHigueraCary(*P, mass, charge, E, B, mom, pos);
     }
 
     // ---------------------------------------------------------------------------------------------
@@ -1007,8 +1063,10 @@ extern "C"
             f32 const charge = (P.base_charge * chargeRatio) * w[i];
             if(P.pusher == 0)
                 pushBoris(P, mass, charge, Ef, Bf, m, p);
-            else
+            else if(P.pusher == 1)
                 pushVay(P, mass, charge, Ef, Bf, m, p);
+            else
+                pushHigueraCary(P, mass, charge, Ef, Bf, m, p);
             int lc[3] = {cc[0] % D.sc[0], cc[1] % D.sc[1], cc[2] % D.sc[2]};
             int dir[3];
             f32 pout[3];
@@ -1185,12 +1243,22 @@ extern "C"
     {
         Dom const D(*Pp);
         int const g = D.g[axis], n = D.n[axis];
+        // transverse extent: the whole padded axis, except beyond an open outer boundary (the reference has no
+        // edge / corner exchange across a missing neighbour: Mask::getRelativeDirections, Exchange.hpp:46-54)
+        int tlo[3], thi[3];
+        for(int d = 0; d < 3; ++d)
+        {
+            tlo[d] = Pp->open[d][0] ? D.g[d] : 0;
+            thi[d] = Pp->open[d][1] ? D.g[d] + D.n[d] : D.N[d];
+        }
+        tlo[axis] = 0;
+        thi[axis] = 1;
         for(int c = 0; c < ncomp; ++c)
         {
             f32* f = F + c * D.vol;
-            for(int z = 0; z < (axis == 2 ? 1 : D.N[2]); ++z)
-                for(int y = 0; y < (axis == 1 ? 1 : D.N[1]); ++y)
-                    for(int x = 0; x < (axis == 0 ? 1 : D.N[0]); ++x)
+            for(int z = tlo[2]; z < thi[2]; ++z)
+                for(int y = tlo[1]; y < thi[1]; ++y)
+                    for(int x = tlo[0]; x < thi[0]; ++x)
                     {
                         auto at = [&](int pl) -> f32&
                         {
@@ -1267,6 +1335,51 @@ extern "C"
         OrcParams const& P = *Pp;
         Dom const D(P);
         f32 const coeff = -(1.0f / P.eps0) * P.dt;
+        if(P.current_interp == 1)
+        {
+            // currentInterpolation::Binomial<DIM3> (P/fields/currentInterpolation/Binomial.hpp:62-110); the J guards
+            // hold the neighbours' border values (FieldJ "receive" exchange, P/fields/FieldJ.x.cpp:118-141)
+            f32 const M = 8.0f, S = 4.0f, Dw = 2.0f, T = 1.0f;
+            f32 const inverseDivisor = 1.0f / (M + 6.0f * S + 12.0f * Dw + 8.0f * T);
+#pragma omp parallel for schedule(static) collapse(2)
+            for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
+                for(int y = D.g[1]; y < D.g[1] + D.n[1]; ++y)
+                    for(int x = D.g[0]; x < D.g[0] + D.n[0]; ++x)
+                        for(int c = 0; c < 3; ++c)
+                        {
+                            f32 const* j = J + c * D.vol;
+                            auto at = [&](int dx, int dy, int dz) { return j[D.idx(x + dx, y + dy, z + dz)]; };
+                            f32 far = at(-1, -1, -1) + at(+1, -1, -1);
+                            far = far + at(-1, +1, -1);
+                            far = far + at(+1, +1, -1);
+                            far = far + at(-1, -1, +1);
+                            far = far + at(+1, -1, +1);
+                            far = far + at(-1, +1, +1);
+                            far = far + at(+1, +1, +1);
+                            f32 edge = at(-1, -1, 0) + at(+1, -1, 0);
+                            edge = edge + at(-1, +1, 0);
+                            edge = edge + at(+1, +1, 0);
+                            edge = edge + at(-1, 0, -1);
+                            edge = edge + at(+1, 0, -1);
+                            edge = edge + at(-1, 0, +1);
+                            edge = edge + at(+1, 0, +1);
+                            edge = edge + at(0, -1, -1);
+                            edge = edge + at(0, +1, -1);
+                            edge = edge + at(0, -1, +1);
+                            edge = edge + at(0, +1, +1);
+                            f32 face = at(-1, 0, 0) + at(+1, 0, 0);
+                            face = face + at(0, -1, 0);
+                            face = face + at(0, +1, 0);
+                            face = face + at(0, 0, -1);
+                            face = face + at(0, 0, +1);
+                            f32 avg = T * far + Dw * edge;
+                            avg = avg + S * face;
+                            avg = avg + M * at(0, 0, 0);
+                            avg *= inverseDivisor;
+                            E[c * D.vol + D.idx(x, y, z)] += coeff * avg;
+                        }
+            return;
+        }
 #pragma omp parallel for schedule(static) collapse(2)
         for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
             for(int y = D.g[1]; y < D.g[1] + D.n[1]; ++y)
@@ -1276,6 +1389,55 @@ extern "C"
                     for(int c = 0; c < 3; ++c)
                         E[c * D.vol + i] += coeff * J[c * D.vol + i];
                 }
+    }
+
+    /** ExponentialImpl::run (P/fields/absorber/exponential/Exponential.hpp:67-108) + KernelAbsorbBorder
+     * (Exponential.kernel:45-118): for every face without neighbour, in exchange-type order RIGHT(+x), LEFT(-x),
+     * BOTTOM(+y), TOP(-y), BACK(+z), FRONT(-z): each guard cell walks inwards in steps of the guard width and damps
+     * field(cell) *= exp(-strength * factor) while factor > 0; factor = thickness-1 at the outermost active cell.
+     * The transverse range of a face is CORE+BORDER (ExchangeMappingMethods<GUARD>, ExchangeMappingMethods.hpp:60-100). */
+    void orc_absorb(OrcParams const* Pp, float* F)
+    {
+        OrcParams const& P = *Pp;
+        Dom const D(P);
+        for(int axis = 0; axis < 3; ++axis)
+            for(int side = 1; side >= 0; --side) // positive direction first (exchange types 1,3,9 are the + faces)
+            {
+                int const thickness = P.absorber_cells[axis][side];
+                if(!P.open[axis][side] || thickness == 0)
+                    continue;
+                f32 const strength = P.absorber_strength[axis][side];
+                int const rel = side ? 1 : -1;
+                int lo[3] = {D.g[0], D.g[1], D.g[2]}, hi[3] = {D.g[0] + D.n[0], D.g[1] + D.n[1], D.g[2] + D.n[2]};
+                // guard supercell layer of this face
+                lo[axis] = side ? D.g[axis] + D.n[axis] : 0;
+                hi[axis] = side ? D.N[axis] : D.g[axis];
+                for(int c = 0; c < 3; ++c)
+                {
+                    f32* f = F + c * D.vol;
+#pragma omp parallel for schedule(static) collapse(2)
+                    for(int z = lo[2]; z < hi[2]; ++z)
+                        for(int y = lo[1]; y < hi[1]; ++y)
+                            for(int x = lo[0]; x < hi[0]; ++x)
+                            {
+                                int cell[3] = {x, y, z};
+                                while(true)
+                                {
+                                    cell[axis] += D.g[axis] * -rel;
+                                    int factor;
+                                    if(rel < 0)
+                                        factor = D.g[axis] - cell[axis] + thickness - 1;
+                                    else
+                                        factor = D.g[axis] + cell[axis] - D.N[axis] + thickness;
+                                    if(factor <= 0)
+                                        break;
+                                    f32 const a = std::exp(-strength * f32(factor));
+                                    int64_t const i = D.idx(cell[0], cell[1], cell[2]);
+                                    f[i] = f[i] * a;
+                                }
+                            }
+                }
+            }
     }
 
     // ---------------------------------------------------------------------------------------------
@@ -1404,6 +1566,8 @@ extern "C"
         for(int s = 0; s < nSpecies; ++s) // CurrentDeposition (stage/CurrentDeposition.x.cpp:105-116)
             orc_deposit(Pp, sp[s].massRatio, sp[s].chargeRatio, J, sp[s].np, sp[s].pos, sp[s].mom, sp[s].w, sp[s].cell);
         orc_guard_add(Pp, J); // FieldJ::asyncCommunication (stage/CurrentInterpolationAndAdditionToEMF.hpp:99-148)
+        if(P.current_interp == 1)
+            orc_guard_copy(Pp, J); // fieldJrecv: GUARD := neighbour BORDER (FieldJ.x.cpp:118-141); all axes periodic here
         orc_add_current(Pp, E, J);
         // update_afterCurrent (FDTDBase.hpp:151-183)
         orc_guard_copy(Pp, E);

@@ -36,6 +36,10 @@ class OrcParams(C.Structure):
         ("solver", C.c_int),
         ("lehe_dir", C.c_int),
         ("wrap", C.c_int * 3),
+        ("current_interp", C.c_int),
+        ("open", (C.c_int * 2) * 3),
+        ("absorber_cells", (C.c_int * 2) * 3),
+        ("absorber_strength", (C.c_float * 2) * 3),
     ]
 
 
@@ -102,6 +106,7 @@ def lib():
     L.orc_step.argtypes = [P, f32p, f32p, f32p, C.c_int, C.POINTER(OrcSpecies)]
     L.orc_khi_init.argtypes = [P, i32p, i32p, i32p, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double, C.c_uint32,
                                f32p, f32p, f32p, i32p, f32p, f32p, f32p, i32p]
+    L.orc_absorb.argtypes = [P, f32p]
     L.orc_num_threads.restype = C.c_int
     L.orc_set_num_threads.argtypes = [C.c_int]
     _LIB = L
@@ -129,6 +134,13 @@ def make_params(cfg):
     p.current = int(g("current_solver"))
     p.solver = int(g("field_solver"))
     p.lehe_dir = int(g("lehe_dir"))
+    p.current_interp = int(g("current_interpolation")) if _has(cfg, "current_interpolation") else 0
+    absorbing = _has(cfg, "absorber_kind") and int(g("absorber_kind")) == 1
+    for d in range(3):
+        for sd in range(2):
+            p.open[d][sd] = int(g("open")[d][sd]) if _has(cfg, "open") else 0
+            p.absorber_cells[d][sd] = int(g("absorber_cells")[d][sd]) if absorbing else 0
+            p.absorber_strength[d][sd] = float(g("absorber_strength")[d][sd]) if absorbing else 0.0
     return p
 
 
@@ -200,6 +212,51 @@ class Oracle:
                 assert s[k].flags["C_CONTIGUOUS"]
                 setattr(arr[i], k, s[k].ctypes.data)
         self.L.orc_step(C.byref(self.p), E, B, J, len(species), arr)
+
+    def absorb(self, F):
+        self.L.orc_absorb(C.byref(self.p), F)
+
+    def step_open(self, E, B, J, species):
+        """One PIC step for a single domain with any mix of periodic and open (absorbing) axes, composed of the stage
+        calls in the order of Simulation::runOneStep (Simulation.hpp:526-541).  Particles that leave through an open
+        face are deleted before the current deposition (Particles.tpp:322-368: push, shift, applyBoundary).
+        species dicts are updated (arrays are REPLACED when particles were absorbed).  Exchange passes are done
+        axis by axis over the periodic axes only (orc_halo_axis)."""
+        periodic = [bool(self.p.wrap[d]) for d in range(3)]
+        g = self.g
+        J[...] = 0
+        for s in species:
+            self.push(s["massRatio"], s["chargeRatio"], E, B, s["pos"], s["mom"], s["w"], s["cell"])
+            keep = s["cell"] >= 0
+            if not keep.all():
+                s["pos"] = np.ascontiguousarray(s["pos"][:, keep])
+                s["mom"] = np.ascontiguousarray(s["mom"][:, keep])
+                s["w"] = np.ascontiguousarray(s["w"][keep])
+                s["cell"] = np.ascontiguousarray(s["cell"][keep])
+
+        def copy_guards(F, width=None):
+            for a in range(3):
+                if periodic[a]:
+                    w = g[a] if width is None else width
+                    self.halo_axis(F, a, w, w, add=False)
+
+        self.update_b_half(E, B)
+        copy_guards(B)
+        self.update_e(E, B)
+        for s in species:
+            if s["w"].shape[0]:
+                self.deposit(s["massRatio"], s["chargeRatio"], J, s["pos"], s["mom"], s["w"], s["cell"])
+        for a in range(3):
+            if periodic[a]:
+                self.halo_axis(J, a, g[a], g[a], add=True)
+        if self.p.current_interp == 1:
+            copy_guards(J, 1)
+        self.add_current(E, J)
+        self.absorb(E)
+        copy_guards(E)
+        self.update_b_half(E, B)
+        self.absorb(B)
+        copy_guards(B)
 
     def field_energy(self, E, B):
         out = np.zeros(2, np.float64)

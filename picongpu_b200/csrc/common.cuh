@@ -65,6 +65,19 @@ namespace picstep
         float cell[3];
         float dt, c, eps0, mue0;
         int lehe_dir;
+        // guard exchange passes span [tlo, thi) of the padded extent of a transverse axis: the whole extent where the
+        // axis is periodic / has a neighbour rank on that side, only the active cells where it ends at an open boundary
+        // (the reference has no edge / corner exchange across a missing neighbour, Mask::getRelativeDirections)
+        int tlo[3], thi[3];
+    };
+
+    // exponential field absorber: thickness per [axis][side] (0 where the face is not absorbing) and the tabulated
+    // attenuation exp(-strength * factor), factor < ABS_MAX, in device memory
+    constexpr int ABS_MAX = 256;
+    struct AbsorberDev
+    {
+        int cells[3][2];
+        float const* damp;
     };
 
     struct SpeciesDev

@@ -115,6 +115,98 @@ namespace picstep
             E.c[c][i] += coeff * J.c[c][i];
     }
 
+    // KernelAddCurrentDensity + Binomial: E += coeff * (1-2-1 filter of J in x, y and z) with the reference's summation
+    // order: corners (T=1), edges (D=2), faces (S=4), centre (M=8), times 1/64 (Binomial.hpp:62-110).  J guards hold
+    // the neighbours' border values (second, "receive" exchange of FieldJ::asyncCommunication, FieldJ.x.cpp:118-141).
+    __global__ void __launch_bounds__(256) addCurrentBinomialKernel(DevParams P, Field3 E, Field3 J)
+    {
+        int const x = blockIdx.x * blockDim.x + threadIdx.x;
+        int const y = blockIdx.y * blockDim.y + threadIdx.y;
+        int const z = blockIdx.z * blockDim.z + threadIdx.z;
+        if(x >= P.n[0] || y >= P.n[1] || z >= P.n[2])
+            return;
+        long long const i = fidx(P, x + P.g[0], y + P.g[1], z + P.g[2]);
+        long long const sy = P.N[0], sz = (long long) P.N[0] * P.N[1];
+        float const coeff = -(1.0f / P.eps0) * P.dt;
+#pragma unroll
+        for(int c = 0; c < 3; ++c)
+        {
+            float const* __restrict__ j = J.c[c] + i;
+            auto at = [&](int dx, int dy, int dz) { return j[dx + dy * sy + dz * sz]; };
+            float t = at(-1, -1, -1) + at(+1, -1, -1);
+            t += at(-1, +1, -1);
+            t += at(+1, +1, -1);
+            t += at(-1, -1, +1);
+            t += at(+1, -1, +1);
+            t += at(-1, +1, +1);
+            t += at(+1, +1, +1);
+            float d = at(-1, -1, 0) + at(+1, -1, 0);
+            d += at(-1, +1, 0);
+            d += at(+1, +1, 0);
+            d += at(-1, 0, -1);
+            d += at(+1, 0, -1);
+            d += at(-1, 0, +1);
+            d += at(+1, 0, +1);
+            d += at(0, -1, -1);
+            d += at(0, +1, -1);
+            d += at(0, -1, +1);
+            d += at(0, +1, +1);
+            float f = at(-1, 0, 0) + at(+1, 0, 0);
+            f += at(0, -1, 0);
+            f += at(0, +1, 0);
+            f += at(0, 0, -1);
+            f += at(0, 0, +1);
+            float avg = 1.0f * t + 2.0f * d;
+            avg = avg + 4.0f * f;
+            avg = avg + 8.0f * at(0, 0, 0);
+            avg *= 1.0f / 64.0f;
+            E.c[c][i] += coeff * avg;
+        }
+    }
+
+    // exponential::KernelAbsorbBorder (Exponential.kernel:45-118) for all six faces in the order of Exponential.hpp:70-108
+    // (x+, x-, y+, y-, z+, z-): every active cell closer than `cells` to an absorbing face is multiplied by
+    // exp(-strength * factor), factor = cells-1 ... 1 from the face inwards.  The attenuation factors are tabulated on
+    // the host with the same libm call the CPU reference makes: damp[(axis*2+side)*ABS_MAX + factor].
+    __global__ void __launch_bounds__(256) absorbKernel(DevParams P, Field3 F, AbsorberDev A)
+    {
+        int const x = blockIdx.x * blockDim.x + threadIdx.x;
+        int const y = blockIdx.y * blockDim.y + threadIdx.y;
+        int const z = blockIdx.z * blockDim.z + threadIdx.z;
+        if(x >= P.n[0] || y >= P.n[1] || z >= P.n[2])
+            return;
+        int const q[3] = {x, y, z};
+        int fac[6];
+        bool any = false;
+#pragma unroll
+        for(int a = 0; a < 3; ++a)
+        {
+            // positive side first (exchange types RIGHT, BOTTOM, BACK are odd), then negative
+            int const fp = A.cells[a][1] > 0 ? q[a] - P.n[a] + A.cells[a][1] : 0;
+            int const fn = A.cells[a][0] > 0 ? A.cells[a][0] - 1 - q[a] : 0;
+            fac[2 * a] = fp > 0 ? fp : 0;
+            fac[2 * a + 1] = fn > 0 ? fn : 0;
+            any = any || fp > 0 || fn > 0;
+        }
+        if(!any)
+            return;
+        long long const i = fidx(P, x + P.g[0], y + P.g[1], z + P.g[2]);
+#pragma unroll
+        for(int c = 0; c < 3; ++c)
+        {
+            float v = F.c[c][i];
+#pragma unroll
+            for(int a = 0; a < 3; ++a)
+            {
+                if(fac[2 * a])
+                    v = v * A.damp[(2 * a + 1) * ABS_MAX + fac[2 * a]];
+                if(fac[2 * a + 1])
+                    v = v * A.damp[(2 * a + 0) * ABS_MAX + fac[2 * a + 1]];
+            }
+            F.c[c][i] = v;
+        }
+    }
+
     // ---- guard exchange ------------------------------------------------------------------------------------------
     // One axis at a time (x, then y, then z for copies; the same order for the J reduction), every pass spanning the
     // full padded extent of the two other axes, so the 26 directions of the reference collapse into 3 passes.
@@ -127,6 +219,12 @@ namespace picstep
         c[(axis == 0) ? 1 : 0] = u;
         c[(axis == 2) ? 1 : 2] = v;
         return fidx(P, c[0], c[1], c[2]);
+    }
+
+    __device__ __forceinline__ bool slabInRange(DevParams const& P, int axis, int u, int v)
+    {
+        int const au = (axis == 0) ? 1 : 0, av = (axis == 2) ? 1 : 2;
+        return u >= P.tlo[au] && u < P.thi[au] && v >= P.tlo[av] && v < P.thi[av];
     }
 
     // local periodic wrap: dst planes <- (or +=) src planes, all three components
@@ -163,6 +261,8 @@ namespace picstep
                     w = int(r / V);
                 }
             }
+            if(!slabInRange(P, axis, u, v))
+                continue;
             long long const s = slabIndex(P, axis, srcStart + w, u, v), d = slabIndex(P, axis, dstStart + w, u, v);
             if(ADD)
                 F.c[comp][d] += F.c[comp][s];
@@ -185,7 +285,7 @@ namespace picstep
             r /= U;
             int const v = int(r % V);
             int const w = int(r / V);
-            buf[t] = F.c[comp][slabIndex(P, axis, start + w, u, v)];
+            buf[t] = slabInRange(P, axis, u, v) ? F.c[comp][slabIndex(P, axis, start + w, u, v)] : 0.0f;
         }
     }
 
@@ -203,6 +303,8 @@ namespace picstep
             r /= U;
             int const v = int(r % V);
             int const w = int(r / V);
+            if(!slabInRange(P, axis, u, v))
+                continue;
             long long const d = slabIndex(P, axis, start + w, u, v);
             if(ADD)
                 F.c[comp][d] += buf[t];
@@ -372,10 +474,20 @@ namespace picstep
         return cudaGetLastError();
     }
 
-    cudaError_t launchAddCurrent(DevParams const& P, Field3 E, Field3 J, cudaStream_t st)
+    cudaError_t launchAddCurrent(DevParams const& P, Field3 E, Field3 J, bool binomial, cudaStream_t st)
     {
         dim3 const b(32, 4, 2);
-        addCurrentKernel<<<cellGrid(P, b), b, 0, st>>>(P, E, J);
+        if(binomial)
+            addCurrentBinomialKernel<<<cellGrid(P, b), b, 0, st>>>(P, E, J);
+        else
+            addCurrentKernel<<<cellGrid(P, b), b, 0, st>>>(P, E, J);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchAbsorb(DevParams const& P, Field3 F, AbsorberDev const& A, cudaStream_t st)
+    {
+        dim3 const b(32, 4, 2);
+        absorbKernel<<<cellGrid(P, b), b, 0, st>>>(P, F, A);
         return cudaGetLastError();
     }
 

@@ -36,7 +36,8 @@ namespace picstep
     cudaError_t launchSupercellCounts(uint32_t const*, long long*, int, cudaStream_t);
     cudaError_t launchUpdateBHalf(int, DevParams const&, LeheCoeffs const&, Field3, Field3, cudaStream_t);
     cudaError_t launchUpdateE(DevParams const&, LeheCoeffs const&, Field3, Field3, cudaStream_t);
-    cudaError_t launchAddCurrent(DevParams const&, Field3, Field3, cudaStream_t);
+    cudaError_t launchAddCurrent(DevParams const&, Field3, Field3, bool, cudaStream_t);
+    cudaError_t launchAbsorb(DevParams const&, Field3, AbsorberDev const&, cudaStream_t);
     cudaError_t launchHaloLocal(bool, DevParams const&, Field3, int, int, int, int, int, cudaStream_t);
     cudaError_t launchHaloPack(DevParams const&, Field3, int, int, int, int, float*, cudaStream_t);
     cudaError_t launchHaloUnpack(bool, DevParams const&, Field3, int, int, int, int, float const*, cudaStream_t);
@@ -92,6 +93,9 @@ struct picstep_ctx
     picstep_params prm{};
     DevParams P{};
     LeheCoeffs lehe{};
+    AbsorberDev absorber{}; // exponential absorber: thickness per face (0 = not absorbing) + attenuation table
+    float* dampDev = nullptr;
+    bool absorbing = false;
     int device = 0;
     cudaStream_t stream = nullptr;
     float* fieldMem[3] = {}; // E,B,J : 3*vol floats each
@@ -313,15 +317,19 @@ namespace
     };
 
     // ---- guard exchange of one field along all axes ------------------------------------------------------------
-    int exchangeField(picstep_ctx* c, int f)
+    // mode -1: by field (E,B: guard := neighbour border; J: border += neighbour guard), 0: copy, 1: add;
+    // width >= 0 overrides the margins of picstep_exchange_widths on both sides
+    int exchangeField(picstep_ctx* c, int f, int mode = -1, int width = -1)
     {
         DevParams const& P = c->P;
         Field3 F = fieldOf(c, f);
-        bool const add = (f == PICSTEP_FIELD_J);
+        bool const add = mode < 0 ? (f == PICSTEP_FIELD_J) : (mode == 1);
         for(int a = 0; a < 3; ++a)
         {
             int w[2];
             picstep_exchange_widths(c->prm.shape, c->prm.field_solver, c->prm.lehe_dir, f, a, w);
+            if(width >= 0)
+                w[0] = w[1] = width;
             int const lo = w[0], up = w[1];
             int const g = P.g[a], n = P.n[a];
             if(P.wrap[a])
@@ -563,10 +571,16 @@ extern "C"
             return fail(nullptr, PICSTEP_ERR_INVALID, "only SuperCellSize 8x8x4 is compiled in");
         if(p->guard_supercells[0] != 1 || p->guard_supercells[1] != 1 || p->guard_supercells[2] != 1)
             return fail(nullptr, PICSTEP_ERR_INVALID, "only GuardSize 1x1x1 is supported");
-        if(p->shape < 0 || p->shape > 4 || p->pusher < 0 || p->pusher > 1 || p->current_solver < 0 || p->current_solver > 1 || p->field_solver < 0 || p->field_solver > 1 || p->lehe_dir < 0 || p->lehe_dir > 2)
+        if(p->shape < 0 || p->shape > 4 || p->pusher < 0 || p->pusher > 2 || p->current_solver < 0 || p->current_solver > 1 || p->field_solver < 0 || p->field_solver > 1 || p->lehe_dir < 0 || p->lehe_dir > 2)
             return fail(nullptr, PICSTEP_ERR_INVALID, "unknown shape / pusher / current solver / field solver");
         if(p->current_solver == PICSTEP_CURRENT_EMZ && p->shape == PICSTEP_SHAPE_NGP)
             return fail(nullptr, PICSTEP_ERR_INVALID, "EmZ needs at least CIC");
+        if(p->current_interpolation < 0 || p->current_interpolation > 1 || p->absorber_kind < 0 || p->absorber_kind > 1)
+            return fail(nullptr, PICSTEP_ERR_INVALID, "unknown current interpolation / absorber kind");
+        for(int d = 0; d < 3; ++d)
+            for(int sd = 0; sd < 2; ++sd)
+                if(p->absorber_kind && (p->absorber_cells[d][sd] < 0 || p->absorber_cells[d][sd] >= ABS_MAX || p->absorber_cells[d][sd] > p->grid[d]))
+                    return fail(nullptr, PICSTEP_ERR_INVALID, "absorber thickness must be in [0, min(255, local grid)]");
         int nsplit = 0, split = -1;
         for(int d = 0; d < 3; ++d)
         {
@@ -612,6 +626,24 @@ extern "C"
             picstep_neighbor_ranks(p->devices, p->periodic, c->rank, split, &c->rankLo, &c->rankHi);
         P.has_lower = c->rankLo >= 0;
         P.has_upper = c->rankHi >= 0;
+        std::vector<float> damp(size_t(6) * ABS_MAX, 1.0f);
+        for(int d = 0; d < 3; ++d)
+        {
+            // does a neighbour (possibly this rank itself through the periodic wrap) exist below / above along d?
+            bool const nbLo = P.wrap[d] || (d == split && c->rankLo >= 0);
+            bool const nbHi = P.wrap[d] || (d == split && c->rankHi >= 0);
+            P.tlo[d] = nbLo ? 0 : P.g[d];
+            P.thi[d] = nbHi ? P.N[d] : P.g[d] + P.n[d];
+            bool const nb[2] = {nbLo, nbHi};
+            for(int sd = 0; sd < 2; ++sd)
+            {
+                int const cells = (p->absorber_kind == PICSTEP_ABSORBER_EXPONENTIAL && !nb[sd]) ? p->absorber_cells[d][sd] : 0;
+                c->absorber.cells[d][sd] = cells;
+                c->absorbing = c->absorbing || cells > 1;
+                for(int f = 0; f < cells; ++f) // math::exp(-absorberStrength * float_X(factor)) (Exponential.kernel:107)
+                    damp[size_t(2 * d + sd) * ABS_MAX + f] = std::exp(-p->absorber_strength[d][sd] * float(f));
+            }
+        }
         computeLehe(*p, c->lehe);
         if((long long) numCells(c) >= (1ll << 30))
         {
@@ -637,6 +669,9 @@ extern "C"
             CUC(cudaMalloc(&c->fieldMem[f], sizeof(float) * 3 * P.vol));
             CUC(cudaMemsetAsync(c->fieldMem[f], 0, sizeof(float) * 3 * P.vol, c->stream));
         }
+        CUC(cudaMalloc(&c->dampDev, sizeof(float) * damp.size()));
+        CUC(cudaMemcpy(c->dampDev, damp.data(), sizeof(float) * damp.size(), cudaMemcpyHostToDevice));
+        c->absorber.damp = c->dampDev;
         CUC(cudaMalloc(&c->redBuf, sizeof(double) * 4));
         CUC(cudaMalloc(&c->flags, sizeof(int) * 4));
         CUC(cudaMemsetAsync(c->flags, 0, sizeof(int) * 4, c->stream));
@@ -680,6 +715,7 @@ extern "C"
         for(int b = 0; b < 4; ++b)
             cudaFree(c->haloBuf[b]);
         cudaFree(c->redBuf);
+        cudaFree(c->dampDev);
         cudaFree(c->flags);
         if(c->hostPinned)
             cudaFreeHost(c->hostPinned);
@@ -1059,7 +1095,11 @@ extern "C"
         int rc = exchangeField(c, PICSTEP_FIELD_J);
         if(rc)
             return rc;
-        KL(c, 1, launchAddCurrent(c->P, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_J), c->stream));
+        bool const binomial = c->prm.current_interpolation == PICSTEP_CURRENT_INTERPOLATION_BINOMIAL;
+        if(binomial) // "receive" exchange of FieldJ: one guard cell := neighbour border (FieldJ.x.cpp:118-141, 156-174)
+            if((rc = exchangeField(c, PICSTEP_FIELD_J, 0, 1)))
+                return rc;
+        KL(c, 1, launchAddCurrent(c->P, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_J), binomial, c->stream));
         return PICSTEP_OK;
     }
 
@@ -1069,10 +1109,14 @@ extern "C"
             return PICSTEP_ERR_INVALID;
         StageTimer t(c, 6);
         Field3 E = fieldOf(c, PICSTEP_FIELD_E), B = fieldOf(c, PICSTEP_FIELD_B);
+        if(c->absorbing) // exponentialImpl.run(E) (FDTDBase.hpp:153-158)
+            KL(c, 1, launchAbsorb(c->P, E, c->absorber, c->stream));
         int rc = exchangeField(c, PICSTEP_FIELD_E);
         if(rc)
             return rc;
         KL(c, 1, launchUpdateBHalf(c->prm.field_solver, c->P, c->lehe, E, B, c->stream)); // updateBFirstHalf
+        if(c->absorbing) // exponentialImpl.run(B) (FDTDBase.hpp:175-179)
+            KL(c, 1, launchAbsorb(c->P, B, c->absorber, c->stream));
         return exchangeField(c, PICSTEP_FIELD_B);
     }
 
@@ -1083,7 +1127,21 @@ extern "C"
         CU(c, cudaSetDevice(c->device));
         int const ns = int(c->species.size());
         // fast path: the deposition does not depend on the field update, so it is fused into the push kernel
-        bool const fused = runKernelSupports(c->prm.shape, c->prm.current_solver) && !(c->prm.flags & 7);
+        // Exception: the Binomial filter next to an open face reads J guard cells that no exchange overwrites (edge /
+        // corner cells between an open and an exchanged axis).  They hold the un-folded deposits, which depend on the
+        // cell a particle is deposited from, so the reference's order (move, wrap, then deposit) has to be kept there.
+        bool staleGuardsRead = false;
+        if(c->prm.current_interpolation == PICSTEP_CURRENT_INTERPOLATION_BINOMIAL)
+        {
+            bool anyOpen = false, anyExchange = false;
+            for(int d = 0; d < 3; ++d)
+            {
+                anyOpen = anyOpen || c->P.tlo[d] != 0 || c->P.thi[d] != c->P.N[d];
+                anyExchange = anyExchange || c->P.wrap[d] || (d == c->P.split_axis && c->nranks > 1);
+            }
+            staleGuardsRead = anyOpen && anyExchange;
+        }
+        bool const fused = runKernelSupports(c->prm.shape, c->prm.current_solver) && !(c->prm.flags & 7) && !staleGuardsRead;
         for(uint32_t it = 0; it < n; ++it)
         {
             uint32_t const step = first + it;

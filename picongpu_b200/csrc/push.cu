@@ -67,10 +67,7 @@ namespace picstep
             gatherEB<SHAPE>(tB, tE, lx, ly, lz, px, py, pz, Ef, Bf);
             float const mass = S.mass_per_w * w;
             float const charge = S.charge_per_w * w;
-            if constexpr(PUSHER == 0)
-                boris(P, mass, charge, Ef, Bf, u);
-            else
-                vay(P, rc2, mass, charge, Ef, Bf, u);
+            pushMomentum<PUSHER>(P, rc2, mass, charge, Ef, Bf, u);
             float vx, vy, vz;
             velocityOf(rc2, mass, u[0], u[1], u[2], vx, vy, vz);
             float np[3] = {px + ps_div(vx * P.dt, P.cell[0]), py + ps_div(vy * P.dt, P.cell[1]), pz + ps_div(vz * P.dt, P.cell[2])};
@@ -190,6 +187,11 @@ namespace picstep
         PS_CASE(2, 1)
         PS_CASE(3, 1)
         PS_CASE(4, 1)
+        PS_CASE(0, 2)
+        PS_CASE(1, 2)
+        PS_CASE(2, 2)
+        PS_CASE(3, 2)
+        PS_CASE(4, 2)
 #undef PS_CASE
         return cudaErrorInvalidValue;
     }

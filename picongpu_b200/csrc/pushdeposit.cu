@@ -232,10 +232,7 @@ namespace picstep
                 {
                     float Bf[3], Ef[3];
                     gatherEB<SHAPE>(tB, tE, lx, ly, lz, x1[0], x1[1], x1[2], Ef, Bf);
-                    if constexpr(PUSHER == 0)
-                        boris(P, mass, charge, Ef, Bf, u);
-                    else
-                        vay(P, rc2, mass, charge, Ef, Bf, u);
+                    pushMomentum<PUSHER>(P, rc2, mass, charge, Ef, Bf, u);
                     velocityOf(rc2, mass, u[0], u[1], u[2], vel[0], vel[1], vel[2]);
                     // moveParticle (MoveParticle.hpp:48-160)
 #pragma unroll
@@ -569,6 +566,10 @@ namespace picstep
         PS_CASE(1, 1)
         PS_CASE(2, 1)
         PS_CASE(3, 1)
+        PS_CASE(0, 2)
+        PS_CASE(1, 2)
+        PS_CASE(2, 2)
+        PS_CASE(3, 2)
 #undef PS_CASE
         return cudaErrorInvalidValue;
     }

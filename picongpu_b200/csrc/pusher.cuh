@@ -263,4 +263,66 @@ namespace picstep
             u[d] = s * (mp[d] + dp * t[d] + cr[d]);
     }
 
+    // particlePusherHigueraCary.hpp:45-145 (auxiliary quantities in fp64: sqrt_HigueraCary = precision64Bit,
+    // param/pusher.param:71; Gamma<> itself computes in fp32)
+    __device__ __forceinline__ void higueraCary(DevParams const& P, float mass, float charge, float const E[3], float const B[3], float u[3])
+    {
+        float const dt = P.dt;
+        float he[3], mm[3];
+        double mmd[3], tau[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+        {
+            he[d] = 0.5f * charge * E[d] * dt;
+            mm[d] = u[d] + he[d];
+            mmd[d] = double(mm[d]);
+            tau[d] = double(ps_div(0.5f * B[d] * charge * dt, mass));
+        }
+        double const gm = double(gammaOf(P.c, mm[0], mm[1], mm[2], mass));
+        double tau2 = tau[0] * tau[0];
+        tau2 += tau[1] * tau[1];
+        tau2 += tau[2] * tau[2];
+        double const sigma = gm * gm - tau2;
+        double dpt = mmd[0] * tau[0];
+        dpt += mmd[1] * tau[1];
+        dpt += mmd[2] * tau[2];
+        double const ustar = dpt / double(mass * P.c);
+        double const gplus = sqrt(0.5 * (sigma + sqrt(sigma * sigma + 4.0 * (tau2 + ustar * ustar))));
+        double t[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            t[d] = tau[d] / gplus;
+        double t2 = t[0] * t[0];
+        t2 += t[1] * t[1];
+        t2 += t[2] * t[2];
+        double const sf = 1.0 / (1.0 + t2);
+        double dmt = mmd[0] * t[0];
+        dmt += mmd[1] * t[1];
+        dmt += mmd[2] * t[2];
+        double const cr[3] = {mmd[1] * t[2] - mmd[2] * t[1], mmd[2] * t[0] - mmd[0] * t[2], mmd[0] * t[1] - mmd[1] * t[0]};
+        double mp[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            mp[d] = sf * (mmd[d] + dmt * t[d] + cr[d]);
+        double const c2[3] = {mp[1] * t[2] - mp[2] * t[1], mp[2] * t[0] - mp[0] * t[2], mp[0] * t[1] - mp[1] * t[0]};
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+        {
+            float const diff = he[d] + float(c2[d]);
+            u[d] = float(mp[d]) + diff;
+        }
+    }
+
+    /** UsedParticlePusher dispatch: 0 Boris, 1 Vay, 2 HigueraCary */
+    template<int PUSHER>
+    __device__ __forceinline__ void pushMomentum(DevParams const& P, float rc2, float mass, float charge, float const E[3], float const B[3], float u[3])
+    {
+        if constexpr(PUSHER == 0)
+            boris(P, mass, charge, E, B, u);
+        else if constexpr(PUSHER == 1)
+            vay(P, rc2, mass, charge, E, B, u);
+        else
+            higueraCary(P, mass, charge, E, B, u);
+    }
+
 } // namespace picstep

@@ -12,12 +12,12 @@ import numpy as np
 
 # enums shared with include/picstep.h
 SHAPE_NGP, SHAPE_CIC, SHAPE_TSC, SHAPE_PQS, SHAPE_PCS = range(5)
-PUSHER_BORIS, PUSHER_VAY = range(2)
+PUSHER_BORIS, PUSHER_VAY, PUSHER_HIGUERA_CARY = range(3)
 CURRENT_ESIRKEPOV, CURRENT_EMZ = range(2)
 SOLVER_YEE, SOLVER_LEHE = range(2)
 
 SHAPE_NAMES = {"NGP": 0, "CIC": 1, "TSC": 2, "PQS": 3, "PCS": 4}
-PUSHER_NAMES = {"Boris": 0, "Vay": 1}
+PUSHER_NAMES = {"Boris": 0, "Vay": 1, "HigueraCary": 2}
 CURRENT_NAMES = {"Esirkepov": 0, "EmZ": 1, "EZ": 1}
 SOLVER_NAMES = {"Yee": 0, "Lehe": 1}
 
@@ -60,6 +60,12 @@ class SimParams:
     current_solver: int = CURRENT_ESIRKEPOV
     field_solver: int = SOLVER_YEE
     lehe_dir: int = 1
+    # --- --currentInterpolation (0 none, 1 binomial); fieldAbsorber.param (0 none, 1 exponential; NUM_CELLS and
+    #     exponential::STRENGTH per [axis][negative, positive], only used at non-periodic outer boundaries) ---
+    current_interpolation: int = 0
+    absorber_kind: int = 0
+    absorber_cells: tuple = ((12, 12), (12, 12), (12, 12))
+    absorber_strength: tuple = ((1.0e-3, 1.0e-3), (1.0e-3, 1.0e-3), (1.0e-3, 1.0e-3))
     # --- runtime (-d, --periodic) ---
     periodic: tuple = (1, 1, 1)
     devices: tuple = (1, 1, 1)
@@ -98,6 +104,9 @@ class SimParams:
             * _f32(np.float32(self.cell_size[0]) * np.float32(self.cell_size[1]) * np.float32(self.cell_size[2]))
         )
         self.wrap = tuple(1 if (self.periodic[d] and self.devices[d] == 1) else 0 for d in range(3))
+        # open[d] = (lower, upper): this rank's face is a non-periodic outer boundary of the global domain
+        self.open = tuple((int(not self.periodic[d] and self.rank_pos[d] == 0),
+                           int(not self.periodic[d] and self.rank_pos[d] == self.devices[d] - 1)) for d in range(3))
 
     @property
     def guard_cells(self):

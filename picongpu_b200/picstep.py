@@ -60,6 +60,10 @@ class Params(C.Structure):
         ("rank_pos", C.c_int32 * 3),
         ("device", C.c_int32),
         ("flags", C.c_int32),
+        ("current_interpolation", C.c_int32),
+        ("absorber_kind", C.c_int32),
+        ("absorber_cells", (C.c_int32 * 2) * 3),
+        ("absorber_strength", (C.c_float * 2) * 3),
     ]
 
 
@@ -134,6 +138,12 @@ def to_c_params(p, device=0, flags=0):
         p.shape, p.pusher, p.current_solver, p.field_solver, p.lehe_dir)
     cp.device = device
     cp.flags = flags
+    cp.current_interpolation = int(getattr(p, "current_interpolation", 0))
+    cp.absorber_kind = int(getattr(p, "absorber_kind", 0))
+    for d in range(3):
+        for sd in range(2):
+            cp.absorber_cells[d][sd] = int(getattr(p, "absorber_cells", ((0, 0),) * 3)[d][sd])
+            cp.absorber_strength[d][sd] = float(getattr(p, "absorber_strength", ((0.0, 0.0),) * 3)[d][sd])
     return cp
 
 

@@ -133,7 +133,7 @@ def test_gather(orc, shape, exact):
 # ---------------------------------------------------------------------------------------------------------------
 # push + move + re-sort
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("pusher", [prm.PUSHER_BORIS, prm.PUSHER_VAY])
+@pytest.mark.parametrize("pusher", [prm.PUSHER_BORIS, prm.PUSHER_VAY, prm.PUSHER_HIGUERA_CARY])
 @pytest.mark.parametrize("shape", [prm.SHAPE_CIC, prm.SHAPE_TSC, prm.SHAPE_PCS])
 def test_push_and_resort_exact(orc, pusher, shape):
     """Exact build: positions, momenta and every integer (cell, supercell counts) bit identical to the oracle."""
@@ -166,7 +166,7 @@ def test_push_and_resort_exact(orc, pusher, shape):
     s.close()
 
 
-@pytest.mark.parametrize("pusher", [prm.PUSHER_BORIS, prm.PUSHER_VAY])
+@pytest.mark.parametrize("pusher", [prm.PUSHER_BORIS, prm.PUSHER_VAY, prm.PUSHER_HIGUERA_CARY])
 def test_push_production_tolerance(orc, pusher):
     """Production build (FMA, rsqrtf): momenta/positions within 1e-6 relative; cells equal except for particles whose
     new position is within rounding distance of a face."""
@@ -413,10 +413,10 @@ def test_khi_step_stage_calls_equal_fused_step(orc):
 
 
 @pytest.mark.parametrize("exact", [True, False])
-@pytest.mark.parametrize("shape,pusher", [(prm.SHAPE_TSC, prm.PUSHER_BORIS), (prm.SHAPE_CIC, prm.PUSHER_VAY), (prm.SHAPE_PQS, prm.PUSHER_BORIS)])
+@pytest.mark.parametrize("shape,pusher", [(prm.SHAPE_TSC, prm.PUSHER_BORIS), (prm.SHAPE_CIC, prm.PUSHER_VAY), (prm.SHAPE_PQS, prm.PUSHER_BORIS), (prm.SHAPE_TSC, prm.PUSHER_HIGUERA_CARY)])
 def test_fused_push_equals_separate_kernels(orc, exact, shape, pusher):
     """One step from identical fields and particles: the fused push+deposit kernel must move every particle exactly
-    like the stand-alone push kernel (bit-identical positions, momenta, cells) and deposit the same current."""
+    like the stand-alone push kernel (exact build: bit-identical positions, momenta, cells) and deposit the same current."""
     p = util.make_params((16, 16, 8), shape=shape, pusher=pusher)
     E, B = util.smooth_fields(p, seed=5, amp=0.05)
     pos, mom, w, cell = util.random_particles(p, ppc=6, seed=9, thermal=0.4)
@@ -430,9 +430,17 @@ def test_fused_push_equals_separate_kernels(orc, exact, shape, pusher):
         res.append((util.order_by_weight(*s.download_particles("e")), s.download_field(FJ), s.supercell_counts("e")))
         s.close()
     (pa, Ja, ca), (pb, Jb, cb) = res
-    for x, y in zip(pa, pb):
-        assert np.array_equal(x, y)
-    assert np.array_equal(ca, cb)
+    if exact:
+        for x, y in zip(pa, pb):
+            assert np.array_equal(x, y)
+        assert np.array_equal(ca, cb)
+    else:
+        # production build: the compiler may contract multiply-adds differently in the two kernels (last-bit effects)
+        same = pa[3] == pb[3]
+        assert same.mean() > 0.9999
+        assert np.abs(pa[0][:, same] - pb[0][:, same]).max() < 2e-6
+        assert _relerr(pa[1], pb[1]) < 1e-6
+        assert np.abs(ca - cb).sum() <= 2
     # interior only: the guard cells hold the un-folded contributions, which depend on the anchor cell of the window
     g, n = p.guard_cells, p.grid
     Ja, Jb = (x[:, g[2]:g[2] + n[2], g[1]:g[1] + n[1], g[0]:g[0] + n[0]] for x in (Ja, Jb))
@@ -533,3 +541,87 @@ def test_step_host_matches_device_resident(orc):
     assert en[2] > 0
     s.close()
     s2.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY 8(f) widening: Binomial current interpolation, exponential absorber + absorbing particle boundary
+# ---------------------------------------------------------------------------------------------------------------
+def test_binomial_add_current_exact(orc):
+    """E += coeff * Binomial(J) with the reference's summation order: bit identical in the exact build."""
+    p = util.make_params((24, 16, 8), current_interpolation=1)
+    rng = np.random.RandomState(3)
+    o = orc.Oracle(p)
+    J = util.pad_periodic(rng.normal(size=(3, 8, 16, 24)).astype(np.float32), p.guard_cells)
+    E0 = util.pad_periodic(rng.normal(size=(3, 8, 16, 24)).astype(np.float32), p.guard_cells)
+    s = _sim(p, True)
+    s.upload_field(FE, E0)
+    # picstep_add_current first folds J guards into the border, then fills one guard cell: start from zero guards
+    Jz = np.zeros_like(J)
+    o.interior(Jz)[...] = o.interior(J)
+    s.upload_field(FJ, Jz)
+    s.add_current()
+    Eg = s.download_field(FE)
+    E = E0.copy()
+    o.add_current(E, J)
+    assert np.array_equal(o.interior(Eg), o.interior(E))
+    s.close()
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("periodic,interp", [((1, 0, 1), 0), ((0, 0, 0), 1), ((0, 1, 1), 1)])
+def test_open_boundary_steps_vs_oracle(orc, exact, periodic, interp):
+    """Absorbing particle boundary + exponential field absorber (+ Binomial filter) over 20 coupled steps: particle
+    counts equal the oracle's (absorbed particles are deleted before the deposition), fields within tolerance."""
+    p = util.make_params((16, 16, 8), periodic=periodic, current_interpolation=interp, absorber_kind=1,
+                         absorber_cells=((6, 6), (5, 7), (3, 3)), absorber_strength=((0.05, 0.05), (0.1, 0.02), (0.2, 0.2)))
+    o, e, i = util.khi_ic(orc, p)
+    # hot electrons so that a visible fraction reaches the open faces
+    rng = np.random.RandomState(11)
+    e["mom"] += (rng.normal(size=e["mom"].shape) * 0.3).astype(np.float32) * (np.float32(p.base_mass) * e["w"] * np.float32(p.c))
+    s = _sim(p, exact)
+    for name, sp in (("e", e), ("i", i)):
+        s.upload_particles(name, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+    n0 = e["w"].shape[0]
+    E, B, J = o.field(), o.field(), o.field()
+    steps = 20
+    for _ in range(steps):
+        o.step_open(E, B, J, [e, i])
+    s.step(steps)
+    s.sync()
+    assert e["w"].shape[0] < n0, "no particle was absorbed: the test would not test anything"
+    ne, ni = s.particle_count("e"), s.particle_count("i")
+    if exact:
+        assert (ne, ni) == (e["w"].shape[0], i["w"].shape[0])
+    else:
+        assert abs(ne - e["w"].shape[0]) <= 3 and abs(ni - i["w"].shape[0]) <= 3
+    Eg, Bg = s.download_field(FE), s.download_field(FB)
+    scale = np.abs(o.interior(E)).max()
+    tol = 2e-5 if exact else 2e-4
+    assert np.abs(o.interior(Eg) - o.interior(E)).max() / scale < tol
+    assert np.abs(o.interior(Bg) - o.interior(B)).max() / np.abs(o.interior(B)).max() < tol
+    s.close()
+
+
+def test_absorber_damps_outgoing_wave():
+    """Physics check of the absorber: a pulse leaving through an absorbing face loses energy, the same pulse in a
+    periodic box does not."""
+    res = {}
+    for kind in (0, 1):
+        p = util.make_params((64, 8, 4), periodic=(0, 1, 1), absorber_kind=kind, absorber_cells=((24, 24), (0, 0), (0, 0)),
+                             absorber_strength=((0.05, 0.05), (0, 0), (0, 0)))
+        s = _sim(p, False)
+        N = p.padded
+        x = np.arange(N[0]) - p.guard_cells[0]
+        E = np.zeros((3, N[2], N[1], N[0]), np.float32)
+        B = np.zeros_like(E)
+        env = np.exp(-((x - 32.0) / 5.0) ** 2) * np.cos(2 * np.pi * (x - 32.0) / 8.0)
+        E[1] = env[None, None, :]
+        xb = x + 0.5
+        B[2] = (np.exp(-((xb - 32.0) / 5.0) ** 2) * np.cos(2 * np.pi * (xb - 32.0) / 8.0) / p.c)[None, None, :]
+        s.upload_field(FE, E)
+        s.upload_field(FB, B)
+        e0 = s.field_energy().sum()
+        s.step(int(3 * 64 * p.cell_size[0] / (p.c * p.dt)))
+        res[kind] = s.field_energy().sum() / e0
+        s.close()
+    assert res[1] < 0.05 and res[1] < 0.2 * res[0], res
