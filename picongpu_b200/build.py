@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["picstep.cu", "push.cu", "pushdeposit.cu", "deposit.cu", "resort.cu", "fields.cu", "init.cu", "comm.cu"]
-HEADERS = ["common.cuh", "shapes.cuh", "pusher.cuh", "esirkepov.cuh", "f2.cuh", os.path.join("..", "..", "include", "picstep.h")]
+HEADERS = ["common.cuh", "shapes.cuh", "pusher.cuh", "esirkepov.cuh", "f2.cuh", "tma.cuh", os.path.join("..", "..", "include", "picstep.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 VARIANTS = {

@@ -3,6 +3,7 @@
 // on one compute stream; guard/migration traffic between ranks goes through NCCL send/recv (comm.cu).
 #include "../../include/picstep.h"
 #include "common.cuh"
+#include "tma.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -14,12 +15,14 @@
 namespace picstep
 {
     // kernels (push.cu, deposit.cu, resort.cu, fields.cu, init.cu)
-    cudaError_t launchPush(int, int, DevParams const&, SpeciesDev const&, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, cudaStream_t);
+    cudaError_t launchPush(int, int, DevParams const&, SpeciesDev const&, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, TileMaps const&, cudaStream_t);
+    void tileBox(int, int*, int*);
+    int makeTileMap(CUtensorMap*, float*, int const*, long long, int const*, char*, size_t);
     cudaError_t launchGather(int, DevParams const&, SpeciesDev const&, Field3, Field3, uint32_t const*, float*, long long, cudaStream_t);
     cudaError_t launchDeposit(int, int, bool, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
     bool runKernelSupports(int, int);
     cudaError_t launchDepositRun(int, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
-    cudaError_t launchPushDeposit(int, int, DevParams const&, SpeciesDev const&, SpeciesDev const&, uint32_t const*, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, cudaStream_t);
+    cudaError_t launchPushDeposit(int, int, DevParams const&, SpeciesDev const&, SpeciesDev const&, uint32_t const*, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, TileMaps const&, cudaStream_t);
     cudaError_t launchInvertRanked(uint32_t const*, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t const*, uint32_t*, uint16_t*, cudaStream_t);
     cudaError_t launchAppendRecords(MigRecord const*, uint32_t, uint32_t const*, uint32_t, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, uint32_t*, int*, cudaStream_t);
     cudaError_t launchGatherPerm(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t, cudaStream_t);
@@ -93,12 +96,14 @@ struct picstep_ctx
     picstep_params prm{};
     DevParams P{};
     LeheCoeffs lehe{};
+    TileMaps tileMaps{}; // TMA descriptors of E and B for the supercell tile of this shape
     AbsorberDev absorber{}; // exponential absorber: thickness per face (0 = not absorbing) + attenuation table
     float* dampDev = nullptr;
     bool absorbing = false;
     int device = 0;
     cudaStream_t stream = nullptr;
-    float* fieldMem[3] = {}; // E,B,J : 3*vol floats each
+    float* fieldMem[3] = {}; // E,B,J : 3*vol floats each, fieldAlloc + tileMaps.lead floats
+    float* fieldAlloc[3] = {}; // the cudaMalloc'ed blocks
     float* rho = nullptr; // vol floats (Gauss check scratch)
     float* aosTmp = nullptr; // 3*vol floats (layout conversion scratch)
     float* haloBuf[4] = {}; // sendLo, sendHi, recvLo, recvHi
@@ -664,10 +669,26 @@ extern "C"
     } while(0)
         CUC(cudaSetDevice(c->device));
         CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        int tbox[3], tlo = 0;
+        tileBox(p->shape, tbox, &tlo);
+        c->tileMaps.lead = tlo & 3;
         for(int f = 0; f < 3; ++f)
         {
-            CUC(cudaMalloc(&c->fieldMem[f], sizeof(float) * 3 * P.vol));
-            CUC(cudaMemsetAsync(c->fieldMem[f], 0, sizeof(float) * 3 * P.vol, c->stream));
+            // The fields start `lead` floats into their allocation so that the x origin of every supercell tile
+            // (8k + 8 - margin) is a 16-byte aligned address: TMA box coordinates have to be (coordinate 0 of the
+            // descriptor, which is anchored at the allocation, is then a multiple of four floats).
+            CUC(cudaMalloc(&c->fieldAlloc[f], sizeof(float) * (3 * P.vol + 4)));
+            c->fieldMem[f] = c->fieldAlloc[f] + c->tileMaps.lead;
+            CUC(cudaMemsetAsync(c->fieldAlloc[f], 0, sizeof(float) * (3 * P.vol + 4), c->stream));
+        }
+        {
+            char msg[128];
+            for(int f = 0; f < 2; ++f)
+                if(makeTileMap(f == PICSTEP_FIELD_E ? &c->tileMaps.E : &c->tileMaps.B, c->fieldAlloc[f], P.N, P.vol, tbox, msg, sizeof(msg)))
+                {
+                    picstep_destroy(c);
+                    return fail(nullptr, PICSTEP_ERR_CUDA, msg);
+                }
         }
         CUC(cudaMalloc(&c->dampDev, sizeof(float) * damp.size()));
         CUC(cudaMemcpy(c->dampDev, damp.data(), sizeof(float) * damp.size(), cudaMemcpyHostToDevice));
@@ -709,7 +730,7 @@ extern "C"
             cudaFree(s.sendCnt);
         }
         for(int f = 0; f < 3; ++f)
-            cudaFree(c->fieldMem[f]);
+            cudaFree(c->fieldAlloc[f]);
         cudaFree(c->rho);
         cudaFree(c->aosTmp);
         for(int b = 0; b < 4; ++b)
@@ -997,7 +1018,7 @@ extern "C"
         s.ranked = false;
         if(int rc = ensureSorted(c, s))
             return rc;
-        KL(c, 1, launchPush(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], s.cellCnt, s.key, c->stream));
+        KL(c, 1, launchPush(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], s.cellCnt, s.key, c->tileMaps, c->stream));
         return PICSTEP_OK;
     }
 
@@ -1082,7 +1103,7 @@ extern "C"
         SpeciesHost& s = c->species[sp];
         if(s.capacity == 0)
             return PICSTEP_OK;
-        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), devOf(c, s, s.cur ^ 1), s.lazy ? s.inv : nullptr, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, c->stream));
+        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), devOf(c, s, s.cur ^ 1), s.lazy ? s.inv : nullptr, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, c->tileMaps, c->stream));
         s.ranked = true;
         return PICSTEP_OK;
     }

@@ -8,6 +8,9 @@
 // accumulated in shared memory and flushed with one global atomic per touched cell.
 #include "common.cuh"
 #include "pusher.cuh"
+#include "tma.cuh"
+
+#include <cstdio>
 #include "shapes.cuh"
 
 namespace picstep
@@ -20,11 +23,13 @@ namespace picstep
         Field3 B,
         uint32_t const* __restrict__ cellOff,
         uint32_t* __restrict__ cellCnt,
-        uint32_t* __restrict__ key)
+        uint32_t* __restrict__ key,
+        const __grid_constant__ TileMaps maps)
     {
         using T = Tile<SHAPE>;
-        extern __shared__ float tile[]; // [B0,B1,B2,E0,E1,E2][TZ][TY][PX] followed by the 10x10x6 histogram
-        uint32_t* hist = reinterpret_cast<uint32_t*>(tile + 6 * T::TV);
+        extern __shared__ __align__(128) float tile[]; // [B0,B1,B2 | E0,E1,E2][TZ][TY][PX] followed by the 10x10x6 histogram
+        __shared__ uint64_t tileBar;
+        uint32_t* hist = reinterpret_cast<uint32_t*>(tile + T::WORDS);
         constexpr int HX = SCX + 2, HY = SCY + 2, HZ = SCZ + 2, HV = HX * HY * HZ;
 
         int const sc = blockIdx.x;
@@ -35,25 +40,21 @@ namespace picstep
 
         for(int i = threadIdx.x; i < HV; i += blockDim.x)
             hist[i] = 0u;
-        // stage the tiles: rows of TX consecutive floats, coalesced per row
+        // stage the E and B tiles with one TMA box each (x, y, z, 3 components); the histogram is cleared meanwhile
+        if(threadIdx.x == 0)
         {
-            int const ox = scx * SCX + P.g[0] - T::LO, oy = scy * SCY + P.g[1] - T::LO, oz = scz * SCZ + P.g[2] - T::LO;
-            constexpr int ROWS = T::TY * T::TZ;
-            for(int i = threadIdx.x; i < 6 * ROWS * T::TX; i += blockDim.x)
-            {
-                int const x = i % T::TX;
-                int const row = (i / T::TX) % ROWS;
-                int const comp = i / (T::TX * ROWS);
-                int const y = row % T::TY, z = row / T::TY;
-                float const* src = comp < 3 ? B.c[comp] : E.c[comp - 3];
-                tile[comp * T::TV + row * T::PX + x] = __ldg(src + fidx(P, ox + x, oy + y, oz + z));
-            }
+            int const ox = scx * SCX + P.g[0] - T::LO + maps.lead, oy = scy * SCY + P.g[1] - T::LO, oz = scz * SCZ + P.g[2] - T::LO;
+            mbarInit(&tileBar, 1);
+            mbarExpectTx(&tileBar, 2 * T::BYTES_PER_FIELD);
+            tmaLoadTile(tile, &maps.B, ox, oy, oz, &tileBar);
+            tmaLoadTile(tile + T::HALF, &maps.E, ox, oy, oz, &tileBar);
         }
         __syncthreads();
+        mbarWait(&tileBar, 0);
 
         float const rc2 = float(1.0 / double(P.c) / double(P.c));
         float const* tB = tile;
-        float const* tE = tile + 3 * T::TV;
+        float const* tE = tile + T::HALF;
 
         for(uint32_t i = p0 + threadIdx.x; i < p1; i += blockDim.x)
         {
@@ -157,26 +158,26 @@ namespace picstep
     template<int SHAPE>
     size_t pushSmemBytes()
     {
-        return sizeof(float) * 6 * Tile<SHAPE>::TV + sizeof(uint32_t) * (SCX + 2) * (SCY + 2) * (SCZ + 2);
+        return sizeof(float) * Tile<SHAPE>::WORDS + sizeof(uint32_t) * (SCX + 2) * (SCY + 2) * (SCZ + 2);
     }
 
     template<int SHAPE, int PUSHER>
-    cudaError_t launchPushT(DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* key, cudaStream_t st)
+    cudaError_t launchPushT(DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* key, TileMaps const& maps, cudaStream_t st)
     {
         int const nscTot = P.nsc[0] * P.nsc[1] * P.nsc[2];
         size_t const smem = pushSmemBytes<SHAPE>();
         cudaError_t e = cudaFuncSetAttribute(pushKernel<SHAPE, PUSHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if(e != cudaSuccess)
             return e;
-        pushKernel<SHAPE, PUSHER><<<nscTot, 256, smem, st>>>(P, S, E, B, cellOff, cellCnt, key);
+        pushKernel<SHAPE, PUSHER><<<nscTot, 256, smem, st>>>(P, S, E, B, cellOff, cellCnt, key, maps);
         return cudaGetLastError();
     }
 
-    cudaError_t launchPush(int shape, int pusher, DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* key, cudaStream_t st)
+    cudaError_t launchPush(int shape, int pusher, DevParams const& P, SpeciesDev const& S, Field3 E, Field3 B, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* key, TileMaps const& maps, cudaStream_t st)
     {
 #define PS_CASE(SH, PU)                                                                                               \
     if(shape == SH && pusher == PU)                                                                                   \
-        return launchPushT<SH, PU>(P, S, E, B, cellOff, cellCnt, key, st);
+        return launchPushT<SH, PU>(P, S, E, B, cellOff, cellCnt, key, maps, st);
         PS_CASE(0, 0)
         PS_CASE(1, 0)
         PS_CASE(2, 0)
@@ -194,6 +195,55 @@ namespace picstep
         PS_CASE(4, 2)
 #undef PS_CASE
         return cudaErrorInvalidValue;
+    }
+
+    /** box of the E/B tile of one supercell for `shape`: {PX, TY, TZ} and the margin below the supercell origin */
+    void tileBox(int shape, int box[3], int* lo)
+    {
+#define PS_CASE(SH)                                                                                                   \
+    if(shape == SH)                                                                                                   \
+    {                                                                                                                 \
+        box[0] = Tile<SH>::PX;                                                                                        \
+        box[1] = Tile<SH>::TY;                                                                                        \
+        box[2] = Tile<SH>::TZ;                                                                                        \
+        *lo = Tile<SH>::LO;                                                                                           \
+    }
+        PS_CASE(0)
+        PS_CASE(1)
+        PS_CASE(2)
+        PS_CASE(3)
+        PS_CASE(4)
+#undef PS_CASE
+    }
+
+    /** TMA descriptor of one field: 4-D tensor (x, y, z, component) over the SoA planes, box = one supercell tile.
+     * cuTensorMapEncodeTiled is taken from the driver through the runtime (no link dependency on libcuda). */
+    int makeTileMap(CUtensorMap* map, float* base, int const N[3], long long vol, int const box[3], char* err, size_t errLen)
+    {
+        using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, cuuint64_t const*, cuuint64_t const*, cuuint32_t const*, cuuint32_t const*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static Encode encode = nullptr;
+        if(!encode)
+        {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn)
+            {
+                snprintf(err, errLen, "cuTensorMapEncodeTiled not available from the driver");
+                return 1;
+            }
+            encode = reinterpret_cast<Encode>(fn);
+        }
+        cuuint64_t const dims[4] = {cuuint64_t(N[0]), cuuint64_t(N[1]), cuuint64_t(N[2]), 3};
+        cuuint64_t const strides[3] = {cuuint64_t(N[0]) * 4, cuuint64_t(N[0]) * N[1] * 4, cuuint64_t(vol) * 4};
+        cuuint32_t const bx[4] = {cuuint32_t(box[0]), cuuint32_t(box[1]), cuuint32_t(box[2]), 3};
+        cuuint32_t const es[4] = {1, 1, 1, 1};
+        CUresult const r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if(r != CUDA_SUCCESS)
+        {
+            snprintf(err, errLen, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+            return 1;
+        }
+        return 0;
     }
 
     // ---- gather only (parity test hook for FieldToParticleInterpolation) --------------------------------------
@@ -215,7 +265,7 @@ namespace picstep
             int const row = (i / T::TX) % ROWS;
             int const comp = i / (T::TX * ROWS);
             float const* src = comp < 3 ? B.c[comp] : E.c[comp - 3];
-            tile[comp * T::TV + row * T::PX + x] = __ldg(src + fidx(P, ox + x, oy + row % T::TY, oz + row / T::TY));
+            tile[(comp < 3 ? comp * T::TV : T::HALF + (comp - 3) * T::TV) + row * T::PX + x] = __ldg(src + fidx(P, ox + x, oy + row % T::TY, oz + row / T::TY));
         }
         __syncthreads();
         for(uint32_t i = p0 + threadIdx.x; i < p1; i += blockDim.x)
@@ -224,7 +274,7 @@ namespace picstep
             int const lc = S.cell[i];
             int const lx = lc % SCX, ly = (lc / SCX) % SCY, lz = lc / (SCX * SCY);
             float Ef[3], Bf[3];
-            gatherEB<SHAPE>(tile, tile + 3 * T::TV, lx, ly, lz, px, py, pz, Ef, Bf);
+            gatherEB<SHAPE>(tile, tile + T::HALF, lx, ly, lz, px, py, pz, Ef, Bf);
 #pragma unroll
             for(int k = 0; k < 3; ++k)
             {
@@ -240,7 +290,7 @@ namespace picstep
 #define PS_CASE(SH)                                                                                                   \
     if(shape == SH)                                                                                                   \
     {                                                                                                                 \
-        size_t const smem = sizeof(float) * 6 * Tile<SH>::TV;                                                         \
+        size_t const smem = sizeof(float) * Tile<SH>::WORDS;                                                          \
         cudaFuncSetAttribute(gatherKernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));               \
         gatherKernel<SH><<<nscTot, 256, smem, st>>>(P, S, E, B, cellOff, out, np);                                    \
         return cudaGetLastError();                                                                                    \

@@ -30,6 +30,7 @@
 #include "esirkepov.cuh"
 #include "pusher.cuh"
 #include "shapes.cuh"
+#include "tma.cuh"
 
 namespace picstep
 {
@@ -46,7 +47,7 @@ namespace picstep
         static constexpr int WARPS = 8, CELLS_PER_WARP = SCVOL / WARPS; // 32 cells: 8 x, 4 y, 1 z
         static constexpr int PX = SCX + WN - 1, PY = SCY / 2 + WN - 1, PZ = 1 + WN - 1, PV = PX * PY * PZ;
         static constexpr int TX = SCX + WN - 1, TY = SCY + WN - 1, TZ = SCZ + WN - 1, TV = TX * TY * TZ;
-        static constexpr int EBW = (6 * Tile<SHAPE>::TV + 3) / 4 * 4; // E/B tile words (FUSED), 16-byte padded
+        static constexpr int EBW = Tile<SHAPE>::WORDS; // E/B tile words (FUSED): two 128-byte aligned TMA destinations
         static_assert(Sh::SUPP <= 4, "narrow window of 4 nodes needs a support of at most 4");
         static_assert((3 * PV * WARPS) % 4 == 0 && RECW % 4 == 0, "records must stay 16-byte aligned");
     };
@@ -71,7 +72,8 @@ namespace picstep
         uint32_t* __restrict__ cellCnt, // FUSED: per destination cell, number of particles arriving from other cells
         uint32_t* __restrict__ stayCnt, // FUSED: per cell, number of particles that stay in it
         uint32_t* __restrict__ key, // FUSED: destination supercell * 256 + cell (+ leave flags)
-        uint32_t* __restrict__ rank) // FUSED: slot inside the destination cell: stayers first, then arrivals (bit 31)
+        uint32_t* __restrict__ rank, // FUSED: slot inside the destination cell: stayers first, then arrivals (bit 31)
+        const __grid_constant__ TileMaps maps) // FUSED: TMA descriptors of E and B
     {
         using Sh = Shape<SHAPE>;
         using C = RunCfg<SHAPE>;
@@ -79,7 +81,8 @@ namespace picstep
         constexpr bool even = (Sh::SUPP % 2) == 0;
         constexpr uint32_t FULL = 0xffffffffu;
 
-        extern __shared__ __align__(16) float smem[];
+        extern __shared__ __align__(128) float smem[];
+        __shared__ uint64_t ebBar;
         float* const ebTile = smem;
         float* const tiles = smem + (FUSED ? C::EBW : 0);
         float* const recs = tiles + C::WARPS * 3 * C::PV;
@@ -93,31 +96,31 @@ namespace picstep
         float* const myTile = tiles + warp * 3 * C::PV;
         float* const myRecs = recs + warp * C::NREC * C::RECW;
 
+        if constexpr(FUSED)
+        {
+            // stage the E and B tiles: one TMA box (x, y, z, 3 components) per field, issued by one thread before the
+            // CTA clears its J tiles and records, completion is awaited after the barrier
+            if(threadIdx.x == 0)
+            {
+                int const ox = scx * SCX + P.g[0] - T::LO + maps.lead, oy = scy * SCY + P.g[1] - T::LO, oz = scz * SCZ + P.g[2] - T::LO;
+                mbarInit(&ebBar, 1);
+                mbarExpectTx(&ebBar, 2 * T::BYTES_PER_FIELD);
+                tmaLoadTile(ebTile, &maps.B, ox, oy, oz, &ebBar);
+                tmaLoadTile(ebTile + T::HALF, &maps.E, ox, oy, oz, &ebBar);
+            }
+        }
         for(int i = threadIdx.x; i < C::WARPS * 3 * C::PV; i += blockDim.x)
             tiles[i] = 0.0f;
         for(int i = lane; i < C::NREC * C::RECW; i += 32) // record 32 stays all zero
             myRecs[i] = 0.0f;
-        if constexpr(FUSED)
-        {
-            // stage the six E/B component tiles: rows of TX consecutive floats, coalesced per row
-            int const ox = scx * SCX + P.g[0] - T::LO, oy = scy * SCY + P.g[1] - T::LO, oz = scz * SCZ + P.g[2] - T::LO;
-            constexpr int ROWS = T::TY * T::TZ;
-            for(int i = threadIdx.x; i < 6 * ROWS * T::TX; i += blockDim.x)
-            {
-                int const x = i % T::TX;
-                int const row = (i / T::TX) % ROWS;
-                int const comp = i / (T::TX * ROWS);
-                int const y = row % T::TY, z = row / T::TY;
-                float const* src = comp < 3 ? B.c[comp] : E.c[comp - 3];
-                ebTile[comp * T::TV + row * T::PX + x] = __ldg(src + fidx(P, ox + x, oy + y, oz + z));
-            }
-        }
         __syncthreads();
+        if constexpr(FUSED)
+            mbarWait(&ebBar, 0);
 
         float const rc2 = float(1.0 / double(P.c) / double(P.c));
         float const vol = P.cell[0] * P.cell[1] * P.cell[2];
         float const* const tB = ebTile;
-        float const* const tE = ebTile + 3 * T::TV;
+        float const* const tE = ebTile + T::HALF;
 
         // ---- phase 2 lane constants ------------------------------------------------------------------------------
         int const slot = lane >> 4, g = lane & 15;
@@ -521,14 +524,14 @@ namespace picstep
     }
 
     template<int SHAPE, int PUSHER, bool FUSED>
-    cudaError_t launchRunT(DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, cudaStream_t st)
+    cudaError_t launchRunT(DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, TileMaps const& maps, cudaStream_t st)
     {
         int const nscTot = P.nsc[0] * P.nsc[1] * P.nsc[2];
         constexpr size_t smem = runSmemBytes<SHAPE, FUSED>();
         cudaError_t e = cudaFuncSetAttribute(runKernel<SHAPE, PUSHER, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if(e != cudaSuccess)
             return e;
-        runKernel<SHAPE, PUSHER, FUSED><<<nscTot, 256, smem, st>>>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank);
+        runKernel<SHAPE, PUSHER, FUSED><<<nscTot, 256, smem, st>>>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps);
         return cudaGetLastError();
     }
 
@@ -541,9 +544,10 @@ namespace picstep
     cudaError_t launchDepositRun(int shape, DevParams const& P, SpeciesDev const& S, Field3 J, uint32_t const* cellOff, cudaStream_t st)
     {
         Field3 none{};
+        TileMaps const noMaps{};
 #define PS_CASE(SH)                                                                                                   \
     if(shape == SH)                                                                                                   \
-        return launchRunT<SH, 0, false>(P, S, S, nullptr, none, none, J, cellOff, nullptr, nullptr, nullptr, nullptr, st);
+        return launchRunT<SH, 0, false>(P, S, S, nullptr, none, none, J, cellOff, nullptr, nullptr, nullptr, nullptr, noMaps, st);
         PS_CASE(0)
         PS_CASE(1)
         PS_CASE(2)
@@ -553,11 +557,11 @@ namespace picstep
     }
 
     /** fused gather + push + move + deposit of one species (picstep_step fast path) */
-    cudaError_t launchPushDeposit(int shape, int pusher, DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, cudaStream_t st)
+    cudaError_t launchPushDeposit(int shape, int pusher, DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, TileMaps const& maps, cudaStream_t st)
     {
 #define PS_CASE(SH, PU)                                                                                               \
     if(shape == SH && pusher == PU)                                                                                   \
-        return launchRunT<SH, PU, true>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, st);
+        return launchRunT<SH, PU, true>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps, st);
         PS_CASE(0, 0)
         PS_CASE(1, 0)
         PS_CASE(2, 0)

@@ -23,9 +23,13 @@ namespace picstep
     {
         static constexpr int LO = GatherMargin<SHAPE>::LO, UP = GatherMargin<SHAPE>::UP;
         static constexpr int TX = SCX + LO + UP, TY = SCY + LO + UP, TZ = SCZ + LO + UP;
-        // odd row pitch keeps the y/z neighbours of a cell on different banks
-        static constexpr int PX = (TX % 2 == 0) ? TX + 1 : TX;
+        // rows are padded to a multiple of four floats: a TMA box row has to be a multiple of 16 bytes
+        static constexpr int PX = (TX + 3) / 4 * 4;
         static constexpr int TV = PX * TY * TZ;
+        // the B block [3][TZ][TY][PX] is followed by the E block at the next 128-byte boundary (TMA destination)
+        static constexpr int HALF = (3 * TV + 31) / 32 * 32;
+        static constexpr int WORDS = 2 * HALF;
+        static constexpr uint32_t BYTES_PER_FIELD = 3u * TV * sizeof(float);
     };
 
     /** Interpolate one field component to the particle (FieldToParticleInterpolation.hpp:97-124 +

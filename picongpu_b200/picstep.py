@@ -233,12 +233,20 @@ class Simulation:
         self._chk(self.L.picstep_particles_count(self.ctx, self._sid(species), C.byref(n)), "particles_count")
         return n.value
 
-    def download_particles(self, species):
+    def download_particles(self, species, out=None):
+        """Particles in frame-run order.  `out` = (pos[3,n], mom[3,n], w[n], cell[n]) pre-allocated C-contiguous
+        arrays (e.g. views of pinned memory) to download into; allocated here otherwise."""
         n = self.particle_count(species)
-        pos = np.empty((3, n), np.float32)
-        mom = np.empty((3, n), np.float32)
-        w = np.empty(n, np.float32)
-        cell = np.empty(n, np.int32)
+        if out is None:
+            pos = np.empty((3, n), np.float32)
+            mom = np.empty((3, n), np.float32)
+            w = np.empty(n, np.float32)
+            cell = np.empty(n, np.int32)
+        else:
+            pos, mom, w, cell = out
+            assert pos.shape == (3, n) and mom.shape == (3, n) and w.shape == (n,) and cell.shape == (n,)
+            assert pos.dtype == np.float32 and mom.dtype == np.float32 and w.dtype == np.float32 and cell.dtype == np.int32
+            assert all(a.flags["C_CONTIGUOUS"] for a in (pos, mom, w, cell))
         got = C.c_int64(0)
         self._chk(self.L.picstep_particles_download(self.ctx, self._sid(species), n, _ptr(pos), _ptr(mom), _ptr(w), _ptr(cell), C.byref(got)), "particles_download")
         return pos, mom, w, cell
