@@ -583,8 +583,8 @@ extern "C"
         if(p->current_interpolation < 0 || p->current_interpolation > 1 || p->absorber_kind < 0 || p->absorber_kind > 1)
             return fail(nullptr, PICSTEP_ERR_INVALID, "unknown current interpolation / absorber kind");
         for(int d = 0; d < 3; ++d)
-            for(int sd = 0; sd < 2; ++sd)
-                if(p->absorber_kind && (p->absorber_cells[d][sd] < 0 || p->absorber_cells[d][sd] >= ABS_MAX || p->absorber_cells[d][sd] > p->grid[d]))
+            for(int sd = 0; sd < 2; ++sd) // only faces that can absorb (non-periodic axes) are checked
+                if(p->absorber_kind && !p->periodic[d] && (p->absorber_cells[d][sd] < 0 || p->absorber_cells[d][sd] >= ABS_MAX || p->absorber_cells[d][sd] > p->grid[d]))
                     return fail(nullptr, PICSTEP_ERR_INVALID, "absorber thickness must be in [0, min(255, local grid)]");
         int nsplit = 0, split = -1;
         for(int d = 0; d < 3; ++d)

@@ -625,3 +625,67 @@ def test_absorber_damps_outgoing_wave():
         res[kind] = s.field_energy().sum() / e0
         s.close()
     assert res[1] < 0.05 and res[1] < 0.2 * res[0], res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations as parity cases (same kernels, other template arguments; SURVEY 8 header)
+# ---------------------------------------------------------------------------------------------------------------
+def _thermal_species(p, ppc, seed, sigma):
+    """BM/Thermal: electrons only, random in-cell positions, Maxwellian momenta (sigma in units of m c per axis)."""
+    pos, mom, w, cell = util.random_particles(p, ppc=ppc, seed=seed, thermal=sigma, tag_weights=False)
+    return dict(massRatio=1.0, chargeRatio=1.0, pos=pos, mom=mom, w=w, cell=cell)
+
+
+CONFIGS = {
+    # C3 LaserWakefield-like boundaries and shape as BASELINE.json names them: CIC, open + absorbing y, periodic x/z
+    "C3_lwfa_like_CIC_open_y": dict(kind="khi", kw=dict(shape=prm.SHAPE_CIC, periodic=(1, 0, 1), absorber_kind=1), steps=30),
+    # C4 FoilLCT-like stress variant: PQS form factor + Lehe solver, Binomial current smoothing
+    "C4_foil_like_PQS_Lehe": dict(kind="khi", kw=dict(shape=prm.SHAPE_PQS, field_solver=prm.SOLVER_LEHE, lehe_dir=1, current_interpolation=1), steps=30),
+    "C4_foil_like_PQS_Lehe_EmZ": dict(kind="khi", kw=dict(shape=prm.SHAPE_PQS, field_solver=prm.SOLVER_LEHE, lehe_dir=0, current_solver=prm.CURRENT_EMZ), steps=20),
+    # C5 Thermal benchmark: warm uniform electrons, HigueraCary as in BM/Thermal/species.param, and Boris (north star)
+    "C5_thermal_HC": dict(kind="thermal", kw=dict(pusher=prm.PUSHER_HIGUERA_CARY), steps=30),
+    "C5_thermal_Boris_PCS": dict(kind="thermal", kw=dict(pusher=prm.PUSHER_BORIS, shape=prm.SHAPE_PCS), steps=20),
+}
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_named_configs_vs_oracle(orc, name, exact):
+    cfg = CONFIGS[name]
+    if cfg["kind"] == "khi":
+        p = util.make_params((16, 16, 8), **cfg["kw"])
+        o, e, i = util.khi_ic(orc, p)
+        rng = np.random.RandomState(5)
+        e["mom"] += (rng.normal(size=e["mom"].shape) * 0.1).astype(np.float32) * (np.float32(p.base_mass) * e["w"] * np.float32(p.c))
+        species = [("e", e), ("i", i)]
+    else:
+        p = prm.thermal_params(grid=(16, 16, 8), **cfg["kw"])
+        o = orc.Oracle(p)
+        species = [("e", _thermal_species(p, 6, 17, 0.05))]
+    s = _sim(p, exact)
+    for nm, sp in species:
+        s.upload_particles(nm, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+    E, B, J = o.field(), o.field(), o.field()
+    sps = [sp for _, sp in species]
+    for _ in range(cfg["steps"]):
+        o.step_open(E, B, J, sps)
+    s.step(cfg["steps"])
+    s.sync()
+    Eg, Bg = s.download_field(FE), s.download_field(FB)
+    # scale: the field one species' current drives (KHI: e- and ion currents cancel to noise level), else max|E|
+    Emax = np.abs(o.interior(E)).max()
+    escale = max(util.khi_scales(p, 1)[1], Emax) if cfg["kind"] == "khi" else Emax
+    tol = 2e-5 if exact else 1e-4
+    dE = np.abs(o.interior(Eg) - o.interior(E)).max() / escale
+    dB = np.abs(o.interior(Bg) - o.interior(B)).max() / max(np.abs(o.interior(B)).max(), escale / p.c)
+    print(name, "exact" if exact else "production", "dE %.2e dB %.2e" % (dE, dB))
+    assert dE < tol and dB < tol
+    for nm, sp in species:
+        got = s.download_particles(nm)
+        n_ref = sp["w"].shape[0]
+        assert got[2].shape[0] == n_ref if exact else abs(got[2].shape[0] - n_ref) <= 2
+        if got[2].shape[0] == n_ref:
+            pm = np.abs(sp["mom"]).max()
+            for c in range(3):
+                assert np.abs(np.sort(got[1][c]) - np.sort(sp["mom"][c])).max() / pm < 1e-4
+    s.close()
