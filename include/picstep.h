@@ -124,6 +124,9 @@ extern "C"
         int32_t absorber_kind; /* picstep_absorber */
         int32_t absorber_cells[3][2];
         float absorber_strength[3][2];
+        /* -m / --moving: the sliding window is active (simulation/control/MovingWindow.hpp): y must be non-periodic,
+         * the +y absorber is switched off (Exponential.hpp:97-101) and picstep_slide() may be called */
+        int32_t moving_window;
     } picstep_params;
 
     /* library / build information: returns e.g. "picstep sm_100a fmad=on" */
@@ -182,6 +185,19 @@ extern "C"
     /* guard exchange of one field: E/B guards := neighbour border (GridBuffer::asyncCommunication,
      * pmacc/memory/buffers/GridBuffer.hpp:472-483); for J: border += neighbour guard (FieldJ.x.cpp:156-174) */
     int picstep_field_exchange(picstep_ctx* ctx, int32_t field);
+
+    /* Moving window.  picstep_moving_window_info restates MovingWindow::getCurrentSlideInfo
+     * (simulation/control/MovingWindow.hpp:44-170): for the step about to be computed, does the window slide
+     * (*do_slide) and where does it start inside the first GPU afterwards (*offset_first_gpu, in cells).
+     * global_cells / local_cells are the y extents, c_dt = speed of light * dt, cell_size in PIC units, move_point as
+     * --windowMovePoint.  Host-only, no context needed. */
+    int picstep_moving_window_info(int32_t global_cells, int32_t local_cells, double cell_size, double c_dt, double move_point, uint32_t step, int32_t* do_slide, int32_t* offset_first_gpu);
+    /* GridController::slide + Simulation::slide (pmacc/mappings/simulation/GridController.hpp:166-176,
+     * pmacc/communication/CommunicatorMPI.cpp:156-170, simulation/control/Simulation.hpp:581-593): all ranks call it
+     * together; every rank moves one position down in y, neighbours / open faces / absorber follow, and the rank
+     * that becomes the top of the window is reset (fields zero, no particles; *was_reset = 1) so that the caller can
+     * initialise the new slab with picstep_particles_upload. */
+    int picstep_slide(picstep_ctx* ctx, int32_t* was_reset);
 
     /* runOneStep x n : all stages, all species, device resident */
     int picstep_step(picstep_ctx* ctx, uint32_t first_step, uint32_t n);

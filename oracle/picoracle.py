@@ -141,6 +141,8 @@ def make_params(cfg):
             p.open[d][sd] = int(g("open")[d][sd]) if _has(cfg, "open") else 0
             p.absorber_cells[d][sd] = int(g("absorber_cells")[d][sd]) if absorbing else 0
             p.absorber_strength[d][sd] = float(g("absorber_strength")[d][sd]) if absorbing else 0.0
+    if _has(cfg, "moving_window") and int(g("moving_window")):
+        p.absorber_cells[1][1] = 0  # no absorber on the +y side while the window slides (Exponential.hpp:97-101)
     return p
 
 

@@ -100,6 +100,7 @@ struct picstep_ctx
     AbsorberDev absorber{}; // exponential absorber: thickness per face (0 = not absorbing) + attenuation table
     float* dampDev = nullptr;
     bool absorbing = false;
+    int slides = 0; // number of picstep_slide calls so far (moving window)
     int device = 0;
     cudaStream_t stream = nullptr;
     float* fieldMem[3] = {}; // E,B,J : 3*vol floats each, fieldAlloc + tileMaps.lead floats
@@ -430,6 +431,50 @@ namespace
         return PICSTEP_OK;
     }
 
+    // Everything that depends on where this rank sits in the device grid: neighbour ranks, which faces are outer
+    // boundaries, transverse exchange ranges, absorber thickness per face and the attenuation table.  Called by
+    // picstep_create and again by picstep_slide (the moving window rotates the rank positions along y).
+    static void setupBoundaries(picstep_ctx* c, std::vector<float>& damp)
+    {
+        picstep_params const* p = &c->prm;
+        DevParams& P = c->P;
+        int const split = P.split_axis;
+        c->rankLo = c->rankHi = -1;
+        if(split >= 0)
+        {
+            // NCCL ranks keep their identity when the window slides: after k slides the rank at position q is (q + k) mod n
+            int const n = p->devices[split], pos = p->rank_pos[split], k = c->slides % n;
+            bool const per = p->periodic[split] != 0;
+            if(pos > 0 || per)
+                c->rankLo = ((pos - 1 + n) % n + k) % n;
+            if(pos < n - 1 || per)
+                c->rankHi = ((pos + 1) % n + k) % n;
+        }
+        P.has_lower = c->rankLo >= 0;
+        P.has_upper = c->rankHi >= 0;
+        damp.assign(size_t(6) * ABS_MAX, 1.0f);
+        c->absorbing = false;
+        for(int d = 0; d < 3; ++d)
+        {
+            // does a neighbour (possibly this rank itself through the periodic wrap) exist below / above along d?
+            bool const nbLo = P.wrap[d] || (d == split && c->rankLo >= 0);
+            bool const nbHi = P.wrap[d] || (d == split && c->rankHi >= 0);
+            P.tlo[d] = nbLo ? 0 : P.g[d];
+            P.thi[d] = nbHi ? P.N[d] : P.g[d] + P.n[d];
+            bool const nb[2] = {nbLo, nbHi};
+            for(int sd = 0; sd < 2; ++sd)
+            {
+                int cells = (p->absorber_kind == PICSTEP_ABSORBER_EXPONENTIAL && !nb[sd]) ? p->absorber_cells[d][sd] : 0;
+                if(p->moving_window && d == 1 && sd == 1)
+                    cells = 0; // the absorber on the +y side is off while the window slides (Exponential.hpp:97-101)
+                c->absorber.cells[d][sd] = cells;
+                c->absorbing = c->absorbing || cells > 1;
+                for(int f = 0; f < cells; ++f) // math::exp(-absorberStrength * float_X(factor)) (Exponential.kernel:107)
+                    damp[size_t(2 * d + sd) * ABS_MAX + f] = std::exp(-p->absorber_strength[d][sd] * float(f));
+            }
+        }
+    }
+
     // lazy -> physical run order: gather the attributes through inv into the other buffer (API calls and the
     // un-fused stage functions work on the sorted arrays themselves)
     int ensureSorted(picstep_ctx* c, SpeciesHost& s)
@@ -627,28 +672,13 @@ extern "C"
         P.lehe_dir = p->lehe_dir;
         c->nranks = p->devices[0] * p->devices[1] * p->devices[2];
         c->rank = p->rank_pos[0] + p->devices[0] * (p->rank_pos[1] + p->devices[1] * p->rank_pos[2]);
-        if(split >= 0)
-            picstep_neighbor_ranks(p->devices, p->periodic, c->rank, split, &c->rankLo, &c->rankHi);
-        P.has_lower = c->rankLo >= 0;
-        P.has_upper = c->rankHi >= 0;
-        std::vector<float> damp(size_t(6) * ABS_MAX, 1.0f);
-        for(int d = 0; d < 3; ++d)
+        if(p->moving_window && (p->periodic[1] || (split >= 0 && split != 1)))
         {
-            // does a neighbour (possibly this rank itself through the periodic wrap) exist below / above along d?
-            bool const nbLo = P.wrap[d] || (d == split && c->rankLo >= 0);
-            bool const nbHi = P.wrap[d] || (d == split && c->rankHi >= 0);
-            P.tlo[d] = nbLo ? 0 : P.g[d];
-            P.thi[d] = nbHi ? P.N[d] : P.g[d] + P.n[d];
-            bool const nb[2] = {nbLo, nbHi};
-            for(int sd = 0; sd < 2; ++sd)
-            {
-                int const cells = (p->absorber_kind == PICSTEP_ABSORBER_EXPONENTIAL && !nb[sd]) ? p->absorber_cells[d][sd] : 0;
-                c->absorber.cells[d][sd] = cells;
-                c->absorbing = c->absorbing || cells > 1;
-                for(int f = 0; f < cells; ++f) // math::exp(-absorberStrength * float_X(factor)) (Exponential.kernel:107)
-                    damp[size_t(2 * d + sd) * ABS_MAX + f] = std::exp(-p->absorber_strength[d][sd] * float(f));
-            }
+            delete c;
+            return fail(nullptr, PICSTEP_ERR_INVALID, "the moving window needs a non-periodic y axis and a decomposition along y only");
         }
+        std::vector<float> damp;
+        setupBoundaries(c, damp);
         computeLehe(*p, c->lehe);
         if((long long) numCells(c) >= (1ll << 30))
         {
@@ -1139,6 +1169,78 @@ extern "C"
         if(c->absorbing) // exponentialImpl.run(B) (FDTDBase.hpp:175-179)
             KL(c, 1, launchAbsorb(c->P, B, c->absorber, c->stream));
         return exchangeField(c, PICSTEP_FIELD_B);
+    }
+
+    /* GridController::slide (pmacc/mappings/simulation/GridController.hpp:166-176, CommunicatorMPI.cpp:156-170) +
+     * Simulation::slide (Simulation.hpp:581-593): every rank moves one position down in y, the lowest one becomes the
+     * top of the window and starts empty (resetAll); ParticleInit of the new slab is the caller's upload. */
+    int picstep_slide(picstep_ctx* c, int32_t* was_reset)
+    {
+        if(!c)
+            return PICSTEP_ERR_INVALID;
+        if(!c->prm.moving_window)
+            return fail(c, PICSTEP_ERR_INVALID, "picstep_slide needs picstep_params.moving_window");
+        CU(c, cudaSetDevice(c->device));
+        int const n = c->prm.devices[1];
+        c->slides += 1;
+        c->prm.rank_pos[1] = (c->prm.rank_pos[1] - 1 + n) % n;
+        bool const reset = c->prm.rank_pos[1] == n - 1;
+        std::vector<float> damp;
+        setupBoundaries(c, damp);
+        CU(c, cudaMemcpyAsync(c->dampDev, damp.data(), sizeof(float) * damp.size(), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream)); // damp is a local
+        if(reset)
+        {
+            for(int f = 0; f < 3; ++f)
+                CU(c, cudaMemsetAsync(c->fieldAlloc[f], 0, sizeof(float) * (3 * c->P.vol + 4), c->stream));
+            size_t const ncell = size_t(numCells(c));
+            for(auto& s : c->species)
+            {
+                if(s.capacity == 0)
+                    continue;
+                CU(c, cudaMemsetAsync(s.nDev, 0, sizeof(uint32_t) * 2, c->stream));
+                CU(c, cudaMemsetAsync(s.cellOff[s.cur], 0, sizeof(uint32_t) * (ncell + 1), c->stream));
+                CU(c, cudaMemsetAsync(s.cellCnt, 0, sizeof(uint32_t) * ncell, c->stream));
+                CU(c, cudaMemsetAsync(s.stayCnt, 0, sizeof(uint32_t) * ncell, c->stream));
+                s.lazy = false;
+                s.ranked = false;
+                s.nUpper = 0;
+            }
+        }
+        if(was_reset)
+            *was_reset = reset ? 1 : 0;
+        return PICSTEP_OK;
+    }
+
+    /* MovingWindow::getCurrentSlideInfo (simulation/control/MovingWindow.hpp:44-170), a pure function of the step:
+     * does the window slide while `step` is computed, and the window offset inside the first GPU after the step */
+    int picstep_moving_window_info(int32_t global_cells, int32_t local_cells, double cell_size, double c_dt, double move_point, uint32_t step, int32_t* do_slide, int32_t* offset_first_gpu)
+    {
+        if(global_cells <= 0 || local_cells <= 0 || global_cells % local_cells || global_cells < 2 * local_cells || !(cell_size > 0) || !(c_dt > 0))
+            return PICSTEP_ERR_INVALID;
+        if(do_slide)
+            *do_slide = 0;
+        if(offset_first_gpu)
+            *offset_first_gpu = 0;
+        uint32_t const windowSize = uint32_t(global_cells - local_cells);
+        uint32_t const startCell = uint32_t(std::ceil(double(windowSize) * (1.0 - move_point)));
+        uint32_t const firstSlideStep = uint32_t(std::ceil(double(uint32_t(global_cells) - startCell) * cell_size / c_dt) - 1);
+        double const wayToFirstMove = double(windowSize - startCell) * cell_size;
+        int32_t const firstMoveStep = int32_t(std::ceil(wayToFirstMove / c_dt) - 1);
+        if(firstMoveStep <= int32_t(step))
+        {
+            uint32_t const passed = uint32_t(std::floor(c_dt * double(step) / cell_size));
+            uint32_t const pos = passed + startCell;
+            uint32_t const nextPassed = uint32_t(std::floor(c_dt * double(step + 1) / cell_size));
+            uint32_t const nextPos = nextPassed + startCell;
+            bool const endOfInitialGlobalDomain = firstSlideStep <= step;
+            bool const passesBorder = (nextPos % uint32_t(local_cells)) < (pos % uint32_t(local_cells));
+            if(endOfInitialGlobalDomain && passesBorder && do_slide)
+                *do_slide = 1;
+            if(offset_first_gpu)
+                *offset_first_gpu = int32_t(nextPos % uint32_t(local_cells));
+        }
+        return PICSTEP_OK;
     }
 
     int picstep_step(picstep_ctx* c, uint32_t first, uint32_t n)

@@ -66,6 +66,7 @@ class SimParams:
     absorber_kind: int = 0
     absorber_cells: tuple = ((12, 12), (12, 12), (12, 12))
     absorber_strength: tuple = ((1.0e-3, 1.0e-3), (1.0e-3, 1.0e-3), (1.0e-3, 1.0e-3))
+    moving_window: int = 0  # -m: sliding window along y (needs a non-periodic y axis)
     # --- runtime (-d, --periodic) ---
     periodic: tuple = (1, 1, 1)
     devices: tuple = (1, 1, 1)

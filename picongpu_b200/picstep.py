@@ -28,7 +28,7 @@ SYMBOLS = [
     "picstep_field_update_after_current", "picstep_field_exchange", "picstep_step", "picstep_step_host",
     "picstep_sync", "picstep_reduce", "picstep_debug_gather", "picstep_comm_unique_id", "picstep_comm_init",
     "picstep_launch_count", "picstep_stage_times", "picstep_stream", "picstep_neighbor_ranks",
-    "picstep_exchange_widths",
+    "picstep_exchange_widths", "picstep_slide", "picstep_moving_window_info",
 ]
 
 
@@ -64,6 +64,7 @@ class Params(C.Structure):
         ("absorber_kind", C.c_int32),
         ("absorber_cells", (C.c_int32 * 2) * 3),
         ("absorber_strength", (C.c_float * 2) * 3),
+        ("moving_window", C.c_int32),
     ]
 
 
@@ -109,6 +110,7 @@ def load(exact=False):
     L.picstep_step.argtypes = [vp, u32, u32]
     L.picstep_step_host.argtypes = [vp, u32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.picstep_sync.argtypes = [vp]
+    L.picstep_slide.argtypes = [vp, C.POINTER(i32)]
     L.picstep_reduce.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
     L.picstep_debug_gather.argtypes = [vp, i32, i64, vp]
     L.picstep_comm_unique_id.argtypes = [vp]
@@ -140,11 +142,23 @@ def to_c_params(p, device=0, flags=0):
     cp.flags = flags
     cp.current_interpolation = int(getattr(p, "current_interpolation", 0))
     cp.absorber_kind = int(getattr(p, "absorber_kind", 0))
+    cp.moving_window = int(getattr(p, "moving_window", 0))
     for d in range(3):
         for sd in range(2):
             cp.absorber_cells[d][sd] = int(getattr(p, "absorber_cells", ((0, 0),) * 3)[d][sd])
             cp.absorber_strength[d][sd] = float(getattr(p, "absorber_strength", ((0.0, 0.0),) * 3)[d][sd])
     return cp
+
+
+def moving_window_info(global_cells, local_cells, cell_size, c_dt, move_point, step, exact=False):
+    """MovingWindow::getCurrentSlideInfo: (slide during this step?, window offset in the first GPU after it)."""
+    L = load(exact)
+    L.picstep_moving_window_info.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    sl, off = C.c_int32(0), C.c_int32(0)
+    rc = L.picstep_moving_window_info(global_cells, local_cells, cell_size, c_dt, move_point, step, C.byref(sl), C.byref(off))
+    if rc:
+        raise PicstepError("picstep_moving_window_info: invalid argument")
+    return bool(sl.value), off.value
 
 
 def neighbor_ranks(devices, periodic, rank, axis, exact=False):
@@ -325,6 +339,14 @@ class Simulation:
         """n steps through the fused C entry point picstep_step()."""
         self._chk(self.L.picstep_step(self.ctx, self.step_index, n), "step")
         self.step_index += n
+
+    def slide(self):
+        """GridController::slide + Simulation::slide: returns True when this rank became the (empty) top of the window."""
+        r = C.c_int32(0)
+        self._chk(self.L.picstep_slide(self.ctx, C.byref(r)), "slide")
+        n = self.p.devices[1]
+        self.p.rank_pos = (self.p.rank_pos[0], (self.p.rank_pos[1] - 1 + n) % n, self.p.rank_pos[2])
+        return bool(r.value)
 
     def step_host(self, E, B, species_arrays):
         """One step through HOST buffers (upload E,B + all species, step, download E,B + energies).

@@ -82,3 +82,33 @@ def test_unit_system_khi():
     n_pic = p.real_particles_per_cell / (p.cell_size[0] ** 3) / p.typical_num_particles_per_macro
     wpe_pic = (n_pic * (p.base_charge * p.typical_num_particles_per_macro) ** 2 / (p.eps0 * p.base_mass * p.typical_num_particles_per_macro)) ** 0.5
     assert abs(wpe_pic - wpe * 1.79e-16) / (wpe * 1.79e-16) < 1e-4
+
+
+def test_moving_window_schedule():
+    """MovingWindow::getCurrentSlideInfo (MovingWindow.hpp:44-170): hand-computed answers for 4 GPUs x 16 cells,
+    dy = 1, c*dt = 0.5, movePoint 0.5 (window starts to move in step 47, slides in steps 79, 111, 143, ...), and a
+    straight restatement of the formulas over a range of steps."""
+    import math
+
+    G, L, dy, cdt, mp = 64, 16, 1.0, 0.5, 0.5
+    info = lambda st: picstep.moving_window_info(G, L, dy, cdt, mp, st)
+    assert info(0) == (False, 0) and info(46) == (False, 0) and info(47) == (False, 0)
+    assert info(49) == (False, 1) and info(78) == (False, 15)
+    assert info(79) == (True, 0) and info(80) == (False, 0) and info(81) == (False, 1)
+    slides = [st for st in range(400) if info(st)[0]]
+    assert slides[:4] == [79, 111, 143, 175]
+
+    def ref(st, G, L, dy, cdt, mp):
+        win = G - L
+        start = math.ceil(win * (1.0 - mp))
+        first_slide = math.ceil((G - start) * dy / cdt) - 1
+        first_move = math.ceil((win - start) * dy / cdt) - 1
+        if first_move > st:
+            return False, 0
+        pos = math.floor(cdt * st / dy) + start
+        nxt = math.floor(cdt * (st + 1) / dy) + start
+        return (first_slide <= st and (nxt % L) < (pos % L)), nxt % L
+
+    for (G, L, dy, cdt, mp) in ((64, 16, 1.0, 0.5, 0.5), (2048, 256, 1.7417, 1.0, 0.9), (96, 32, 0.8, 0.45, 0.0)):
+        for st in range(0, 3000, 7):
+            assert picstep.moving_window_info(G, L, dy, cdt, mp, st) == ref(st, G, L, dy, cdt, mp)
