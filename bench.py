@@ -172,6 +172,10 @@ def run_ours(args):
             pass
 
     grid = tuple(args.grid)
+    if args.scaling == "strong":
+        if grid[1] % (8 * world) or grid[1] // world < 16:
+            raise SystemExit("strong scaling: the global y extent must split into >= 2 supercells per GPU")
+        grid = (grid[0], grid[1] // world, grid[2])
     p = prm.khi_params(grid=grid, devices=(1, world, 1), rank_pos=(0, rank, 0))
     sim = picstep.Simulation(p, device=local, exact=False)
     if world > 1:
@@ -318,7 +322,7 @@ def run_ours(args):
             "warmup": args.warmup,
             "ms_per_step": ms_step,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": args.scaling,
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
@@ -392,6 +396,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --grid is the grid per GPU (default, what the driver runs); strong: --grid is the GLOBAL grid, split in y over the GPUs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
