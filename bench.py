@@ -86,8 +86,20 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+VARIANT = {"shape": "TSC", "pusher": "Boris", "current": "Esirkepov", "solver": "Yee", "interp": "none"}
+
+
 def workload_name(grid, ppc, n):
-    return "KelvinHelmholtz3D_%dx%dx%d_per_gpu_%d+%dppc_TSC_Boris_Esirkepov_Yee_periodic_d1x%dx1" % (grid[0], grid[1], grid[2], ppc, ppc, n)
+    v = VARIANT
+    extra = "" if v["interp"] == "none" else "_Binomial"
+    return "KelvinHelmholtz3D_%dx%dx%d_per_gpu_%d+%dppc_%s_%s_%s_%s%s_periodic_d1x%dx1" % (
+        grid[0], grid[1], grid[2], ppc, ppc, v["shape"], v["pusher"], v["current"], v["solver"], extra, n)
+
+
+def variant_kwargs():
+    v = VARIANT
+    return dict(shape=prm.SHAPE_NAMES[v["shape"]], pusher=prm.PUSHER_NAMES[v["pusher"]], current_solver=prm.CURRENT_NAMES[v["current"]],
+                field_solver=prm.SOLVER_NAMES[v["solver"]], current_interpolation=1 if v["interp"] == "binomial" else 0)
 
 
 # -------------------------------------------------------------------------------------------------------------------
@@ -98,7 +110,7 @@ def cpu_oracle_rate(steps, warmup, grid=(64, 64, 64)):
     import util
     from oracle import picoracle
 
-    p = prm.khi_params(grid=grid)
+    p = prm.khi_params(grid=grid, **variant_kwargs())
     o, e, i = util.khi_ic(picoracle, p)
     E, B, J = o.field(), o.field(), o.field()
     npart = 2 * e["w"].shape[0]
@@ -176,7 +188,7 @@ def run_ours(args):
         if grid[1] % (8 * world) or grid[1] // world < 16:
             raise SystemExit("strong scaling: the global y extent must split into >= 2 supercells per GPU")
         grid = (grid[0], grid[1] // world, grid[2])
-    p = prm.khi_params(grid=grid, devices=(1, world, 1), rank_pos=(0, rank, 0))
+    p = prm.khi_params(grid=grid, devices=(1, world, 1), rank_pos=(0, rank, 0), **variant_kwargs())
     sim = picstep.Simulation(p, device=local, exact=False)
     if world > 1:
         if rank == 0:
@@ -242,12 +254,12 @@ def run_ours(args):
     fused = stage["deposit"] == 0.0  # picstep_step fast path: gather+push+move+deposit in one kernel (runKernel)
     if fused:
         per_launch = {
-            "run": (stage["push"] / (args.steps * nspec), (npart / nspec) * BYTES_PER_UPDATE + ncell * FUSED_BYTES_PER_CELL, "runKernel<TSC,Boris,fused>"),
+            "run": (stage["push"] / (args.steps * nspec), (npart / nspec) * BYTES_PER_UPDATE + ncell * FUSED_BYTES_PER_CELL, "runKernel<%s,%s,fused>" % (VARIANT["shape"], VARIANT["pusher"])),
         }
     else:
         per_launch = {
-            "deposit": (stage["deposit"] / (args.steps * nspec), (npart / nspec) * DEPOSIT_BYTES_PER_PARTICLE + ncell * DEPOSIT_BYTES_PER_CELL, "depositCellKernel<TSC,Esirkepov>"),
-            "push": (stage["push"] / (args.steps * nspec), (npart / nspec) * PUSH_BYTES_PER_PARTICLE + ncell * 24.0, "pushKernel<TSC,Boris>"),
+            "deposit": (stage["deposit"] / (args.steps * nspec), (npart / nspec) * DEPOSIT_BYTES_PER_PARTICLE + ncell * DEPOSIT_BYTES_PER_CELL, "depositKernel<%s,%s>" % (VARIANT["shape"], VARIANT["current"])),
+            "push": (stage["push"] / (args.steps * nspec), (npart / nspec) * PUSH_BYTES_PER_PARTICLE + ncell * 24.0, "pushKernel<%s,%s>" % (VARIANT["shape"], VARIANT["pusher"])),
         }
     dom = max(per_launch, key=lambda k: per_launch[k][0])
     ms_k, bytes_k, kname = per_launch[dom]
@@ -286,7 +298,7 @@ def run_ours(args):
                 egrid[1] //= 2
             if tuple(egrid) != grid:
                 sim.close()
-                p = prm.khi_params(grid=tuple(egrid), devices=(1, world, 1), rank_pos=(0, rank, 0))
+                p = prm.khi_params(grid=tuple(egrid), devices=(1, world, 1), rank_pos=(0, rank, 0), **variant_kwargs())
                 sim = picstep.Simulation(p, device=local, exact=False)
                 if world > 1:
                     uid = sim.comm_unique_id() if rank == 0 else bytes(128)
@@ -398,7 +410,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --grid is the grid per GPU (default, what the driver runs); strong: --grid is the GLOBAL grid, split in y over the GPUs")
+    # other BASELINE.json configurations are the same kernels with other template arguments (defaults = the headline)
+    ap.add_argument("--shape", default="TSC", choices=sorted(prm.SHAPE_NAMES))
+    ap.add_argument("--pusher", default="Boris", choices=sorted(prm.PUSHER_NAMES))
+    ap.add_argument("--current", default="Esirkepov", choices=["Esirkepov", "EmZ"])
+    ap.add_argument("--solver", default="Yee", choices=sorted(prm.SOLVER_NAMES))
+    ap.add_argument("--interp", default="none", choices=["none", "binomial"])
     args = ap.parse_args()
+    VARIANT.update(shape=args.shape, pusher=args.pusher, current=args.current, solver=args.solver, interp=args.interp)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -317,6 +317,13 @@ namespace picstep
                     F2 t[3][Sh::SUPP];
                     float f[3], p0[3], p1[3];
                     int o0[3], o1[3], gs3[3], status[3];
+                    // A support as wide as the window (PQS) leaves no room for a cell crossing.  SEMI: such a particle
+                    // still goes through the records when it crosses on ONE axis: the window part as usual, the one
+                    // plane of nodes outside the window (40 values) with global atomics instead of the whole particle
+                    // (184); this took the PQS step from 161 to 120 ms at 256^3 (12 % of the KHI particles cross a cell per step).
+                    constexpr bool SEMI = (Sh::SUPP == C::WN);
+                    constexpr int MLO = SEMI ? -1 : 0, MHI = C::NMAX0 + (SEMI ? 1 : 0);
+                    int ext[3] = {0, 0, 0}, nExt = 0;
                     bool narrow = true;
 #pragma unroll
                     for(int d = 0; d < 3; ++d)
@@ -332,13 +339,24 @@ namespace picstep
                         o0[d] = iS + Sh::BEGIN + C::WLO + dir[d];
                         o1[d] = iE + Sh::BEGIN + C::WLO + dir[d];
                         if(o0[d] < 0 || o0[d] > C::NMAX0 || o1[d] < 0 || o1[d] > C::NMAX0)
-                            narrow = false;
+                        {
+                            int const lo = o0[d] < o1[d] ? o0[d] : o1[d], hi = o0[d] < o1[d] ? o1[d] : o0[d];
+                            if(!SEMI || lo < MLO || hi > MHI || (lo < 0 && hi > C::NMAX0))
+                                narrow = false;
+                            ext[d] = lo < 0 ? -1 : 1;
+                            ++nExt;
+                        }
                         p0[d] = y0;
                         p1[d] = y1;
                         gs3[d] = gs;
                         status[d] = (gs == iS ? 2 : 0) | (gs == iE ? 4 : 0) | (iS != iE ? 1 : 0);
                     }
                     float* const rec = myRecs + lane * C::RECW;
+                    if(nExt > 1)
+                        narrow = false;
+                    // SEMI: assignment values of start / end point at the node outside the window, its axis and side
+                    float sOut0 = 0.0f, sOut1 = 0.0f, fOut = 0.0f;
+                    int axOut = -1, sideOut = 0;
                     if(narrow)
                     {
                         useRec = true;
@@ -346,12 +364,26 @@ namespace picstep
                         for(int d = 0; d < 3; ++d)
                         {
                             float S0[C::WN], S1[C::WN];
+                            if constexpr(SEMI)
+                                if(ext[d] != 0)
+                                {
+                                    int const nout = ext[d] < 0 ? -1 : C::WN;
+#pragma unroll
+                                    for(int sx = 0; sx < Sh::SUPP; ++sx)
+                                    {
+                                        sOut0 = (nout - o0[d] == sx) ? t[d][sx].x : sOut0;
+                                        sOut1 = (nout - o1[d] == sx) ? t[d][sx].y : sOut1;
+                                    }
+                                    axOut = d;
+                                    sideOut = ext[d];
+                                    fOut = f[d];
+                                }
 #pragma unroll
                             for(int n = 0; n < C::WN; ++n)
                             {
                                 float v0 = 0.0f, v1 = 0.0f;
 #pragma unroll
-                                for(int m = 0; m <= C::NMAX0; ++m)
+                                for(int m = MLO; m <= MHI; ++m)
                                 {
                                     int const s = n - m;
                                     if(s >= 0 && s < Sh::SUPP)
@@ -375,9 +407,48 @@ namespace picstep
                                 r4[j] = make_float4(s0p.x, s0p.y, DS[j].x, DS[j].y);
                                 r4[2 + j] = make_float4(Pp.x, Pp.y, Qp.x, Qp.y);
                             }
-                            float const c0 = DS[0].x, c1 = c0 + DS[0].y, c2 = c1 + DS[1].x;
+                            // prefix sums start at the node left of the window when that one carries weight
+                            float const cm = (SEMI && ext[d] < 0) ? sOut1 - sOut0 : 0.0f;
+                            float const c0 = cm + DS[0].x, c1 = c0 + DS[0].y, c2 = c1 + DS[1].x;
                             r4[4] = make_float4(c0 * f[d], c1 * f[d], c2 * f[d], 0.0f);
                         }
+                        if constexpr(SEMI)
+                            if(axOut >= 0)
+                            {
+                                // the plane of nodes outside the window: J_A at the node next to it along A (16 values)
+                                // and the two transverse components on the plane itself (2 x 12 values)
+                                int const A = axOut, iA = (A + 1) % 3, jA = (A + 2) % 3;
+                                float const dsOut = sOut1 - sOut0;
+                                float const pOut = sOut0 + 0.5f * dsOut, qOut = 0.5f * sOut0 + (1.0f / 3.0f) * dsOut;
+                                long long const strd[3] = {1, P.N[0], (long long) P.N[0] * P.N[1]};
+                                long long const base = fidx(P, scx * SCX + P.g[0] + lx - C::WLO, scy * SCY + P.g[1] + ly - C::WLO, scz * SCZ + P.g[2] + lz - C::WLO);
+                                auto jOf = [&](int c) { return c == 0 ? J.c[0] : (c == 1 ? J.c[1] : J.c[2]); };
+                                auto at = [&](int d, int off, int n) { return rec[d * C::AXW + off + (n >> 1) * 4 + (n & 1)]; }; // off 0: S0, 2: DS, 8: P, 10: Q
+                                int const nout = sideOut < 0 ? -1 : C::WN, kout = sideOut < 0 ? -1 : C::WN - 1;
+                                float const cx = sideOut < 0 ? fOut * dsOut : -(fOut * dsOut);
+                                float* const ja = jOf(A) + base + kout * strd[A];
+#pragma unroll 1
+                                for(int a = 0; a < C::WN; ++a)
+#pragma unroll
+                                    for(int b = 0; b < C::WN; ++b)
+                                        redGlobal(ja + a * strd[iA] + b * strd[jA], cx * (at(iA, 0, a) * at(jA, 8, b) + at(iA, 2, a) * at(jA, 10, b)));
+                                // component iA = (A+1)%3: its (i, j) axes are (jA, A), the outside node sits on j
+                                float* const j1 = jOf(iA) + base + nout * strd[A];
+                                // component jA = (A+2)%3: its (i, j) axes are (A, iA), the outside node sits on i
+                                float* const j2 = jOf(jA) + base + nout * strd[A];
+#pragma unroll 1
+                                for(int a = 0; a < C::WN; ++a)
+                                {
+                                    float const t1 = at(jA, 0, a) * pOut + at(jA, 2, a) * qOut;
+                                    float const t2 = sOut0 * at(iA, 8, a) + dsOut * at(iA, 10, a);
+#pragma unroll
+                                    for(int k = 0; k < C::NK; ++k)
+                                    {
+                                        redGlobal(j1 + a * strd[jA] + k * strd[iA], rec[iA * C::AXW + 16 + k] * t1);
+                                        redGlobal(j2 + a * strd[iA] + k * strd[jA], rec[jA * C::AXW + 16 + k] * t2);
+                                    }
+                                }
+                            }
                     }
                     else
                     {
