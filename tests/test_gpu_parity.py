@@ -689,3 +689,35 @@ def test_named_configs_vs_oracle(orc, name, exact):
             for c in range(3):
                 assert np.abs(np.sort(got[1][c]) - np.sort(sp["mom"][c])).max() / pm < 1e-4
     s.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's own end-to-end acceptance test of this path: share/picongpu/tests/KHI_growthRate
+# ---------------------------------------------------------------------------------------------------------------
+def test_khi_growth_rate_reference_acceptance():
+    """share/picongpu/tests/KHI_growthRate (bin/ci.sh:120: `-g 192 512 12 --periodic 1 1 1 -s 3000
+    --fields_energy.period 10`, param/simulation.param: KHI cell and time step scaled by 0.86) evaluated like
+    lib/python/test/setups/ESKHI: growth rate of the B_x field energy, Gamma(t_k) = 0.5 ln(f_{k+1}/f_{k-1})/(t_{k+1}-t_{k-1})
+    with t in 1/omega_pe (relativistic, testsuite/Math/physics.py:177-215, math.py:22-54), its maximum must lie within
+    `acceptance = 0.2` (ESKHI/config.py:42) of the theory value 1/(sqrt(8) gamma) (config.py:45-60)."""
+    p = prm.khi_params(grid=(192, 512, 12), delta_t_si=1.79e-16 * 0.86, cell_si=(9.34635e-8 * 0.86,) * 3)
+    s = _sim(p, False)
+    s.init_khi()
+    g, n = p.guard_cells, p.grid
+    en = []
+    for _ in range(301):
+        Bx = s.download_field(FB)[0, g[2]:g[2] + n[2], g[1]:g[1] + n[1], g[0]:g[0] + n[0]].astype(np.float64)
+        en.append((Bx**2).sum())
+        s.step(10)
+    s.sync()
+    s.close()
+    f = np.array(en)
+    gamma = 1.021
+    omega = np.sqrt(1.0e25 * prm.ELECTRON_CHARGE_SI**2 / (8.8541878128e-12 * gamma * prm.ELECTRON_MASS_SI))
+    t = np.arange(301) * 10 * p.delta_t_si * omega
+    growth = 0.5 * np.log(f[3:] / f[1:-2]) / (t[3:] - t[1:-2])
+    theory = 1.0 / (8.0**0.5 * gamma)
+    sim = float(np.nanmax(growth))
+    print("KHI growth rate: simulation %.4f, theory %.4f, difference %.1f %%" % (sim, theory, 100 * (theory - sim) / sim))
+    assert abs(theory - sim) / sim <= 0.2
+    assert f[-1] > 1e4 * f[1]  # the instability really grew
