@@ -343,6 +343,7 @@ def run_ours(args):
                        "parallelism": "domain decomposition 1x%dx1" % world},
             "updates_per_s_per_gpu": value / world,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "stage_note": "spans per stage on the stream the stage runs on; at N=1 the re-sort (migrate) runs on a second stream next to the following push / field update, so its span overlaps theirs and the spans do not add up to ms_per_step",
             "roofline": roofline,
             "step_roofline": step_roofline,
             "cpu_baseline": cpu,
