@@ -109,10 +109,14 @@ namespace picstep
                 tmaLoadTile(ebTile + T::HALF, &maps.E, ox, oy, oz, &ebBar);
             }
         }
-        for(int i = threadIdx.x; i < C::WARPS * 3 * C::PV; i += blockDim.x)
-            tiles[i] = 0.0f;
-        for(int i = lane; i < C::NREC * C::RECW; i += 32) // record 32 stays all zero
-            myRecs[i] = 0.0f;
+        {
+            static_assert((C::WARPS * 3 * C::PV) % 4 == 0, "tiles are cleared with 16-byte stores");
+            float4* const t4 = reinterpret_cast<float4*>(tiles);
+            for(int i = threadIdx.x; i < C::WARPS * 3 * C::PV / 4; i += blockDim.x)
+                t4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            for(int i = lane; i < C::RECW; i += 32) // record 32 stays all zero
+                myRecs[32 * C::RECW + i] = 0.0f;
+        }
         __syncthreads();
         if constexpr(FUSED)
             mbarWait(&ebBar, 0);
@@ -463,11 +467,21 @@ namespace picstep
             if(!useRec)
             {
                 // nothing to add for this record in phase 2 (absorbed / wide trajectory / slot beyond the end of the
-                // piece): C = 0; the S0/DS/P/Q words are stale but finite (the record area is zeroed at kernel start)
+                // piece): C = 0.  The S0/DS/P/Q words are stale but finite, except for a slot that has never been
+                // written (first chunk of the piece): that one is cleared completely.
                 float* const rec = myRecs + lane * C::RECW;
+                if(chunk == pBeg)
+                {
 #pragma unroll
-                for(int d = 0; d < 3; ++d)
-                    *reinterpret_cast<float4*>(rec + d * C::AXW + 16) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    for(int q = 0; q < C::RECW / 4; ++q)
+                        reinterpret_cast<float4*>(rec)[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+                else
+                {
+#pragma unroll
+                    for(int d = 0; d < 3; ++d)
+                        *reinterpret_cast<float4*>(rec + d * C::AXW + 16) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
             }
             // ---- phase 2: two records per pass (one per half warp), accumulators flushed when the cell changes ------
             uint32_t const validMask = __ballot_sync(FULL, valid);
@@ -565,31 +579,42 @@ namespace picstep
         }
         __syncthreads();
         // ---- combine the warp-private tiles and flush once to global J (red.global.add.f32) --------------------------
+        // one thread per (component, z, y) row of the supercell's J tile: which private tiles overlap the row is
+        // decided once per row, the TX values of the row are summed in registers (231 rows for TSC: one pass)
         {
             int const ox = scx * SCX + P.g[0] - C::WLO, oy = scy * SCY + P.g[1] - C::WLO, oz = scz * SCZ + P.g[2] - C::WLO;
-            for(int i = threadIdx.x; i < 3 * C::TV; i += blockDim.x)
+            constexpr int ROWS = 3 * C::TZ * C::TY;
+            for(int row = threadIdx.x; row < ROWS; row += blockDim.x)
             {
-                int const cmp = i / C::TV;
-                int const rr = i % C::TV;
-                int const x = rr % C::TX, y = (rr / C::TX) % C::TY, z = rr / (C::TX * C::TY);
-                float v = 0.0f;
+                int const cmp = row / (C::TZ * C::TY);
+                int const r = row - cmp * (C::TZ * C::TY);
+                int const z = r / C::TY, y = r - z * C::TY;
+                float v[C::TX];
+#pragma unroll
+                for(int x = 0; x < C::TX; ++x)
+                    v[x] = 0.0f;
 #pragma unroll
                 for(int zc = 0; zc < SCZ; ++zc)
                 {
                     int const tz = z - zc;
-                    if(tz < 0 || tz >= C::PZ)
-                        continue;
 #pragma unroll
                     for(int h = 0; h < 2; ++h)
                     {
                         int const ty = y - h * (SCY / 2);
-                        if(ty < 0 || ty >= C::PY)
-                            continue;
-                        v += tiles[(zc * 2 + h) * 3 * C::PV + cmp * C::PV + x + C::PX * (ty + C::PY * tz)];
+                        if(tz >= 0 && tz < C::PZ && ty >= 0 && ty < C::PY)
+                        {
+                            float const* __restrict__ src = tiles + (zc * 2 + h) * 3 * C::PV + cmp * C::PV + C::PX * (ty + C::PY * tz);
+#pragma unroll
+                            for(int x = 0; x < C::TX; ++x)
+                                v[x] += src[x];
+                        }
                     }
                 }
-                if(v != 0.0f)
-                    atomicAdd(J.c[cmp] + fidx(P, ox + x, oy + y, oz + z), v);
+                float* const dst = (cmp == 0 ? J.c[0] : (cmp == 1 ? J.c[1] : J.c[2])) + fidx(P, ox, oy + y, oz + z);
+#pragma unroll
+                for(int x = 0; x < C::TX; ++x)
+                    if(v[x] != 0.0f)
+                        redGlobal(dst + x, v[x]);
             }
         }
     }
