@@ -69,6 +69,9 @@ class Params(C.Structure):
 
 
 def lib_path(exact=False):
+    # PICSTEP_LIB: another build of the production library (A/B timing of kernel variants on one box)
+    if not exact and os.environ.get("PICSTEP_LIB"):
+        return os.environ["PICSTEP_LIB"]
     return os.path.join(_HERE, "libpicstep_exact.so" if exact else "libpicstep.so")
 
 
