@@ -12,6 +12,12 @@
 //   * share/picongpu/tests/CurrentDeposition (Python Esirkepov reference imported from the reference
 //     tree to generate tests/golden/current_deposition.npz)
 //   * share/picongpu/tests/Pusher/README.rst        (gyro radius / phase drift bounds)
+// Restated without a golden vector in the reference (checked by their own known answers in
+// tests/test_oracle_golden.py and by construction against the cited source): the Higuera-Cary pusher
+// (gyration test of share/picongpu/tests/Pusher applies), the Binomial current interpolation (delta
+// response = 1-2-1 tensor weights / 64), the exponential absorber (attenuation profile), the open-boundary step.
+// The coupled step as a whole is additionally pinned on the GPU by the reference's acceptance test
+// share/picongpu/tests/KHI_growthRate (tests/test_gpu_parity.py::test_khi_growth_rate_reference_acceptance).
 // The reference binary itself cannot be built in this image (needs Boost + MPI), see DESIGN.md.
 //
 // All paths cited below are relative to /root/reference/include/ unless stated otherwise
