@@ -370,13 +370,16 @@ namespace picstep
     }
 
     // EnergyParticles.x.cpp:100-131 + KinEnergy.hpp:38-68
-    __global__ void __launch_bounds__(256) particleEnergyKernel(DevParams P, SpeciesDev S, uint32_t const* __restrict__ nPart, double* __restrict__ out)
+    __global__ void __launch_bounds__(256) particleEnergyKernel(DevParams P, SpeciesDev S, uint32_t const* __restrict__ nPart, uint32_t const* __restrict__ inv, double* __restrict__ out)
     {
         uint32_t const n = *nPart;
         double ek = 0, et = 0;
         float const c2 = P.c * P.c;
-        for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        for(uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
         {
+            // lazily re-sorted species: slot j of the frame runs lives at inv[j] (the sum does not care about the order,
+            // but the buffer also holds the slots of particles that have left)
+            uint32_t const i = inv ? inv[j] : j;
             float const ux = S.mom[0][i], uy = S.mom[1][i], uz = S.mom[2][i];
             float m2 = ux * ux;
             m2 += uy * uy;
@@ -549,9 +552,9 @@ namespace picstep
         return cudaGetLastError();
     }
 
-    cudaError_t launchParticleEnergy(DevParams const& P, SpeciesDev S, uint32_t const* nPart, double* out, cudaStream_t st)
+    cudaError_t launchParticleEnergy(DevParams const& P, SpeciesDev S, uint32_t const* nPart, uint32_t const* inv, double* out, cudaStream_t st)
     {
-        particleEnergyKernel<<<148 * 8, 256, 0, st>>>(P, S, nPart, out);
+        particleEnergyKernel<<<148 * 8, 256, 0, st>>>(P, S, nPart, inv, out);
         return cudaGetLastError();
     }
 

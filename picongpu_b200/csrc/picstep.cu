@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -47,7 +48,7 @@ namespace picstep
     cudaError_t launchAosToSoa(float const*, Field3, long long, cudaStream_t);
     cudaError_t launchSoaToAos(Field3, float*, long long, cudaStream_t);
     cudaError_t launchFieldEnergy(DevParams const&, Field3, Field3, double*, cudaStream_t);
-    cudaError_t launchParticleEnergy(DevParams const&, SpeciesDev, uint32_t const*, double*, cudaStream_t);
+    cudaError_t launchParticleEnergy(DevParams const&, SpeciesDev, uint32_t const*, uint32_t const*, double*, cudaStream_t);
     cudaError_t launchChargeDensity(int, DevParams const&, SpeciesDev, uint32_t const*, float*, cudaStream_t);
     cudaError_t launchGaussResidual(DevParams const&, Field3, float const*, int*, cudaStream_t);
     cudaError_t launchKhiInit(DevParams const&, SpeciesDev, SpeciesDev, uint32_t*, uint32_t*, KhiArgs const&, cudaStream_t);
@@ -73,6 +74,7 @@ namespace picstep
         uint32_t* cellCnt = nullptr; // per destination cell: histogram of the re-sort keys (ranked mode: arrivals only)
         uint32_t* stayCnt = nullptr; // per cell: particles that stay (written by the fused kernel, zero otherwise)
         uint32_t* rank = nullptr; // per particle: slot inside the destination cell (fused kernel)
+        uint32_t uploadN = 0; // particle count of the upload in flight (uploadCopies -> uploadSort)
         bool ranked = false; // key/rank/stayCnt come from the fused kernel (which wrote the pushed attributes into buffer cur^1)
         uint32_t* inv = nullptr; // lazy re-sort: attribute index of slot j of the run order
         bool lazy = false; // attr[cur] is addressed through inv; cell[cur], cellOff[cur] are in run order
@@ -884,7 +886,9 @@ extern "C"
     }
 
     // ---- particles ------------------------------------------------------------------------------------------------
-    static int uploadAsync(picstep_ctx* c, int32_t sp, int64_t n, const float* pos, const float* mom, const float* w, const int32_t* cell)
+    // Upload of one species in two parts: the host-to-device copies (on any stream: picstep_step_host sends the next
+    // species on the second stream while the previous one is being pushed) and the sort into frame runs.
+    static int uploadCopies(picstep_ctx* c, int32_t sp, int64_t n, const float* pos, const float* mom, const float* w, const int32_t* cell, cudaStream_t st)
     {
         SpeciesHost& s = c->species[sp];
         if(n > s.capacity || s.capacity == 0)
@@ -897,23 +901,37 @@ extern "C"
         s.lazy = false; // everything is overwritten
         int const stage = s.cur ^ 1;
         int const ncell = numCells(c);
-        CU(c, cudaMemsetAsync(s.cellCnt, 0, sizeof(uint32_t) * ncell, c->stream));
-        uint32_t const n32 = uint32_t(n);
-        CU(c, cudaMemcpyAsync(s.nDev + stage, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemsetAsync(s.cellCnt, 0, sizeof(uint32_t) * ncell, st));
+        s.uploadN = uint32_t(n);
+        CU(c, cudaMemcpyAsync(s.nDev + stage, &s.uploadN, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         for(int k = 0; k < 3; ++k)
         {
-            CU(c, cudaMemcpyAsync(s.attr[stage][k], pos + k * n, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
-            CU(c, cudaMemcpyAsync(s.attr[stage][3 + k], mom + k * n, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+            CU(c, cudaMemcpyAsync(s.attr[stage][k], pos + k * n, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+            CU(c, cudaMemcpyAsync(s.attr[stage][3 + k], mom + k * n, sizeof(float) * n, cudaMemcpyHostToDevice, st));
         }
-        CU(c, cudaMemcpyAsync(s.attr[stage][6], w, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(s.attr[stage][6], w, sizeof(float) * n, cudaMemcpyHostToDevice, st));
         // the int32 host cell indices travel through the (not yet used) key array of the active buffer's pos.x
         int32_t* cellIn = reinterpret_cast<int32_t*>(s.attr[s.cur][0]);
-        CU(c, cudaMemcpyAsync(cellIn, cell, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(cellIn, cell, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        return PICSTEP_OK;
+    }
+
+    static int uploadSort(picstep_ctx* c, int32_t sp)
+    {
+        SpeciesHost& s = c->species[sp];
+        int const stage = s.cur ^ 1;
+        int32_t* cellIn = reinterpret_cast<int32_t*>(s.attr[s.cur][0]);
         s.ranked = false;
-        KL(c, 1, launchKeysFromCells(c->P, cellIn, n32, s.key, s.cellCnt, c->flags + 1, c->stream));
+        KL(c, 1, launchKeysFromCells(c->P, cellIn, s.uploadN, s.key, s.cellCnt, c->flags + 1, c->stream));
         s.cur = stage; // resortSpecies reads from `cur` and writes to the other one
-        s.nUpper = n32;
+        s.nUpper = s.uploadN;
         return resortSpecies(c, s, 0, 0);
+    }
+
+    static int uploadAsync(picstep_ctx* c, int32_t sp, int64_t n, const float* pos, const float* mom, const float* w, const int32_t* cell)
+    {
+        int const rc = uploadCopies(c, sp, n, pos, mom, w, cell, c->stream);
+        return rc ? rc : uploadSort(c, sp);
     }
 
     int picstep_particles_upload(picstep_ctx* c, int32_t sp, int64_t n, const float* pos, const float* mom, const float* w, const int32_t* cell)
@@ -1256,10 +1274,9 @@ extern "C"
         return PICSTEP_OK;
     }
 
-    int picstep_step(picstep_ctx* c, uint32_t first, uint32_t n)
+    // hook(s): called before species s is pushed in the FIRST step (picstep_step_host finishes the upload of s there)
+    static int stepImpl(picstep_ctx* c, uint32_t first, uint32_t n, std::function<int(int)> const& hook)
     {
-        if(!c)
-            return PICSTEP_ERR_INVALID;
         CU(c, cudaSetDevice(c->device));
         int const ns = int(c->species.size());
         // fast path: the deposition does not depend on the field update, so it is fused into the push kernel
@@ -1297,6 +1314,8 @@ extern "C"
             rc = picstep_current_reset(c);
             for(int s = 0; s < ns && !rc; ++s)
             {
+                if(it == 0 && (rc = hook(s)))
+                    break;
                 if(!fused)
                 {
                     rc = picstep_push(c, s, step);
@@ -1343,6 +1362,13 @@ extern "C"
         return rc;
     }
 
+    int picstep_step(picstep_ctx* c, uint32_t first, uint32_t n)
+    {
+        if(!c)
+            return PICSTEP_ERR_INVALID;
+        return stepImpl(c, first, n, [](int) { return int(PICSTEP_OK); });
+    }
+
     int picstep_step_host(picstep_ctx* c, uint32_t step, float* E, float* B, int32_t nSpecies, const int64_t* n, const float* const* pos, const float* const* mom, const float* const* w, const int32_t* const* cell, double* energies4)
     {
         if(!c || !E || !B || nSpecies != int(c->species.size()))
@@ -1351,13 +1377,37 @@ extern "C"
         size_t const fbytes = sizeof(float) * 3 * c->P.vol;
         CU(c, cudaMemcpyAsync(c->fieldMem[PICSTEP_FIELD_E], E, fbytes, cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemcpyAsync(c->fieldMem[PICSTEP_FIELD_B], B, fbytes, cudaMemcpyHostToDevice, c->stream));
-        for(int s = 0; s < nSpecies; ++s)
+        // Species 0 is uploaded and sorted on the main stream; the copies of every further species go to the second
+        // stream, so that they travel while the species before them is pushed, and are sorted right before their push.
+        std::vector<cudaEvent_t> copied(size_t(nSpecies), nullptr);
+        int rc = uploadCopies(c, 0, n[0], pos[0], mom[0], w[0], cell[0], c->stream);
+        if(!rc)
         {
-            int const rc = uploadAsync(c, s, n[s], pos[s], mom[s], w[s], cell[s]);
-            if(rc)
-                return rc;
+            // the copies of the next species start when these are through (both streams share the PCIe link; started
+            // together they would each get half of it and the first push could not begin any earlier)
+            CU(c, cudaEventRecord(c->evFused, c->stream));
+            CU(c, cudaStreamWaitEvent(c->side, c->evFused, 0));
+            rc = uploadSort(c, 0);
         }
-        int rc = picstep_step(c, step, 1);
+        for(int s = 1; s < nSpecies && !rc; ++s)
+        {
+            rc = uploadCopies(c, s, n[s], pos[s], mom[s], w[s], cell[s], c->side);
+            if(!rc && cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming) == cudaSuccess)
+                cudaEventRecord(copied[s], c->side);
+        }
+        if(!rc)
+            rc = stepImpl(c, step, 1, [&](int s) {
+                if(s == 0)
+                    return int(PICSTEP_OK);
+                if(copied[s])
+                    cudaStreamWaitEvent(c->stream, copied[s], 0);
+                else
+                    cudaStreamSynchronize(c->side);
+                return uploadSort(c, s);
+            });
+        for(auto e : copied)
+            if(e)
+                cudaEventDestroy(e);
         if(rc)
             return rc;
         CU(c, cudaMemcpyAsync(E, c->fieldMem[PICSTEP_FIELD_E], fbytes, cudaMemcpyDeviceToHost, c->stream));
@@ -1413,10 +1463,8 @@ extern "C"
         {
             SpeciesHost& s = c->species[sp];
             CU(c, cudaMemsetAsync(c->redBuf, 0, sizeof(double) * 2, c->stream));
-            if(int rc = ensureSorted(c, s))
-                return rc;
             if(s.capacity)
-                KL(c, 1, launchParticleEnergy(P, devOf(c, s, s.cur), s.nDev + s.cur, c->redBuf, c->stream));
+                KL(c, 1, launchParticleEnergy(P, devOf(c, s, s.cur), s.nDev + s.cur, s.lazy ? s.inv : nullptr, c->redBuf, c->stream));
             CU(c, cudaMemcpyAsync(c->hostPinned, c->redBuf, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
             CU(c, cudaStreamSynchronize(c->stream));
             double const* r = reinterpret_cast<double const*>(c->hostPinned);
