@@ -12,6 +12,7 @@
 //   * share/picongpu/tests/CurrentDeposition (Python Esirkepov reference imported from the reference
 //     tree to generate tests/golden/current_deposition.npz)
 //   * share/picongpu/tests/Pusher/README.rst        (gyro radius / phase drift bounds)
+//   * share/picongpu/tests/PusherScaling/README.rst (phase lag ~ dt^2: exponent 2 +- 0.1, std <= 0.05)
 // Restated without a golden vector in the reference (checked by their own known answers in
 // tests/test_oracle_golden.py and by construction against the cited source): the Higuera-Cary pusher
 // (gyration test of share/picongpu/tests/Pusher applies), the Binomial current interpolation (delta

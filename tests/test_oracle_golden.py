@@ -346,3 +346,39 @@ def test_step_open_equals_periodic_step(orc):
     for a, b in zip(Fa[:2], Fb[:2]):
         assert np.abs(o.interior(a) - o.interior(b)).max() <= 2e-6 * np.abs(o.interior(a)).max()
     assert np.abs(e["mom"] - e2["mom"]).max() <= 1e-6 * np.abs(e["mom"]).max() and np.array_equal(i["cell"], i2["cell"])
+
+
+# ---- share/picongpu/tests/PusherScaling/README.rst -----------------------------------------------------------
+@pytest.mark.parametrize("pusher", [prm.PUSHER_BORIS, prm.PUSHER_VAY, prm.PUSHER_HIGUERA_CARY])
+def test_pusher_phase_lag_scales_with_dt_squared(orc, pusher):
+    """Electron with beta = 0.5 gyrating in a homogeneous B_z at 10, 20, 40, 80 and 160 steps per turn: the numerical
+    phase lag per turn grows by a factor of four when the time step doubles, d(phi) ~ dt^x with |x - 2| <= 0.1 and a
+    standard deviation of x below 0.05 (epsilon / delta of the README)."""
+    p = prm.khi_params(grid=(16, 16, 16), pusher=pusher)
+    o = orc.Oracle(p)
+    L = o.L
+    w = np.float32(p.typical_num_particles_per_macro)
+    mass = np.float32(p.base_mass) * w
+    q = np.float32(p.base_charge) * w
+    beta = 0.5
+    gamma = 1.0 / math.sqrt(1 - beta * beta)
+    lags = []
+    for steps_per_turn in (160, 80, 40, 20, 10):
+        mom = np.array([gamma * beta * float(mass) * p.c, 0, 0], np.float32)
+        omega = 2 * math.pi / (steps_per_turn * p.dt)
+        B = np.array([0, 0, omega * gamma * float(mass) / abs(float(q))], np.float32)
+        E = np.zeros(3, np.float32)
+        cur = np.zeros(3, np.float32)
+        turns = 4
+        ph = [0.0]
+        for _ in range(turns * steps_per_turn):
+            cur[:] = 0
+            L.orc_push_one(C.byref(o.p), 1.0, 1.0, w, E, B, mom, cur)
+            ph.append(math.atan2(float(mom[1]), float(mom[0])))
+        total = abs(np.unwrap(np.array(ph))[-1])
+        lags.append((2 * math.pi * turns - total) / turns)
+    lags = np.array(lags)
+    assert np.all(lags > 0)
+    x = np.log2(lags[1:] / lags[:-1])
+    assert abs(x.mean() - 2.0) <= 0.1, x
+    assert x.std() <= 0.05, x
