@@ -43,7 +43,12 @@ namespace picstep
         static constexpr int NK = WN - 1;
         static constexpr int FR = Sh::SUPP + 1; // entries of the off-support assignment arrays
         static constexpr int NMAX0 = WN - Sh::SUPP; // largest window index of frame entry 0 in a narrow record
-        static constexpr int AXW = 20, RECW = 3 * AXW, NREC = 33; // record 32 stays all zero
+        // record, per axis: {S0[0],S0[1],DS[0],DS[1]}, {S0[2],S0[3],DS[2],DS[3]}, [PQREC: {P[0],P[1],Q[0],Q[1]},
+        // {P[2],P[3],Q[2],Q[3]},] {C[0],C[1],C[2],0}; the 33rd record is all zero.  TSC keeps P = S0 + DS/2 and
+        // Q = S0/2 + DS/3 in the record (measured 0.2 % faster); PQS forms them in phase 2, which shrinks the records from
+        // 63 to 38 KB per CTA and lets two CTAs share an SM next to the larger E/B tile (122 -> 95.5 ms/step).
+        static constexpr bool PQREC = Sh::SUPP != WN;
+        static constexpr int COFF = PQREC ? 16 : 8, AXW = COFF + 4, RECW = 3 * AXW, NREC = 33;
         static constexpr int WARPS = 8, CELLS_PER_WARP = SCVOL / WARPS; // 32 cells: 8 x, 4 y, 1 z
         static constexpr int PX = SCX + WN - 1, PY = SCY / 2 + WN - 1, PZ = 1 + WN - 1, PV = PX * PY * PZ;
         static constexpr int TX = SCX + WN - 1, TY = SCY + WN - 1, TZ = SCZ + WN - 1, TV = TX * TY * TZ;
@@ -134,8 +139,8 @@ namespace picstep
         int const ai = (comp + 1) % 3, aj = (comp + 2) % 3; // Jx: (i,j) = (y,z); Jy: (z,x); Jz: (x,y)
         // a lane reads {S0,DS} of axis i at nodes 2ah,2ah+1, {P,Q} of axis j at nodes 2bh,2bh+1 and C of its component
         int const offSD = ai * C::AXW + 4 * ah;
-        int const offPQ = aj * C::AXW + 8 + 4 * bh;
-        int const offC = comp * C::AXW + 16;
+        int const offPQ = aj * C::AXW + (C::PQREC ? 8 : 0) + 4 * bh; // {P,Q} (or {S0,DS}: P, Q formed in the pass) of axis j
+        int const offC = comp * C::AXW + C::COFF;
         auto strideOf = [](int a) { return a == 0 ? 1 : (a == 1 ? C::PX : C::PX * C::PY); };
         int const sC = strideOf(comp), sJ = strideOf(aj);
         int const laneTile = comp * C::PV + (2 * ah + slot) * strideOf(ai) + 2 * bh * sJ;
@@ -406,15 +411,18 @@ namespace picstep
                             {
                                 F2 const s0p(S0[2 * j], S0[2 * j + 1]);
                                 DS[j] = F2(S1[2 * j], S1[2 * j + 1]) - s0p;
-                                F2 const Pp = fma2(DS[j], F2(0.5f), s0p);
-                                F2 const Qp = fma2(DS[j], F2(1.0f / 3.0f), s0p * F2(0.5f));
                                 r4[j] = make_float4(s0p.x, s0p.y, DS[j].x, DS[j].y);
-                                r4[2 + j] = make_float4(Pp.x, Pp.y, Qp.x, Qp.y);
+                                if constexpr(C::PQREC)
+                                {
+                                    F2 const Pp = fma2(DS[j], F2(0.5f), s0p);
+                                    F2 const Qp = fma2(DS[j], F2(1.0f / 3.0f), s0p * F2(0.5f));
+                                    r4[2 + j] = make_float4(Pp.x, Pp.y, Qp.x, Qp.y);
+                                }
                             }
                             // prefix sums start at the node left of the window when that one carries weight
                             float const cm = (SEMI && ext[d] < 0) ? sOut1 - sOut0 : 0.0f;
                             float const c0 = cm + DS[0].x, c1 = c0 + DS[0].y, c2 = c1 + DS[1].x;
-                            r4[4] = make_float4(c0 * f[d], c1 * f[d], c2 * f[d], 0.0f);
+                            r4[C::COFF / 4] = make_float4(c0 * f[d], c1 * f[d], c2 * f[d], 0.0f);
                         }
                         if constexpr(SEMI)
                             if(axOut >= 0)
@@ -427,7 +435,13 @@ namespace picstep
                                 long long const strd[3] = {1, P.N[0], (long long) P.N[0] * P.N[1]};
                                 long long const base = fidx(P, scx * SCX + P.g[0] + lx - C::WLO, scy * SCY + P.g[1] + ly - C::WLO, scz * SCZ + P.g[2] + lz - C::WLO);
                                 auto jOf = [&](int c) { return c == 0 ? J.c[0] : (c == 1 ? J.c[1] : J.c[2]); };
-                                auto at = [&](int d, int off, int n) { return rec[d * C::AXW + off + (n >> 1) * 4 + (n & 1)]; }; // off 0: S0, 2: DS, 8: P, 10: Q
+                                // off 0: S0, 2: DS of the record; 8: P = S0 + DS/2, 10: Q = S0/2 + DS/3
+                                auto at = [&](int d, int off, int n)
+                                {
+                                    float const* q = rec + d * C::AXW + (n >> 1) * 4 + (n & 1);
+                                    float const s0 = q[0], ds = q[2];
+                                    return off == 0 ? s0 : (off == 2 ? ds : (off == 8 ? s0 + 0.5f * ds : 0.5f * s0 + (1.0f / 3.0f) * ds));
+                                };
                                 int const nout = sideOut < 0 ? -1 : C::WN, kout = sideOut < 0 ? -1 : C::WN - 1;
                                 float const cx = sideOut < 0 ? fOut * dsOut : -(fOut * dsOut);
                                 float* const ja = jOf(A) + base + kout * strd[A];
@@ -448,8 +462,8 @@ namespace picstep
 #pragma unroll
                                     for(int k = 0; k < C::NK; ++k)
                                     {
-                                        redGlobal(j1 + a * strd[jA] + k * strd[iA], rec[iA * C::AXW + 16 + k] * t1);
-                                        redGlobal(j2 + a * strd[iA] + k * strd[jA], rec[jA * C::AXW + 16 + k] * t2);
+                                        redGlobal(j1 + a * strd[jA] + k * strd[iA], rec[iA * C::AXW + C::COFF + k] * t1);
+                                        redGlobal(j2 + a * strd[iA] + k * strd[jA], rec[jA * C::AXW + C::COFF + k] * t2);
                                     }
                                 }
                             }
@@ -480,7 +494,7 @@ namespace picstep
                 {
 #pragma unroll
                     for(int d = 0; d < 3; ++d)
-                        *reinterpret_cast<float4*>(rec + d * C::AXW + 16) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        *reinterpret_cast<float4*>(rec + d * C::AXW + C::COFF) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 }
             }
             // ---- phase 2: two records per pass (one per half warp), accumulators flushed when the cell changes ------
@@ -516,9 +530,15 @@ namespace picstep
             auto pass = [&](float const* pSD, float const* pPQ, float const* pC)
             {
                 float4 const sd = *reinterpret_cast<float4 const*>(pSD); // {S0[a0], S0[a0+1], DS[a0], DS[a0+1]}
-                float4 const pq = *reinterpret_cast<float4 const*>(pPQ); // {P[b0], P[b0+1], Q[b0], Q[b0+1]}
+                float4 const sj = *reinterpret_cast<float4 const*>(pPQ); // PQREC: {P[b0], P[b0+1], Q[b0], Q[b0+1]}, else {S0.., DS..}
                 float4 const c4 = *reinterpret_cast<float4 const*>(pC);
-                F2 const pp(pq.x, pq.y), qq(pq.z, pq.w);
+                F2 pp(sj.x, sj.y), qq(sj.z, sj.w);
+                if constexpr(!C::PQREC)
+                {
+                    F2 const s0j = pp, dsj = qq;
+                    pp = fma2(dsj, F2(0.5f), s0j); // P = S0 + DS/2
+                    qq = fma2(dsj, F2(1.0f / 3.0f), s0j * F2(0.5f)); // Q = S0/2 + DS/3
+                }
                 F2 const t0 = fma2(F2(sd.z), qq, F2(sd.x) * pp);
                 F2 const t1 = fma2(F2(sd.w), qq, F2(sd.y) * pp);
                 acc[0][0] = fma2(F2(c4.x), t0, acc[0][0]);
