@@ -93,4 +93,53 @@ namespace picstep
         esirkepov1DGlobal<SHAPE, 2, 0, 1>(jy, stride, status, p0, p1, csdy);
         esirkepov1DGlobal<SHAPE, 0, 1, 2>(jz, stride, status, p0, p1, csdz);
     }
+
+    /** emz::DepositCurrent::cptCurrent1D (EmZ/DepositCurrent.hpp:77-118) of one on-support segment with global atomics:
+     * fixed loop bounds SUPP x SUPP x (SUPP-1), origin = node of the segment's assignment cell. */
+    template<int SHAPE, int R0, int R1, int R2>
+    __device__ __forceinline__ void emz1DGlobal(float* __restrict__ origin, long long const stride[3], float const p0[3], float const p1[3], float currentSurfaceDensity)
+    {
+        using S = Shape<SHAPE>;
+        if(p0[R2] == p1[R2])
+            return;
+        constexpr int begin = S::BEGIN;
+        float s0i[S::SUPP], s1i[S::SUPP], s0j[S::SUPP], s1j[S::SUPP], s0k[S::SUPP], s1k[S::SUPP];
+        S::on(p0[R0], s0i);
+        S::on(p1[R0], s1i);
+        S::on(p0[R1], s0j);
+        S::on(p1[R1], s1j);
+        S::on(p0[R2], s0k);
+        S::on(p1[R2], s1k);
+#pragma unroll
+        for(int i = 0; i < S::SUPP; ++i)
+        {
+            float const a0 = s0i[i];
+            float const da = s1i[i] - a0;
+#pragma unroll
+            for(int j = 0; j < S::SUPP; ++j)
+            {
+                float const b0 = s0j[j];
+                float const db = s1j[j] - b0;
+                float const tmp = -currentSurfaceDensity * (a0 * b0 + 0.5f * (da * b0 + a0 * db) + (1.0f / 3.0f) * db * da);
+                float acc = 0.0f;
+#pragma unroll
+                for(int k = 0; k < S::SUPP - 1; ++k)
+                {
+                    acc += (s1k[k] - s0k[k]) * tmp;
+                    redGlobal(origin + (begin + i) * stride[R0] + (begin + j) * stride[R1] + (begin + k) * stride[R2], acc);
+                }
+            }
+        }
+    }
+
+    /** Slow path of the run kernel for EmZ: one segment, all three components */
+    template<int SHAPE>
+    __device__ __noinline__ void emzSegmentGlobal(float* jx, float* jy, float* jz, long long strideY, long long strideZ, float p0x, float p0y, float p0z, float p1x, float p1y, float p1z, float csdx, float csdy, float csdz)
+    {
+        long long const stride[3] = {1, strideY, strideZ};
+        float const p0[3] = {p0x, p0y, p0z}, p1[3] = {p1x, p1y, p1z};
+        emz1DGlobal<SHAPE, 1, 2, 0>(jx, stride, p0, p1, csdx);
+        emz1DGlobal<SHAPE, 2, 0, 1>(jy, stride, p0, p1, csdy);
+        emz1DGlobal<SHAPE, 0, 1, 2>(jz, stride, p0, p1, csdz);
+    }
 } // namespace picstep

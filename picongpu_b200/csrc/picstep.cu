@@ -22,8 +22,8 @@ namespace picstep
     cudaError_t launchGather(int, DevParams const&, SpeciesDev const&, Field3, Field3, uint32_t const*, float*, long long, cudaStream_t);
     cudaError_t launchDeposit(int, int, bool, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
     bool runKernelSupports(int, int);
-    cudaError_t launchDepositRun(int, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
-    cudaError_t launchPushDeposit(int, int, DevParams const&, SpeciesDev const&, SpeciesDev const&, uint32_t const*, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, TileMaps const&, cudaStream_t);
+    cudaError_t launchDepositRun(int, int, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
+    cudaError_t launchPushDeposit(int, int, int, DevParams const&, SpeciesDev const&, SpeciesDev const&, uint32_t const*, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, TileMaps const&, cudaStream_t);
     cudaError_t launchInvertRanked(uint32_t const*, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t const*, uint32_t*, uint16_t*, cudaStream_t);
     cudaError_t launchAppendRecords(MigRecord const*, uint32_t, uint32_t const*, uint32_t, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, uint32_t*, int*, cudaStream_t);
     cudaError_t launchGatherPerm(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t, cudaStream_t);
@@ -1150,7 +1150,7 @@ extern "C"
         if(int rc = ensureSorted(c, s))
             return rc;
         if(runKernelSupports(c->prm.shape, c->prm.current_solver) && !(c->prm.flags & 3))
-            KL(c, 1, launchDepositRun(c->prm.shape, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
+            KL(c, 1, launchDepositRun(c->prm.shape, c->prm.current_solver, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
         else
             KL(c, 1, launchDeposit(c->prm.shape, c->prm.current_solver, (c->prm.flags & 1) != 0, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
         return PICSTEP_OK;
@@ -1164,7 +1164,7 @@ extern "C"
         SpeciesHost& s = c->species[sp];
         if(s.capacity == 0)
             return PICSTEP_OK;
-        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), devOf(c, s, s.cur ^ 1), s.lazy ? s.inv : nullptr, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, c->tileMaps, c->stream));
+        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->prm.current_solver, c->P, devOf(c, s, s.cur), devOf(c, s, s.cur ^ 1), s.lazy ? s.inv : nullptr, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, c->tileMaps, c->stream));
         s.ranked = true;
         return PICSTEP_OK;
     }

@@ -64,7 +64,7 @@ namespace picstep
         return sizeof(float) * ((FUSED ? C::EBW : 0) + C::WARPS * 3 * C::PV + C::WARPS * C::NREC * C::RECW);
     }
 
-    template<int SHAPE, int PUSHER, bool FUSED>
+    template<int SHAPE, int PUSHER, bool FUSED, int SOLVER>
     __global__ void __launch_bounds__(256, 2) runKernel(
         DevParams P,
         SpeciesDev S, // attributes are read from here: slot j of the cell-sorted order lives at index inv[j] (j if inv is null)
@@ -184,6 +184,50 @@ namespace picstep
         uint32_t const pBeg = cellOff[sc * SCVOL + warp * C::CELLS_PER_WARP];
         uint32_t const pEnd = cellOff[sc * SCVOL + (warp + 1) * C::CELLS_PER_WARP];
 
+        // EmZ: record of one on-support segment (start and end values on the same SUPP nodes at window offset o)
+        [[maybe_unused]] auto emzRecord = [&](float* rec, F2 const(&t)[3][Sh::SUPP], int const(&o)[3], float const(&f)[3])
+        {
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+            {
+                float S0[C::WN], S1[C::WN];
+#pragma unroll
+                for(int n = 0; n < C::WN; ++n)
+                {
+                    float v0 = 0.0f, v1 = 0.0f;
+#pragma unroll
+                    for(int m = 0; m <= C::NMAX0; ++m)
+                    {
+                        int const sx = n - m;
+                        if(sx >= 0 && sx < Sh::SUPP)
+                        {
+                            v0 = (o[d] == m) ? t[d][sx].x : v0;
+                            v1 = (o[d] == m) ? t[d][sx].y : v1;
+                        }
+                    }
+                    S0[n] = v0;
+                    S1[n] = v1;
+                }
+                float4* r4 = reinterpret_cast<float4*>(rec + d * C::AXW);
+                F2 DS[2];
+#pragma unroll
+                for(int j = 0; j < 2; ++j)
+                {
+                    F2 const s0p(S0[2 * j], S0[2 * j + 1]);
+                    DS[j] = F2(S1[2 * j], S1[2 * j + 1]) - s0p;
+                    r4[j] = make_float4(s0p.x, s0p.y, DS[j].x, DS[j].y);
+                    if constexpr(C::PQREC)
+                    {
+                        F2 const Pp = fma2(DS[j], F2(0.5f), s0p);
+                        F2 const Qp = fma2(DS[j], F2(1.0f / 3.0f), s0p * F2(0.5f));
+                        r4[2 + j] = make_float4(Pp.x, Pp.y, Qp.x, Qp.y);
+                    }
+                }
+                float const c0 = DS[0].x, c1 = c0 + DS[0].y, c2 = c1 + DS[1].x;
+                r4[C::COFF / 4] = make_float4(c0 * f[d], c1 * f[d], c2 * f[d], 0.0f);
+            }
+        };
+
         // The particle attributes of a chunk are loaded one chunk ahead: the loads are issued before phase 2 of the
         // previous chunk, which does not touch global memory, so the HBM latency is hidden by it.
         // The attributes are addressed through the permutation of the previous step's re-sort (inv), whose entries
@@ -226,6 +270,12 @@ namespace picstep
             bool useRec = false; // this lane wrote a record phase 2 has to add
             bool stays = false;
             uint32_t myRank = 0;
+            // EmZ: a trajectory that changes its assignment cell is split at the relay point; the second segment is
+            // kept here while phase 2 adds the first one
+            [[maybe_unused]] F2 tSeg2[3][Sh::SUPP];
+            [[maybe_unused]] float fSeg2[3] = {0.0f, 0.0f, 0.0f};
+            [[maybe_unused]] int oSeg2[3] = {0, 0, 0};
+            [[maybe_unused]] bool twoSeg = false;
             __syncwarp(); // phase 2 of the previous chunk has finished reading the records
             // ---- phase 1: lane = particle -----------------------------------------------------------------------
             if(valid)
@@ -317,7 +367,63 @@ namespace picstep
                 else
                     velocityOf(rc2, mass, u[0], u[1], u[2], vel[0], vel[1], vel[2]);
 
-                if(deposit)
+                if constexpr(SOLVER == 1)
+                {
+                    // EmZ (EmZ.hpp:66-155, EmZ/DepositCurrent.hpp:35-119): segment A = start -> relay point in the frame of
+                    // the start point's assignment cell, segment B = relay point -> end in the frame of the end point's;
+                    // each is an Esirkepov-type deposit with both points on the same support, i.e. one record each.
+                    if(deposit)
+                    {
+                        float const csd = charge * (1.0f / float(vol * P.dt));
+                        F2 tA[3][Sh::SUPP];
+                        float fA[3];
+                        int oA[3], cA[3], cB[3];
+                        float a0[3], a1[3], b0[3], b1[3];
+                        bool narrow = true, two = false;
+#pragma unroll
+                        for(int d = 0; d < 3; ++d)
+                        {
+                            float const dp = ps_div(vel[d] * P.dt, P.cell[d]);
+                            float const xe = x1[d], xs = xe - dp;
+                            int iS, iE;
+                            float const r = relay<even>(iS, iE, xs, xe);
+                            a0[d] = xs - float(iS);
+                            a1[d] = r - float(iS);
+                            b0[d] = r - float(iE);
+                            b1[d] = xe - float(iE);
+                            Sh::on(F2(a0[d], a1[d]), tA[d]);
+                            Sh::on(F2(b0[d], b1[d]), tSeg2[d]);
+                            fA[d] = (a0[d] == a1[d]) ? 0.0f : -(csd * P.cell[d]);
+                            fSeg2[d] = (b0[d] == b1[d]) ? 0.0f : -(csd * P.cell[d]);
+                            oA[d] = iS + Sh::BEGIN + C::WLO + dir[d];
+                            oSeg2[d] = iE + Sh::BEGIN + C::WLO + dir[d];
+                            if(oA[d] < 0 || oA[d] > C::NMAX0 || oSeg2[d] < 0 || oSeg2[d] > C::NMAX0)
+                                narrow = false;
+                            two = two || iS != iE;
+                            cA[d] = iS;
+                            cB[d] = iE;
+                        }
+                        if(narrow)
+                        {
+                            useRec = true;
+                            twoSeg = two;
+                            emzRecord(myRecs + lane * C::RECW, tA, oA, fA);
+                        }
+                        else
+                        {
+                            // wide trajectory: the reference loops with global atomics, per segment
+                            long long const sY = P.N[0], sZ = (long long) P.N[0] * P.N[1];
+                            long long const oa = fidx(P, scx * SCX + P.g[0] + lx + dir[0] + cA[0], scy * SCY + P.g[1] + ly + dir[1] + cA[1], scz * SCZ + P.g[2] + lz + dir[2] + cA[2]);
+                            emzSegmentGlobal<SHAPE>(J.c[0] + oa, J.c[1] + oa, J.c[2] + oa, sY, sZ, a0[0], a0[1], a0[2], a1[0], a1[1], a1[2], csd * P.cell[0], csd * P.cell[1], csd * P.cell[2]);
+                            if(two)
+                            {
+                                long long const ob = fidx(P, scx * SCX + P.g[0] + lx + dir[0] + cB[0], scy * SCY + P.g[1] + ly + dir[1] + cB[1], scz * SCZ + P.g[2] + lz + dir[2] + cB[2]);
+                                emzSegmentGlobal<SHAPE>(J.c[0] + ob, J.c[1] + ob, J.c[2] + ob, sY, sZ, b0[0], b0[1], b0[2], b1[0], b1[1], b1[2], csd * P.cell[0], csd * P.cell[1], csd * P.cell[2]);
+                            }
+                        }
+                    }
+                }
+                else if(deposit)
                 {
                     // Esirkepov.hpp:84-103: start and end point in the frame of gridShift = min(iS,iE); the on-support
                     // assignment values of both points are evaluated together (packed: .x start, .y end) and placed
@@ -588,6 +694,53 @@ namespace picstep
                 pPQ += 4 * C::RECW;
                 pC += 4 * C::RECW;
             }
+            if constexpr(SOLVER == 1)
+            {
+                // (the pass loop once more; kept out of the Esirkepov instantiation, whose code must not change)
+                auto runPasses = [&](uint32_t sMask)
+                {
+                    float const* q = myRecs + slot * C::RECW;
+                    float const *qSD = q + offSD, *qPQ = q + offPQ, *qC = q + offC;
+#pragma unroll 1
+                    for(int r = 0; r < n; r += 4)
+                    {
+                        uint32_t const b4 = (sMask >> r) & 0xfu;
+                        if(b4 == 0u)
+                        {
+                            pass(qSD, qPQ, qC);
+                            pass(qSD + 2 * C::RECW, qPQ + 2 * C::RECW, qC + 2 * C::RECW);
+                        }
+                        else
+                        {
+                            passSlow(qSD, qPQ, qC, b4 & 3u, r);
+                            passSlow(qSD + 2 * C::RECW, qPQ + 2 * C::RECW, qC + 2 * C::RECW, b4 >> 2, r + 2);
+                        }
+                        qSD += 4 * C::RECW;
+                        qPQ += 4 * C::RECW;
+                        qC += 4 * C::RECW;
+                    }
+                };
+                // second EmZ segment of the trajectories that changed their assignment cell: the same records again
+                if(__ballot_sync(FULL, twoSeg))
+                {
+                    __syncwarp(); // the first round has read the records
+                    float* const rec2 = myRecs + lane * C::RECW;
+                    if(twoSeg)
+                        emzRecord(rec2, tSeg2, oSeg2, fSeg2);
+                    else
+                    {
+#pragma unroll
+                        for(int d = 0; d < 3; ++d)
+                            *reinterpret_cast<float4*>(rec2 + d * C::AXW + C::COFF) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
+                    __syncwarp();
+                    // the round starts over at record 0: the accumulators hold the last cell of the first round
+                    int prev2 = __shfl_up_sync(FULL, lc, 1);
+                    if(lane == 0)
+                        prev2 = curCell;
+                    runPasses(__ballot_sync(FULL, valid && lc != prev2));
+                }
+            }
             if(FUSED && valid)
                 rank[i] = myRank; // last: the rank of an arrival is the return value of a global atomic
         }
@@ -639,45 +792,51 @@ namespace picstep
         }
     }
 
-    template<int SHAPE, int PUSHER, bool FUSED>
+    template<int SHAPE, int PUSHER, bool FUSED, int SOLVER = 0>
     cudaError_t launchRunT(DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, TileMaps const& maps, cudaStream_t st)
     {
         int const nscTot = P.nsc[0] * P.nsc[1] * P.nsc[2];
         constexpr size_t smem = runSmemBytes<SHAPE, FUSED>();
-        cudaError_t e = cudaFuncSetAttribute(runKernel<SHAPE, PUSHER, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaError_t e = cudaFuncSetAttribute(runKernel<SHAPE, PUSHER, FUSED, SOLVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if(e != cudaSuccess)
             return e;
-        runKernel<SHAPE, PUSHER, FUSED><<<nscTot, 256, smem, st>>>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps);
+        runKernel<SHAPE, PUSHER, FUSED, SOLVER><<<nscTot, 256, smem, st>>>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps);
         return cudaGetLastError();
     }
 
     bool runKernelSupports(int shape, int solver)
     {
-        return solver == 0 && shape >= 0 && shape <= 3;
+        // Esirkepov: NGP..PQS (PCS: support 5 does not fit the 4-node window); EmZ: CIC..PQS (no EmZ for NGP)
+        return (solver == 0 && shape >= 0 && shape <= 3) || (solver == 1 && shape >= 1 && shape <= 3);
     }
 
     /** stand-alone deposition of one species (picstep_deposit) */
-    cudaError_t launchDepositRun(int shape, DevParams const& P, SpeciesDev const& S, Field3 J, uint32_t const* cellOff, cudaStream_t st)
+    cudaError_t launchDepositRun(int shape, int solver, DevParams const& P, SpeciesDev const& S, Field3 J, uint32_t const* cellOff, cudaStream_t st)
     {
         Field3 none{};
         TileMaps const noMaps{};
-#define PS_CASE(SH)                                                                                                   \
-    if(shape == SH)                                                                                                   \
-        return launchRunT<SH, 0, false>(P, S, S, nullptr, none, none, J, cellOff, nullptr, nullptr, nullptr, nullptr, noMaps, st);
-        PS_CASE(0)
-        PS_CASE(1)
-        PS_CASE(2)
-        PS_CASE(3)
+#define PS_CASE(SH, SO)                                                                                               \
+    if(shape == SH && solver == SO)                                                                                   \
+        return launchRunT<SH, 0, false, SO>(P, S, S, nullptr, none, none, J, cellOff, nullptr, nullptr, nullptr, nullptr, noMaps, st);
+        PS_CASE(0, 0)
+        PS_CASE(1, 0)
+        PS_CASE(2, 0)
+        PS_CASE(3, 0)
+        PS_CASE(1, 1)
+        PS_CASE(2, 1)
+        PS_CASE(3, 1)
 #undef PS_CASE
         return cudaErrorInvalidValue;
     }
 
     /** fused gather + push + move + deposit of one species (picstep_step fast path) */
-    cudaError_t launchPushDeposit(int shape, int pusher, DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, TileMaps const& maps, cudaStream_t st)
+    cudaError_t launchPushDeposit(int shape, int pusher, int solver, DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, TileMaps const& maps, cudaStream_t st)
     {
 #define PS_CASE(SH, PU)                                                                                               \
-    if(shape == SH && pusher == PU)                                                                                   \
-        return launchRunT<SH, PU, true>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps, st);
+    if(shape == SH && pusher == PU && solver == 0)                                                                    \
+        return launchRunT<SH, PU, true, 0>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps, st);         \
+    if(shape == SH && pusher == PU && solver == 1 && SH >= 1)                                                         \
+        return launchRunT<(SH >= 1 ? SH : 1), PU, true, 1>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps, st);
         PS_CASE(0, 0)
         PS_CASE(1, 0)
         PS_CASE(2, 0)
