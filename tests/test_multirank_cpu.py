@@ -81,20 +81,33 @@ def _exchange_planes(F, axis_np, send_lo, send_hi, recv_lo, recv_hi, lo_rank, hi
 
     bl, bh = take(recv_lo).clone(), take(recv_hi).clone()
     sl_, sh_ = take(send_lo), take(send_hi)
-    # same posting order as comm.cu: sends (lower, upper), receives (upper, lower)
-    ops = [dist.P2POp(dist.isend, sl_, lo_rank), dist.P2POp(dist.isend, sh_, hi_rank),
-           dist.P2POp(dist.irecv, bh, hi_rank), dist.P2POp(dist.irecv, bl, lo_rank)]
+    # same posting order as comm.cu: sends (lower, upper), receives (upper, lower); a missing neighbour (-1, open
+    # boundary) is skipped on both sides
+    ops = []
+    if lo_rank >= 0:
+        ops.append(dist.P2POp(dist.isend, sl_, lo_rank))
+    if hi_rank >= 0:
+        ops.append(dist.P2POp(dist.isend, sh_, hi_rank))
+        ops.append(dist.P2POp(dist.irecv, bh, hi_rank))
+    if lo_rank >= 0:
+        ops.append(dist.P2POp(dist.irecv, bl, lo_rank))
     for r in dist.batch_isend_irecv(ops):
         r.wait()
-    put(recv_lo, bl)
-    put(recv_hi, bh)
+    if lo_rank >= 0:
+        put(recv_lo, bl)
+    if hi_rank >= 0:
+        put(recv_hi, bh)
 
 
-def _field_exchange(o, p, F, field, lo_rank, hi_rank):
-    add = field == FJ
+def _field_exchange(o, p, F, field, lo_rank, hi_rank, mode=None, width=None):
+    add = (field == FJ) if mode is None else (mode == "add")
     g, n = p.guard_cells, p.grid
     for a in range(3):
         lo, up = picstep.exchange_widths(p.shape, p.field_solver, p.lehe_dir, field, a)
+        if width is not None:
+            lo = up = width
+        if not p.periodic[a] and p.devices[a] == 1:
+            continue  # open axis inside one rank: no exchange
         if p.wrap[a]:
             o.halo_axis(F, a, lo, up, add=add)
         else:
@@ -125,15 +138,23 @@ def _migrate(p, sp, cell3, lo_rank, hi_rank):
     s_lo, s_hi = pack(out_lo, n[a]), pack(out_hi, -n[a])
     cnt = torch.tensor([s_lo.shape[1], s_hi.shape[1]])
     rc_hi, rc_lo = torch.zeros(1, dtype=torch.long), torch.zeros(1, dtype=torch.long)
-    ops = [dist.P2POp(dist.isend, cnt[0:1].clone(), lo_rank), dist.P2POp(dist.isend, cnt[1:2].clone(), hi_rank),
-           dist.P2POp(dist.irecv, rc_hi, hi_rank), dist.P2POp(dist.irecv, rc_lo, lo_rank)]
-    for r in dist.batch_isend_irecv(ops):
-        r.wait()
+
+    def both(send_lo_t, send_hi_t, recv_hi_t, recv_lo_t):
+        # particles leaving through an open face (neighbour -1) are absorbed: nothing is sent or received there
+        ops = []
+        if lo_rank >= 0:
+            ops.append(dist.P2POp(dist.isend, send_lo_t, lo_rank))
+        if hi_rank >= 0:
+            ops.append(dist.P2POp(dist.isend, send_hi_t, hi_rank))
+            ops.append(dist.P2POp(dist.irecv, recv_hi_t, hi_rank))
+        if lo_rank >= 0:
+            ops.append(dist.P2POp(dist.irecv, recv_lo_t, lo_rank))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+    both(cnt[0:1].clone(), cnt[1:2].clone(), rc_hi, rc_lo)
     r_hi, r_lo = torch.zeros((8, int(rc_hi)), dtype=torch.float32), torch.zeros((8, int(rc_lo)), dtype=torch.float32)
-    ops = [dist.P2POp(dist.isend, s_lo.contiguous(), lo_rank), dist.P2POp(dist.isend, s_hi.contiguous(), hi_rank),
-           dist.P2POp(dist.irecv, r_hi, hi_rank), dist.P2POp(dist.irecv, r_lo, lo_rank)]
-    for r in dist.batch_isend_irecv(ops):
-        r.wait()
+    both(s_lo.contiguous(), s_hi.contiguous(), r_hi, r_lo)
     rec = np.concatenate([r_lo.numpy(), r_hi.numpy()], axis=1)
     sp["pos"] = np.ascontiguousarray(np.concatenate([sp["pos"][:, stay], rec[0:3]], axis=1))
     sp["mom"] = np.ascontiguousarray(np.concatenate([sp["mom"][:, stay], rec[3:6]], axis=1))
@@ -154,14 +175,15 @@ def _kick(p, sp):
     sp["mom"][2] += (0.3 * np.cos(0.9 * gid)).astype(np.float32) * mass
 
 
-def _worker(rank, world, port, steps, outdir):
+def _worker(rank, world, port, steps, outdir, kw=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import picoracle as orc
 
     orc.lib().orc_set_num_threads(2)
-    p = prm.khi_params(grid=(16, 16, 8), devices=(1, world, 1), rank_pos=(0, rank, 0))
+    kw = kw or {}
+    p = prm.khi_params(grid=(16, 16, 8), devices=(1, world, 1), rank_pos=(0, rank, 0), **kw)
     assert p.wrap == (1, 0, 1)
     lo_rank, hi_rank = picstep.neighbor_ranks(p.devices, p.periodic, rank, 1)
     o, e, i = util.khi_ic(orc, p)
@@ -180,9 +202,13 @@ def _worker(rank, world, port, steps, outdir):
         for sp in (e, i):
             o.deposit(sp["massRatio"], sp["chargeRatio"], J, sp["pos"], sp["mom"], sp["w"], sp["cell"])
         _field_exchange(o, p, J, FJ, lo_rank, hi_rank)
+        if p.current_interpolation == 1:  # FieldJ "receive" exchange: one guard cell := neighbour border
+            _field_exchange(o, p, J, FJ, lo_rank, hi_rank, mode="copy", width=1)
         o.add_current(E, J)
+        o.absorb(E)
         _field_exchange(o, p, E, FE, lo_rank, hi_rank)
         o.update_b_half(E, B)
+        o.absorb(B)
         _field_exchange(o, p, B, FB, lo_rank, hi_rank)
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), E=o.interior(E), B=o.interior(B), ne=e["w"].shape[0], ni=i["w"].shape[0],
              migrated=migrated, ew=np.sort(e["mom"][0]))
@@ -214,4 +240,34 @@ def test_two_rank_slab_decomposition_equals_single_domain(orc, tmp_path):
     # same particles (momentum multiset) on both decompositions; J is summed in a different order per
     # decomposition, so E and with it the momenta agree to fp32 round-off, not bit for bit
     a, b = np.sort(np.concatenate([r[0]["ew"], r[1]["ew"]])), np.sort(e["mom"][0])
+    assert np.abs(a - b).max() / np.abs(b).max() < 1e-6
+
+
+OPEN = dict(periodic=(1, 0, 1), current_interpolation=1, absorber_kind=1, absorber_cells=((0, 0), (6, 6), (0, 0)),
+            absorber_strength=((0, 0), (0.05, 0.05), (0, 0)))
+
+
+def test_two_rank_open_boundary_equals_single_domain(orc, tmp_path):
+    """Same decomposition with an open, absorbing split axis and the Binomial filter: missing neighbours are skipped,
+    leavers through the open faces are absorbed, the J guard gets the neighbour's border for the filter."""
+    world, steps = 2, 4
+    port = 29500 + (os.getpid() % 2000) + 11
+    mp.spawn(_worker, args=(world, port, steps, str(tmp_path), OPEN), nprocs=world, join=True)
+    p = prm.khi_params(grid=(16, 32, 8), **OPEN)
+    o, e, i = util.khi_ic(orc, p)
+    _kick(p, e)
+    _kick(p, i)
+    n0 = e["w"].shape[0]
+    E, B, J = o.field(), o.field(), o.field()
+    sps = [e, i]
+    for _ in range(steps):
+        o.step_open(E, B, J, sps)
+    r = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % k)) for k in range(world)]
+    Eg = np.concatenate([r[0]["E"], r[1]["E"]], axis=2)
+    Bg = np.concatenate([r[0]["B"], r[1]["B"]], axis=2)
+    _, escale = util.khi_scales(p, 1)
+    assert np.abs(Eg - o.interior(E)).max() / escale < 1e-5
+    assert np.abs(Bg - o.interior(B)).max() / escale < 1e-5
+    assert int(r[0]["ne"]) + int(r[1]["ne"]) == sps[0]["w"].shape[0] < n0
+    a, b = np.sort(np.concatenate([r[0]["ew"], r[1]["ew"]])), np.sort(sps[0]["mom"][0])
     assert np.abs(a - b).max() / np.abs(b).max() < 1e-6
