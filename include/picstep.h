@@ -234,6 +234,10 @@ extern "C"
     /* neighbour ranks of `rank` along `axis` in a devices[3] grid, x fastest (CommunicatorMPI.cpp:70-111);
      * -1 where the boundary is not periodic */
     int picstep_neighbor_ranks(const int32_t* devices, const int32_t* periodic, int32_t rank, int32_t axis, int32_t* lower, int32_t* upper);
+    /* the same for the split axis of a sliding window: ranks keep their identity (NCCL / MPI rank) while their
+     * positions rotate, after `slides` calls of picstep_slide the rank at position q is (q + slides) mod n_ranks
+     * (CommunicatorMPI::slide, pmacc/communication/CommunicatorMPI.cpp:156-170); -1 where the window ends */
+    int picstep_window_neighbors(int32_t n_ranks, int32_t periodic, int32_t position, int32_t slides, int32_t* lower, int32_t* upper);
     /* guard widths actually exchanged for E/B (max of interpolation and solver margins,
      * fields/EMFieldBase.x.cpp:58-110) and J (current solver margins, FieldJ.x.cpp:78-118): out[0]=lower, out[1]=upper */
     int picstep_exchange_widths(int32_t shape, int32_t field_solver, int32_t lehe_dir, int32_t field, int32_t axis, int32_t* out2);

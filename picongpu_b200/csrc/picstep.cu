@@ -447,16 +447,8 @@ namespace
         DevParams& P = c->P;
         int const split = P.split_axis;
         c->rankLo = c->rankHi = -1;
-        if(split >= 0)
-        {
-            // NCCL ranks keep their identity when the window slides: after k slides the rank at position q is (q + k) mod n
-            int const n = p->devices[split], pos = p->rank_pos[split], k = c->slides % n;
-            bool const per = p->periodic[split] != 0;
-            if(pos > 0 || per)
-                c->rankLo = ((pos - 1 + n) % n + k) % n;
-            if(pos < n - 1 || per)
-                c->rankHi = ((pos + 1) % n + k) % n;
-        }
+        if(split >= 0) // NCCL ranks keep their identity when the window slides
+            picstep_window_neighbors(p->devices[split], p->periodic[split], p->rank_pos[split], c->slides, &c->rankLo, &c->rankHi);
         P.has_lower = c->rankLo >= 0;
         P.has_upper = c->rankHi >= 0;
         damp.assign(size_t(6) * ABS_MAX, 1.0f);
@@ -1360,6 +1352,16 @@ extern "C"
             if(pendingMig[s])
                 cudaStreamWaitEvent(c->stream, c->evMig[s], 0);
         return rc;
+    }
+
+    int picstep_window_neighbors(int32_t n, int32_t periodic, int32_t pos, int32_t slides, int32_t* lower, int32_t* upper)
+    {
+        if(n < 1 || pos < 0 || pos >= n || slides < 0 || !lower || !upper)
+            return PICSTEP_ERR_INVALID;
+        int const k = slides % n;
+        *lower = (pos > 0 || periodic) ? ((pos - 1 + n) % n + k) % n : -1;
+        *upper = (pos < n - 1 || periodic) ? ((pos + 1) % n + k) % n : -1;
+        return PICSTEP_OK;
     }
 
     int picstep_step(picstep_ctx* c, uint32_t first, uint32_t n)

@@ -28,7 +28,7 @@ SYMBOLS = [
     "picstep_field_update_after_current", "picstep_field_exchange", "picstep_step", "picstep_step_host",
     "picstep_sync", "picstep_reduce", "picstep_debug_gather", "picstep_comm_unique_id", "picstep_comm_init",
     "picstep_launch_count", "picstep_stage_times", "picstep_stream", "picstep_neighbor_ranks",
-    "picstep_exchange_widths", "picstep_slide", "picstep_moving_window_info",
+    "picstep_exchange_widths", "picstep_slide", "picstep_moving_window_info", "picstep_window_neighbors",
 ]
 
 
@@ -162,6 +162,15 @@ def moving_window_info(global_cells, local_cells, cell_size, c_dt, move_point, s
     if rc:
         raise PicstepError("picstep_moving_window_info: invalid argument")
     return bool(sl.value), off.value
+
+
+def window_neighbors(n_ranks, periodic, position, slides, exact=False):
+    """Ranks of the lower / upper neighbour of the rank at `position` after `slides` slides of the moving window."""
+    L = load(exact)
+    lo, hi = C.c_int32(-1), C.c_int32(-1)
+    if L.picstep_window_neighbors(n_ranks, int(periodic), position, slides, C.byref(lo), C.byref(hi)):
+        raise PicstepError("picstep_window_neighbors: invalid argument")
+    return lo.value, hi.value
 
 
 def neighbor_ranks(devices, periodic, rank, axis, exact=False):

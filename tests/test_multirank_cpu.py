@@ -271,3 +271,130 @@ def test_two_rank_open_boundary_equals_single_domain(orc, tmp_path):
     assert int(r[0]["ne"]) + int(r[1]["ne"]) == sps[0]["w"].shape[0] < n0
     a, b = np.sort(np.concatenate([r[0]["ew"], r[1]["ew"]])), np.sort(sps[0]["mom"][0])
     assert np.abs(a - b).max() / np.abs(b).max() < 1e-6
+
+
+# ---- moving window: rank rotation (GridController::slide) on the CPU emulation of the exchange scheme -----------------
+MW = dict(periodic=(1, 0, 1), moving_window=1, absorber_kind=1, absorber_cells=((0, 0), (6, 6), (0, 0)),
+          absorber_strength=((0, 0), (0.05, 0.05), (0, 0)))
+LOCAL = (16, 16, 8)
+
+
+def _new_slab(orc, p_top):
+    """Plasma of the slab that enters the window: KHI recipe with another seed, kept two cells away from the slab faces
+    (the fresh top rank has no guard data from its lower neighbour before the first exchange)."""
+    _, e, i = util.khi_ic(orc, p_top, seed=77)
+    out = []
+    for sp in (e, i):
+        cy = (sp["cell"] // p_top.grid[0]) % p_top.grid[1]
+        keep = (cy >= 2) & (cy < p_top.grid[1] - 2)
+        out.append(dict(massRatio=sp["massRatio"], chargeRatio=sp["chargeRatio"], pos=np.ascontiguousarray(sp["pos"][:, keep]),
+                        mom=np.ascontiguousarray(sp["mom"][:, keep]), w=np.ascontiguousarray(sp["w"][keep]), cell=np.ascontiguousarray(sp["cell"][keep])))
+    return out
+
+
+def _one_step(o, p, E, B, J, species, lo_rank, hi_rank):
+    J[:] = 0
+    for sp in species:
+        _, cell3 = o.push(sp["massRatio"], sp["chargeRatio"], E, B, sp["pos"], sp["mom"], sp["w"], sp["cell"], want_cell3=True)
+        _migrate(p, sp, cell3, lo_rank, hi_rank)
+    o.update_b_half(E, B)
+    _field_exchange(o, p, B, FB, lo_rank, hi_rank)
+    o.update_e(E, B)
+    for sp in species:
+        if sp["w"].shape[0]:
+            o.deposit(sp["massRatio"], sp["chargeRatio"], J, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+    _field_exchange(o, p, J, FJ, lo_rank, hi_rank)
+    o.add_current(E, J)
+    o.absorb(E)
+    _field_exchange(o, p, E, FE, lo_rank, hi_rank)
+    o.update_b_half(E, B)
+    o.absorb(B)
+    _field_exchange(o, p, B, FB, lo_rank, hi_rank)
+
+
+def _mw_worker(rank, world, port, steps, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import picoracle as orc
+
+    orc.lib().orc_set_num_threads(2)
+    pos, slides = rank, 0
+    p = prm.khi_params(grid=LOCAL, devices=(1, world, 1), rank_pos=(0, pos, 0), **MW)
+    lo_rank, hi_rank = picstep.window_neighbors(world, 0, pos, slides)
+    assert (lo_rank, hi_rank) == picstep.neighbor_ranks(p.devices, p.periodic, rank, 1)
+    o, e, i = util.khi_ic(orc, p)
+    _kick(p, e)
+    _kick(p, i)
+    species = [e, i]
+    E, B, J = o.field(), o.field(), o.field()
+    for _ in range(steps):
+        _one_step(o, p, E, B, J, species, lo_rank, hi_rank)
+    # slide: every rank moves one position down, the lowest becomes the (empty) top of the window
+    slides += 1
+    pos = (pos - 1) % world
+    p = prm.khi_params(grid=LOCAL, devices=(1, world, 1), rank_pos=(0, pos, 0), **MW)
+    o = orc.Oracle(p)  # the open faces moved with the positions
+    lo_rank, hi_rank = picstep.window_neighbors(world, 0, pos, slides)
+    if pos == world - 1:
+        E[:], B[:], J[:] = 0, 0, 0
+        species = _new_slab(orc, p)
+    for _ in range(steps):
+        _one_step(o, p, E, B, J, species, lo_rank, hi_rank)
+    np.savez(os.path.join(outdir, "mw%d.npz" % rank), E=o.interior(E), B=o.interior(B), ne=species[0]["w"].shape[0], ew=np.sort(species[0]["mom"][0]), pos=pos)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_window_neighbors_follow_the_slides():
+    """After k slides the rank at position q is (q + k) mod n; the window ends have no neighbour."""
+    n = 4
+    for k in range(9):
+        rank_at = [(q + k) % n for q in range(n)]
+        for q in range(n):
+            lo, hi = picstep.window_neighbors(n, 0, q, k)
+            assert lo == (rank_at[q - 1] if q > 0 else -1) and hi == (rank_at[q + 1] if q < n - 1 else -1)
+    assert picstep.window_neighbors(3, 1, 0, 0) == (2, 1)
+
+
+def test_two_rank_moving_window_slide_equals_shifted_single_domain(orc, tmp_path):
+    world, steps = 2, 3
+    port = 29500 + (os.getpid() % 2000) + 23
+    mp.spawn(_mw_worker, args=(world, port, steps, str(tmp_path)), nprocs=world, join=True)
+    ny = LOCAL[1]
+    p = prm.khi_params(grid=(LOCAL[0], ny * world, LOCAL[2]), **MW)
+    o, e, i = util.khi_ic(orc, p)
+    _kick(p, e)
+    _kick(p, i)
+    E, B, J = o.field(), o.field(), o.field()
+    sps = [e, i]
+    for _ in range(steps):
+        o.step_open(E, B, J, sps)
+    g = p.guard_cells
+    for F in (E, B):  # shift down by one local domain; the entering slab is empty
+        F[:, :, : F.shape[2] - ny, :] = F[:, :, ny:, :].copy()
+        F[:, :, g[1] + ny * (world - 1):, :] = 0.0
+    p_top = prm.khi_params(grid=LOCAL, devices=(1, world, 1), rank_pos=(0, world - 1, 0), **MW)
+    for sp, new in zip(sps, _new_slab(orc, p_top)):
+        n = p.grid
+        cx, cy, cz = sp["cell"] % n[0], (sp["cell"] // n[0]) % n[1], sp["cell"] // (n[0] * n[1])
+        keep = cy >= ny
+        lc = new["cell"]
+        lx, ly, lz = lc % LOCAL[0], (lc // LOCAL[0]) % LOCAL[1], lc // (LOCAL[0] * LOCAL[1])
+        gnew = (lx + n[0] * ((ly + ny * (world - 1)) + n[1] * lz)).astype(np.int32)
+        gold = (cx + n[0] * ((cy - ny) + n[1] * cz)).astype(np.int32)[keep]
+        sp["pos"] = np.ascontiguousarray(np.concatenate([sp["pos"][:, keep], new["pos"]], axis=1))
+        sp["mom"] = np.ascontiguousarray(np.concatenate([sp["mom"][:, keep], new["mom"]], axis=1))
+        sp["w"] = np.ascontiguousarray(np.concatenate([sp["w"][keep], new["w"]]))
+        sp["cell"] = np.ascontiguousarray(np.concatenate([gold, gnew]))
+    for _ in range(steps):
+        o.step_open(E, B, J, sps)
+    r = {int(d["pos"]): d for d in (np.load(os.path.join(str(tmp_path), "mw%d.npz" % k)) for k in range(world))}
+    Eg = np.concatenate([r[0]["E"], r[1]["E"]], axis=2)
+    Bg = np.concatenate([r[0]["B"], r[1]["B"]], axis=2)
+    _, escale = util.khi_scales(p, 1)
+    assert np.abs(Eg - o.interior(E)).max() / escale < 1e-5
+    assert np.abs(Bg - o.interior(B)).max() / escale < 1e-5
+    assert int(r[0]["ne"]) + int(r[1]["ne"]) == sps[0]["w"].shape[0]
+    a, b = np.sort(np.concatenate([r[0]["ew"], r[1]["ew"]])), np.sort(sps[0]["mom"][0])
+    assert np.abs(a - b).max() / np.abs(b).max() < 1e-6
