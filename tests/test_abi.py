@@ -112,3 +112,23 @@ def test_moving_window_schedule():
     for (G, L, dy, cdt, mp) in ((64, 16, 1.0, 0.5, 0.5), (2048, 256, 1.7417, 1.0, 0.9), (96, 32, 0.8, 0.45, 0.0)):
         for st in range(0, 3000, 7):
             assert picstep.moving_window_info(G, L, dy, cdt, mp, st) == ref(st, G, L, dy, cdt, mp)
+
+
+def test_params_struct_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of `picstep_params` (picongpu_b200/picstep.py) has the size and field offsets the C compiler
+    gives the struct in include/picstep.h (a plain C translation unit must be able to include the header)."""
+    import subprocess
+
+    fields = [f[0] for f in picstep.Params._fields_]
+    src = tmp_path / "layout.c"
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "picstep.h"', "int main(void){",
+             'printf("%zu\\n", sizeof(picstep_params));']
+    lines += ['printf("%%zu\\n", offsetof(picstep_params, %s));' % f for f in fields]
+    lines += ["return 0;}"]
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == C.sizeof(picstep.Params)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(picstep.Params, f).offset == off, f
