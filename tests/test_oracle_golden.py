@@ -382,3 +382,66 @@ def test_pusher_phase_lag_scales_with_dt_squared(orc, pusher):
     x = np.log2(lags[1:] / lags[:-1])
     assert abs(x.mean() - 2.0) <= 0.1, x
     assert x.std() <= 0.05, x
+
+
+# ---- property tests (hypothesis): invariants the reference's unit tests state only for single cases -----------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.tuples(*[st.floats(min_value=-0.9990234375, max_value=1.9990234375, width=32) for _ in range(3)]), st.integers(min_value=0, max_value=255))
+def test_move_particle_invariants(newpos, cellidx):
+    """For every new position within one cell of the old cell: the wrapped position stays in [0, 1), the cell index in
+    the supercell, the move is exactly the integer cell shift, and multiMask encodes which supercell faces were crossed
+    (MoveParticle.hpp:48-160)."""
+    from oracle import picoracle as orc
+
+    pos, cell, mask = move(orc, list(newpos), cellidx)
+    assert ((pos >= 0.0) & (pos < 1.0)).all() and 0 <= cell < 256
+    old = [cellidx % 8, (cellidx // 8) % 8, cellidx // 64]
+    new = [cell % 8, (cell // 8) % 8, cell // 64]
+    code = mask - 1
+    for d, (o, n, ext) in enumerate(zip(old, new, (8, 8, 4))):
+        shift = int(np.floor(np.float32(newpos[d]))) if not (-2.0**-24 < newpos[d] < 0) else 0
+        # position and cell together describe the same point (up to the fp32 rounding of the +-0.5 shift trick)
+        assert abs((float(pos[d]) + shift) - float(np.float32(newpos[d]))) <= 2e-7
+        assert n == (o + shift) % ext
+        digit = (code // 3**d) % 3
+        crossed = 0 if 0 <= o + shift < ext else (1 if o + shift >= ext else 2)
+        assert digit == crossed
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(min_value=1, max_value=4), st.integers(min_value=0, max_value=1),
+       st.tuples(*[st.floats(min_value=0.0, max_value=0.9990234375, width=32) for _ in range(3)]),
+       st.tuples(*[st.floats(min_value=-0.875, max_value=0.875, width=32) for _ in range(3)]))
+def test_deposition_continuity_property(shape, current, pos, vel_frac):
+    """Any trajectory shorter than one cell per axis: div J = -d(rho)/dt to round-off for every shape and both
+    current solvers (the Esirkepov / EmZ schemes are charge conserving by construction)."""
+    from oracle import picoracle as orc
+
+    p = prm.khi_params(grid=(16, 16, 8), shape=shape, current_solver=current)
+    o = orc.Oracle(p)
+    J = o.field()
+    cellc = np.array([8, 8, 4], np.int32)
+    vel = (np.array(vel_frac, np.float32) * np.array(p.cell_size, np.float32) / np.float32(p.dt)).astype(np.float32)
+    q = np.float32(1.0)
+    o.L.orc_deposit_one(C.byref(o.p), J, cellc, np.array(pos, np.float32), vel, q)
+    g = p.guard_cells
+    cs = np.array(p.cell_size, np.float64)
+    div = ((J[0] - np.roll(J[0], 1, 2)) / cs[0] + (J[1] - np.roll(J[1], 1, 1)) / cs[1] + (J[2] - np.roll(J[2], 1, 0)) / cs[2]).astype(np.float64)
+    # charge density before / after with the same assignment function
+    rho = []
+    for shift in (1.0, 0.0):
+        pp = np.array(pos, np.float64) - shift * np.array(vel_frac, np.float64)
+        cc = cellc.astype(np.float64) + np.floor(pp)
+        pp = pp - np.floor(pp)
+        r3 = np.zeros((3,) + J.shape[1:], np.float32)
+        cell_lin = np.array([int(cc[0]) + 16 * (int(cc[1]) + 16 * int(cc[2]))], np.int32)
+        o.charge_density(1.0, r3[0], np.ascontiguousarray(pp.astype(np.float32)[:, None]), np.array([1.0 / float(p.base_charge)], np.float32), cell_lin)
+        rho.append(r3[0].astype(np.float64))
+    drho = (rho[1] - rho[0]) / float(p.dt)
+    # relative to the larger of the actual change and the fp32 resolution of one particle's charge density per step
+    unit = 1.0 / (float(np.prod(cs)) * float(p.dt))
+    scale = max(np.abs(drho).max(), 1e-3 * unit)
+    assert np.abs(div + drho).max() / scale < 5e-5
