@@ -14,17 +14,23 @@
 //
 // One CTA (8 warps) per supercell; warp w owns the 32 consecutive cells [32w, 32w+32) of the supercell, i.e. a
 // contiguous piece of the frame run.  It walks that piece in chunks of 32 particles, regardless of cell borders:
-//   phase 1 (lane = particle): [FUSED: interpolate E,B from the shared tile, Boris/Vay push, move, emit the re-sort
-//     key] then the 1-D assignment arrays of start and end point (same arithmetic as Esirkepov.hpp:84-103) are
-//     turned into a 60-word record on the window [-1,2] around the anchor cell: per axis {S0,DS}[4],
-//     {P,Q}[4] = {S0+DS/2, S0/2+DS/3}[4] and C[3] = scaled prefix sums of DS (the accumulated_J recursion of
-//     Esirkepov.hpp:223-236, factored out: J_k = C_k * transverse weight).
+//   prologue: [FUSED] the E and the B tile of the supercell arrive by TMA (one 4-D box per field, tma.cuh) while
+//     the CTA clears its private J tiles.
+//   phase 1 (lane = particle): [FUSED: interpolate E,B from the shared tile, Boris/Vay/Higuera-Cary push, move,
+//     emit the re-sort key and rank] then the 1-D assignment arrays of start and end point (same arithmetic as
+//     Esirkepov.hpp:84-103) are turned into a record on the window [-1,2] around the anchor cell: per axis
+//     {S0,DS}[4], [TSC, CIC, NGP: {P,Q}[4] = {S0+DS/2, S0/2+DS/3}[4]; PQS forms them in phase 2 so that two CTAs
+//     still fit an SM] and C[3] = scaled prefix sums of DS (the accumulated_J recursion of Esirkepov.hpp:223-236,
+//     factored out: J_k = C_k * transverse weight).
 //   phase 2 (lane = (component, a-half, b-half), two records per pass): t(a,b) = S0_i(a) P_j(b) + DS_i(a) Q_j(b),
-//     acc(a,b,k) += C_k t(a,b).  When the cell changes the two record slots are combined with six SHFL and the
-//     144 window values are added to the warp-private tile.
-// The eight private tiles are summed and flushed once per supercell with red.global.add.f32.
-// Trajectories that do not fit the narrow window (more than half a cell per step for odd supports, any cell
-// crossing for PQS) are deposited by their own thread with global atomics, in the reference's loop order.
+//     acc(a,b,k) += C_k t(a,b) with FFMA2 and broadcast scalar operands.  When the cell changes the two record
+//     slots are combined with six SHFL and the 144 window values are added to the warp-private tile.
+//   epilogue: the eight private tiles are summed row by row and flushed once per supercell with red.global.add.f32.
+// Trajectories that do not fit the narrow window (more than half a cell per step for odd supports) are deposited by
+// their own thread with global atomics, in the reference's loop order; a PQS particle that crosses a cell on one
+// axis keeps the record and sends only the plane outside the window through global atomics.
+// SOLVER = 1 is EmZ (EmZ.hpp:66-155): the trajectory is split at the relay point, each on-support segment is one
+// record, the second segments are a second round of phase 2 over the same chunk.
 // Anchor cell: the particle's cell (stand-alone deposit after the re-sort) or, FUSED, the cell it started in.
 #include "common.cuh"
 #include "esirkepov.cuh"
