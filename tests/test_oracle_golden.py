@@ -388,7 +388,7 @@ def test_pusher_phase_lag_scales_with_dt_squared(orc, pusher):
 from hypothesis import given, settings, strategies as st  # noqa: E402
 
 
-@settings(max_examples=300, deadline=None, derandomize=True)
+@settings(max_examples=300, deadline=None, derandomize=True, database=None)
 @given(st.tuples(*[st.floats(min_value=-0.9990234375, max_value=1.9990234375, width=32) for _ in range(3)]), st.integers(min_value=0, max_value=255))
 def test_move_particle_invariants(newpos, cellidx):
     """For every new position within one cell of the old cell: the wrapped position stays in [0, 1), the cell index in
@@ -411,7 +411,7 @@ def test_move_particle_invariants(newpos, cellidx):
         assert digit == crossed
 
 
-@settings(max_examples=100, deadline=None, derandomize=True)
+@settings(max_examples=200, deadline=None, derandomize=True, database=None)
 @given(st.integers(min_value=1, max_value=4), st.integers(min_value=0, max_value=1),
        st.tuples(*[st.floats(min_value=0.0, max_value=0.9990234375, width=32) for _ in range(3)]),
        st.tuples(*[st.floats(min_value=-0.875, max_value=0.875, width=32) for _ in range(3)]))
@@ -441,7 +441,7 @@ def test_deposition_continuity_property(shape, current, pos, vel_frac):
         o.charge_density(1.0, r3[0], np.ascontiguousarray(pp.astype(np.float32)[:, None]), np.array([1.0 / float(p.base_charge)], np.float32), cell_lin)
         rho.append(r3[0].astype(np.float64))
     drho = (rho[1] - rho[0]) / float(p.dt)
-    # relative to the larger of the actual change and the fp32 resolution of one particle's charge density per step
+    # relative to the actual change, plus the fp32 round-off of one particle's charge density per step (the terms of
+    # div J and of d(rho)/dt are of that size even when the net change is tiny)
     unit = 1.0 / (float(np.prod(cs)) * float(p.dt))
-    scale = max(np.abs(drho).max(), 1e-3 * unit)
-    assert np.abs(div + drho).max() / scale < 5e-5
+    assert np.abs(div + drho).max() <= 5e-5 * np.abs(drho).max() + 5e-7 * unit
