@@ -105,11 +105,21 @@ def variant_kwargs():
 # -------------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm restated (oracle/picoracle.cpp), OpenMP over all host cores
 # -------------------------------------------------------------------------------------------------------------------
+def host_cores():
+    """Cores this process may use (cgroup / affinity aware), never the OMP_NUM_THREADS=1 torchrun exports."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_rate(steps, warmup, grid=(64, 64, 64)):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import util
     from oracle import picoracle
 
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every worker: set the team size explicitly
+    picoracle.lib().orc_set_num_threads(host_cores())
     p = prm.khi_params(grid=grid, **variant_kwargs())
     o, e, i = util.khi_ic(picoracle, p)
     E, B, J = o.field(), o.field(), o.field()
@@ -124,13 +134,16 @@ def cpu_oracle_rate(steps, warmup, grid=(64, 64, 64)):
 
 
 def run_reference(args):
+    """The reference's CPU path of the same step (OpenMP restatement, all host cores).  The metric is a RATE of
+    macro-particle updates, so the bounded 64^3 sample is comparable with the 256^3-per-GPU GPU arm; the host of an
+    N-GPU box is ONE CPU arm whatever N is, so the line is n_gpus independent and says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     steps = max(1, min(args.steps, 20))
     warm = max(1, min(args.warmup, 3))
     rate, ms, cores, npart = cpu_oracle_rate(steps, warm)
-    sample = "KelvinHelmholtz 64x64x64, 25+25 ppc (%d macro particles), %d timed steps of the restated reference step" % (npart, steps)
+    sample = "KelvinHelmholtz 64x64x64, 25+25 ppc (%d macro particles), %d timed steps of the restated reference step on %d host threads" % (npart, steps, cores)
     line = {
         "impl": "reference",
         "metric": "macro_particle_updates_per_s",
@@ -145,7 +158,8 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.grid, args.ppc, args.gpus), "sample": sample},
+        "config": {"workload": workload_name(args.grid, args.ppc, args.gpus), "sample": sample,
+                   "n_gpus_independent": "the whole host (all %d cores) is one CPU arm for every N; the value does not grow with --gpus" % cores},
         "cpu_baseline": {"value": rate, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "reference binary not buildable here (needs Boost+MPI); OpenMP restatement of the same arithmetic"},
         "e2e": {"value": rate, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -158,6 +172,75 @@ def run_reference(args):
 # -------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------------------------
+def multi_gpu_parity_check(world, rank, local, dev):
+    """N-rank CUDA step against the single-domain oracle, before the timed region (the oracle as CHECKER only):
+    KHI 16 x 16*N x 8 global, slabs in y, 6 steps, particles kicked in y/z so they cross the rank boundaries
+    (pack / NCCL send-recv / append kernels, E/B/J guard exchange).  Returns the dict stored in checks."""
+    import torch
+    import torch.distributed as dist
+
+    from picongpu_b200 import picstep
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    from oracle import picoracle
+    from test_multirank_cpu import _kick
+
+    steps, local_grid = 6, (16, 16, 8)
+    picoracle.lib().orc_set_num_threads(2 if world > 1 else host_cores())
+    p = prm.khi_params(grid=local_grid, devices=(1, world, 1), rank_pos=(0, rank, 0))
+    o, e, i = util.khi_ic(picoracle, p)
+    _kick(p, e)
+    _kick(p, i)
+    sim = picstep.Simulation(p, device=local, exact=False)
+    if world > 1:
+        uid = sim.comm_unique_id() if rank == 0 else bytes(128)
+        t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        sim.comm_init(bytes(t.cpu().tolist()), rank, world)
+    for name, sp in (("e", e), ("i", i)):
+        sim.upload_particles(name, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+    n0 = [sim.particle_count("e"), sim.particle_count("i")]
+    sim.step(steps)
+    sim.sync()
+    n1 = [sim.particle_count("e"), sim.particle_count("i")]
+    mine = torch.from_numpy(np.stack([o.interior(sim.download_field(picstep.FIELD_E)), o.interior(sim.download_field(picstep.FIELD_B))])).to(dev)
+    cnt = torch.tensor(n0 + n1, device=dev, dtype=torch.int64)
+    sim.close()
+    if world > 1:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        cnts = [torch.empty_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+    else:
+        parts, cnts = [mine], [cnt]
+    if rank != 0:
+        return None
+    G = np.concatenate([t.cpu().numpy() for t in parts], axis=3)  # [E|B][3][z][y*N][x]
+    cn = np.stack([t.cpu().numpy() for t in cnts])
+    pg = prm.khi_params(grid=(local_grid[0], local_grid[1] * world, local_grid[2]))
+    og, eg, ig = util.khi_ic(picoracle, pg)
+    _kick(pg, eg)
+    _kick(pg, ig)
+    E, B, J = og.field(), og.field(), og.field()
+    for _ in range(steps):
+        og.step(E, B, J, [eg, ig])
+    _, escale = util.khi_scales(pg, 1)
+    # per-rank particle counts of the oracle's final state
+    ny = local_grid[1]
+    ref_cnt = []
+    for sp in (eg, ig):
+        cy = (sp["cell"] // pg.grid[0]) % pg.grid[1]
+        ref_cnt.append(np.bincount(cy // ny, minlength=world))
+    counts_equal = bool(np.array_equal(cn[:, 2], ref_cnt[0]) and np.array_equal(cn[:, 3], ref_cnt[1]))
+    migrated = int(np.abs(cn[:, 2] - cn[:, 0]).sum() + np.abs(cn[:, 3] - cn[:, 1]).sum())
+    return {"workload": "KHI 16x%dx8 global on %d rank(s), %d steps, kicked particles, production build vs single-domain oracle" % (ny * world, world, steps),
+            "dE": float(np.abs(G[0] - og.interior(E)).max() / escale), "dB": float(np.abs(G[1] - og.interior(B)).max() / escale),
+            "scale": "per-species drive field of one step (util.khi_scales)", "counts_equal": counts_equal,
+            "count_mismatch": int(np.abs(cn[:, 2] - ref_cnt[0]).sum() + np.abs(cn[:, 3] - ref_cnt[1]).sum()),
+            "migrated": migrated, "particles": int(cn[:, 2:].sum())}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -183,6 +266,12 @@ def run_ours(args):
         except Exception:
             pass
 
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = multi_gpu_parity_check(world, rank, local, dev)
+        except Exception as ex:  # pragma: no cover
+            parity = {"error": str(ex)[:300]}
     grid = tuple(args.grid)
     if args.scaling == "strong":
         if grid[1] % (8 * world) or grid[1] // world < 16:
@@ -242,6 +331,7 @@ def run_ours(args):
 
     # size independent properties at the benchmark size: particle conservation (periodic), Gauss residual at round-off
     checks = {"particles_conserved": bool(abs(npart_total - npart * world) < 0.5)}
+    checks["multi_gpu_vs_oracle"] = parity
     try:
         gr = sim.gauss_residual()
         checks["gauss_residual_over_cell_charge"] = gr / (25.0 * abs(p.base_charge) * p.typical_num_particles_per_macro)
@@ -406,9 +496,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, nargs=3, default=[256, 256, 256], help="cells per GPU")
     ap.add_argument("--ppc", type=int, default=25, help="macro particles per cell and species")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank CUDA-vs-oracle check before the timed region")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --grid is the grid per GPU (default, what the driver runs); strong: --grid is the GLOBAL grid, split in y over the GPUs")
     # other BASELINE.json configurations are the same kernels with other template arguments (defaults = the headline)

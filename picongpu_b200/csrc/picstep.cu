@@ -24,16 +24,16 @@ namespace picstep
     bool runKernelSupports(int, int);
     cudaError_t launchDepositRun(int, int, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
     cudaError_t launchPushDeposit(int, int, int, DevParams const&, SpeciesDev const&, SpeciesDev const&, uint32_t const*, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, TileMaps const&, cudaStream_t);
-    cudaError_t launchInvertRanked(uint32_t const*, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t const*, uint32_t*, uint16_t*, cudaStream_t);
+    cudaError_t launchInvertRanked(uint32_t const*, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t const*, uint32_t*, uint16_t*, uint32_t, cudaStream_t);
     cudaError_t launchAppendRecords(MigRecord const*, uint32_t, uint32_t const*, uint32_t, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, uint32_t*, int*, cudaStream_t);
     cudaError_t launchGatherPerm(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t, cudaStream_t);
     cudaError_t launchScan(uint32_t const*, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, int, uint32_t*, uint32_t, int*, cudaStream_t);
     cudaError_t launchScatterRanked(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t const*, cudaStream_t);
     cudaError_t launchScatterRecordsBack(MigRecord const*, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, cudaStream_t);
     cudaError_t launchClearRecordCounts(MigRecord const*, uint32_t, uint32_t*, cudaStream_t);
-    cudaError_t launchScatter(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t*, cudaStream_t);
+    cudaError_t launchScatter(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t*, uint32_t, cudaStream_t);
     cudaError_t launchCountRecords(MigRecord const*, uint32_t, uint32_t*, cudaStream_t);
-    cudaError_t launchScatterRecords(MigRecord const*, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, cudaStream_t);
+    cudaError_t launchScatterRecords(MigRecord const*, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, uint32_t, cudaStream_t);
     cudaError_t launchPackLeavers(DevParams const&, SpeciesDev, uint32_t const*, uint32_t const*, MigRecord*, MigRecord*, uint32_t*, uint32_t, int*, cudaStream_t);
     cudaError_t launchKeysFromCells(DevParams const&, int32_t const*, uint32_t, uint32_t*, uint32_t*, int*, cudaStream_t);
     cudaError_t launchCellsFromRuns(DevParams const&, uint16_t const*, uint32_t const*, int32_t*, cudaStream_t);
@@ -107,6 +107,8 @@ struct picstep_ctx
     // species and the field update (they are bound by different units: HBM vs. shared memory / issue)
     cudaStream_t side = nullptr;
     cudaEvent_t evFused = nullptr;
+    cudaEvent_t evFlags = nullptr; // completion of the asynchronous error-flag readback (peekFlags)
+    bool flagsPending = false;
     std::vector<cudaEvent_t> evMig;
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -274,6 +276,50 @@ namespace
         return PICSTEP_OK;
     }
 
+    // Grow the per-particle arrays of a species to newCap slots, keeping their contents (the reference grows its frame
+    // heap through mallocMC, ParticlesBox.hpp:97-124; here a rank whose plasma gets denser than its first upload --
+    // a density front entering an initially sparse slab -- re-allocates before the re-sort would overflow).
+    int growSpeciesBuffers(picstep_ctx* c, SpeciesHost& s, int64_t newCap)
+    {
+        if(newCap <= s.capacity)
+            return PICSTEP_OK;
+        if(newCap >= (int64_t(1) << 32) - 1)
+            return fail(c, PICSTEP_ERR_CAPACITY, "species capacity must be < 2^32 particles per rank");
+        int64_t const oldCap = s.capacity;
+        std::vector<void*> oldRaw;
+        oldRaw.swap(s.raw);
+        auto regrow = [&](auto** arr) -> int
+        {
+            auto* old = *arr;
+            if(int rc = allocSkewed(c, s, arr, newCap))
+                return rc;
+            if(old && oldCap)
+                CU(c, cudaMemcpyAsync(*arr, old, sizeof(**arr) * size_t(oldCap), cudaMemcpyDeviceToDevice, c->stream));
+            return PICSTEP_OK;
+        };
+        int rc = PICSTEP_OK;
+        for(int b = 0; b < 2 && !rc; ++b)
+        {
+            for(int k = 0; k < 7 && !rc; ++k)
+                rc = regrow(&s.attr[b][k]);
+            if(!rc)
+                rc = regrow(&s.cell[b]);
+        }
+        if(!rc)
+            rc = regrow(&s.key);
+        if(!rc)
+            rc = regrow(&s.rank);
+        if(!rc)
+            rc = regrow(&s.inv);
+        cudaStreamSynchronize(c->stream);
+        for(void* p : oldRaw)
+            cudaFree(p);
+        if(rc)
+            return rc;
+        s.capacity = newCap;
+        return PICSTEP_OK;
+    }
+
     // Lehe coefficients in fp64 -> fp32 (Lehe/Derivative.hpp:94-111); betas in fp32 (:134-137)
     void computeLehe(picstep_params const& p, LeheCoeffs& L)
     {
@@ -428,7 +474,9 @@ namespace
     {
         CU(c, cudaMemcpyAsync(c->hostPinned, c->flags, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
-        int const* f = reinterpret_cast<int const*>(c->hostPinned);
+        int const f[3] = {int(c->hostPinned[0]), int(c->hostPinned[1]), int(c->hostPinned[2])};
+        if(f[0] | f[1] | f[2]) // report once: a later valid upload / step must not see a stale error
+            CU(c, cudaMemsetAsync(c->flags, 0, sizeof(int) * 3, c->stream));
         if(f[0])
             return fail(c, PICSTEP_ERR_CAPACITY, "particle capacity exceeded during re-sort");
         if(f[1])
@@ -436,6 +484,27 @@ namespace
         if(f[2])
             return fail(c, PICSTEP_ERR_CAPACITY, "migration record buffer overflow");
         return PICSTEP_OK;
+    }
+
+    // non-blocking look at the error flags: the copy of the previous call has landed long ago (same stream, and the
+    // host has queued n steps since); queues the next copy
+    int peekFlags(picstep_ctx* c)
+    {
+        int rc = PICSTEP_OK;
+        if(c->flagsPending && cudaEventQuery(c->evFlags) == cudaSuccess)
+        {
+            c->flagsPending = false;
+            uint32_t const* f = c->hostPinned + 8;
+            if(f[0] | f[1] | f[2])
+                return checkFlags(c); // synchronises, reports and clears
+        }
+        if(!c->flagsPending)
+        {
+            CU(c, cudaMemcpyAsync(c->hostPinned + 8, c->flags, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaEventRecord(c->evFlags, c->stream));
+            c->flagsPending = true;
+        }
+        return rc;
     }
 
     // Everything that depends on where this rank sits in the device grid: neighbour ranks, which faces are outer
@@ -505,7 +574,7 @@ namespace
             // slots were assigned by the fused kernel, which also wrote the pushed attributes into buffer nxt in its
             // processing order: only the permutation (inv) and the new localCellIdx are materialised (lazy re-sort)
             size_t const cntBytes = sizeof(uint32_t) * size_t(nscTot) * SCVOL;
-            KL(c, 1, launchInvertRanked(s.key, s.rank, s.nDev + s.cur, s.nUpper, s.cellOff[nxt], s.stayCnt, s.inv, s.cell[nxt], c->stream));
+            KL(c, 1, launchInvertRanked(s.key, s.rank, s.nDev + s.cur, s.nUpper, s.cellOff[nxt], s.stayCnt, s.inv, s.cell[nxt], uint32_t(s.capacity), c->stream));
             CU(c, cudaMemsetAsync(s.cellCnt, 0, cntBytes, c->stream));
             CU(c, cudaMemsetAsync(s.stayCnt, 0, cntBytes, c->stream));
             c->launches += 2;
@@ -522,11 +591,11 @@ namespace
         }
         else
         {
-            KL(c, 1, launchScatter(devOf(c, s, s.cur), devOf(c, s, nxt), s.key, s.nDev + s.cur, s.nUpper, s.cellOff[nxt], s.cellCnt, c->stream));
+            KL(c, 1, launchScatter(devOf(c, s, s.cur), devOf(c, s, nxt), s.key, s.nDev + s.cur, s.nUpper, s.cellOff[nxt], s.cellCnt, uint32_t(s.capacity), c->stream));
             if(nRecLo)
-                KL(c, 1, launchScatterRecords(s.recvLo, nRecLo, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+                KL(c, 1, launchScatterRecords(s.recvLo, nRecLo, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, uint32_t(s.capacity), c->stream));
             if(nRecHi)
-                KL(c, 1, launchScatterRecords(s.recvHi, nRecHi, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, c->stream));
+                KL(c, 1, launchScatterRecords(s.recvHi, nRecHi, devOf(c, s, nxt), s.cellOff[nxt], s.cellCnt, uint32_t(s.capacity), c->stream));
         }
         s.cur = nxt;
         s.nUpper = uint32_t(std::min<int64_t>(s.capacity, int64_t(s.nUpper) + nRecLo + nRecHi));
@@ -700,6 +769,7 @@ extern "C"
         CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CUC(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
         CUC(cudaEventCreateWithFlags(&c->evFused, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&c->evFlags, cudaEventDisableTiming));
         int tbox[3], tlo = 0;
         tileBox(p->shape, tbox, &tlo);
         c->tileMaps.lead = tlo & 3;
@@ -727,7 +797,7 @@ extern "C"
         CUC(cudaMalloc(&c->redBuf, sizeof(double) * 4));
         CUC(cudaMalloc(&c->flags, sizeof(int) * 4));
         CUC(cudaMemsetAsync(c->flags, 0, sizeof(int) * 4, c->stream));
-        CUC(cudaMallocHost(&c->hostPinned, sizeof(double) * 8));
+        CUC(cudaMallocHost(&c->hostPinned, sizeof(double) * 8)); // 16 words: [0..7] readbacks, [8..10] peekFlags
         if(split >= 0)
         {
             long long const plane = (long long) P.N[(split == 0) ? 1 : 0] * P.N[(split == 2) ? 1 : 2] * 3;
@@ -786,6 +856,8 @@ extern "C"
             cudaStreamDestroy(c->side);
         if(c->evFused)
             cudaEventDestroy(c->evFused);
+        if(c->evFlags)
+            cudaEventDestroy(c->evFlags);
         for(auto e : c->evMig)
             cudaEventDestroy(e);
         delete c;
@@ -818,6 +890,10 @@ extern "C"
         CU(c, cudaMemsetAsync(s.nDev, 0, sizeof(uint32_t) * 2, c->stream));
         CU(c, cudaMalloc(&s.sendCnt, sizeof(uint32_t) * 2));
         CU(c, cudaMemsetAsync(s.sendCnt, 0, sizeof(uint32_t) * 2, c->stream));
+        // A rank of a decomposed run always takes part in the count / payload exchange of the migration (its neighbours
+        // post their send / recv regardless), also when it starts empty: it gets a minimal buffer instead of none.
+        if(capacity == 0 && c->P.split_axis >= 0)
+            capacity = 4096;
         if(capacity > 0)
         {
             int const rc = allocSpeciesBuffers(c, s, capacity);
@@ -1097,15 +1173,33 @@ extern "C"
             if(rc)
                 return PICSTEP_ERR_COMM;
             CU(c, cudaMemcpyAsync(c->hostPinned + 2, s.scSum, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaMemcpyAsync(c->hostPinned + 4, s.nDev + s.cur, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             CU(c, cudaStreamSynchronize(c->stream));
-            uint32_t const nSendLo = c->rankLo >= 0 ? c->hostPinned[0] : 0u, nSendHi = c->rankHi >= 0 ? c->hostPinned[1] : 0u;
+            uint32_t nSendLo = c->rankLo >= 0 ? c->hostPinned[0] : 0u, nSendHi = c->rankHi >= 0 ? c->hostPinned[1] : 0u;
             nRecLo = c->rankLo >= 0 ? c->hostPinned[2] : 0u;
             nRecHi = c->rankHi >= 0 ? c->hostPinned[3] : 0u;
-            if(nSendLo > s.capRec || nSendHi > s.capRec || nRecLo > s.capRec || nRecHi > s.capRec)
-                return fail(c, PICSTEP_ERR_CAPACITY, "migration record buffer overflow");
+            // A buffer overflow on either side must not leave the neighbour blocked in its payload exchange: the
+            // exchange is still posted, with the counts clamped on BOTH sides the same way, and reported afterwards.
+            bool const overflow = nSendLo > s.capRec || nSendHi > s.capRec || nRecLo > s.capRec || nRecHi > s.capRec;
+            nSendLo = std::min(nSendLo, s.capRec);
+            nSendHi = std::min(nSendHi, s.capRec);
+            nRecLo = std::min(nRecLo, s.capRec);
+            nRecHi = std::min(nRecHi, s.capRec);
             rc = commSendRecv(c->comm, s.sendLo, sizeof(MigRecord) * nSendLo, s.recvLo, sizeof(MigRecord) * nRecLo, c->rankLo, s.sendHi, sizeof(MigRecord) * nSendHi, s.recvHi, sizeof(MigRecord) * nRecHi, c->rankHi, c->stream, c->err);
             if(rc)
                 return PICSTEP_ERR_COMM;
+            if(overflow)
+                return fail(c, PICSTEP_ERR_CAPACITY, "migration record buffer overflow");
+            // the exact particle count is on the host now: it bounds the launches of the re-sort (instead of an
+            // ever growing upper bound) and tells whether the arrivals still fit
+            uint32_t const nNow = c->hostPinned[4];
+            s.nUpper = nNow;
+            if(int64_t(nNow) + nRecLo + nRecHi > s.capacity)
+            {
+                int64_t const want = int64_t(nNow) + nRecLo + nRecHi;
+                if(int grc = growSpeciesBuffers(c, s, want + want / 4 + 4096))
+                    return grc;
+            }
         }
         return resortSpecies(c, s, nRecLo, nRecHi);
     }
@@ -1368,13 +1462,21 @@ extern "C"
     {
         if(!c)
             return PICSTEP_ERR_INVALID;
-        return stepImpl(c, first, n, [](int) { return int(PICSTEP_OK); });
+        int const rc = stepImpl(c, first, n, [](int) { return int(PICSTEP_OK); });
+        // the device-side error flags (capacity, record overflow) are read without waiting for the steps: a flag that
+        // is already up is reported here, anything later by the next call or picstep_sync
+        return rc ? rc : peekFlags(c);
     }
 
     int picstep_step_host(picstep_ctx* c, uint32_t step, float* E, float* B, int32_t nSpecies, const int64_t* n, const float* const* pos, const float* const* mom, const float* const* w, const int32_t* const* cell, double* energies4)
     {
         if(!c || !E || !B || nSpecies != int(c->species.size()))
             return PICSTEP_ERR_INVALID;
+        if(nSpecies < 1 || !n || !pos || !mom || !w || !cell)
+            return fail(c, PICSTEP_ERR_INVALID, "picstep_step_host needs at least one species and its host arrays");
+        for(int s = 0; s < nSpecies; ++s)
+            if(n[s] < 0 || (n[s] > 0 && (!pos[s] || !mom[s] || !w[s] || !cell[s])))
+                return fail(c, PICSTEP_ERR_INVALID, "picstep_step_host: null particle array");
         CU(c, cudaSetDevice(c->device));
         size_t const fbytes = sizeof(float) * 3 * c->P.vol;
         CU(c, cudaMemcpyAsync(c->fieldMem[PICSTEP_FIELD_E], E, fbytes, cudaMemcpyHostToDevice, c->stream));

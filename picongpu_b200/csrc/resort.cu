@@ -140,7 +140,8 @@ namespace picstep
         uint32_t const* __restrict__ key,
         uint32_t const* __restrict__ nOld,
         uint32_t const* __restrict__ newOff,
-        uint32_t* __restrict__ cnt)
+        uint32_t* __restrict__ cnt,
+        uint32_t capacity)
     {
         uint32_t const n = *nOld;
         for(uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
@@ -151,7 +152,7 @@ namespace picstep
                 k = key[i];
             bool const valid = (i < n) && !(k & KEY_LEAVE);
             uint32_t const d = claimSlot(cnt, newOff, k, valid);
-            if(valid)
+            if(valid && d < capacity) // beyond the capacity: the scan has raised the overflow flag, nothing is written
             {
                 dst.pos[0][d] = src.pos[0][i];
                 dst.pos[1][d] = src.pos[1][i];
@@ -237,7 +238,8 @@ namespace picstep
         uint32_t const* __restrict__ newOff,
         uint32_t const* __restrict__ stayCnt,
         uint32_t* __restrict__ inv,
-        uint16_t* __restrict__ cellOut)
+        uint16_t* __restrict__ cellOut,
+        uint32_t capacity)
     {
         uint32_t const n = *nOld;
         for(uint32_t base = blockIdx.x * (256u * UNROLL); base < n; base += gridDim.x * (256u * UNROLL))
@@ -257,8 +259,11 @@ namespace picstep
                     uint32_t d = newOff[k[u]] + (r[u] & 0x7fffffffu);
                     if(r[u] >> 31)
                         d += stayCnt[k[u]];
-                    inv[d] = base + u * 256u + threadIdx.x;
-                    cellOut[d] = uint16_t(k[u] & (SCVOL - 1));
+                    if(d < capacity) // else: overflow flag already raised by the scan
+                    {
+                        inv[d] = base + u * 256u + threadIdx.x;
+                        cellOut[d] = uint16_t(k[u] & (SCVOL - 1));
+                    }
                 }
         }
     }
@@ -274,7 +279,7 @@ namespace picstep
             uint32_t const k = r.key & KEY_MASK;
             uint32_t const slot = newOff[k + 1] - 1u - atomicAdd(&cnt[k], 1u);
             uint32_t const d = first + i;
-            if(d >= capacity)
+            if(d >= capacity || slot >= capacity)
             {
                 *overflow = 1;
                 continue;
@@ -335,7 +340,7 @@ namespace picstep
     }
 
     // received migration records -> new runs (KernelInsertParticles, ParticlesBase.kernel:846-938)
-    __global__ void __launch_bounds__(256) scatterRecordsKernel(MigRecord const* __restrict__ rec, uint32_t nRec, SpeciesDev dst, uint32_t const* __restrict__ newOff, uint32_t* __restrict__ cnt)
+    __global__ void __launch_bounds__(256) scatterRecordsKernel(MigRecord const* __restrict__ rec, uint32_t nRec, SpeciesDev dst, uint32_t const* __restrict__ newOff, uint32_t* __restrict__ cnt, uint32_t capacity)
     {
         for(uint32_t base = blockIdx.x * blockDim.x; base < nRec; base += gridDim.x * blockDim.x)
         {
@@ -347,7 +352,7 @@ namespace picstep
             uint32_t const k = r.key & KEY_MASK;
             bool const valid = i < nRec;
             uint32_t const d = claimSlot(cnt, newOff, k, valid);
-            if(valid)
+            if(valid && d < capacity)
             {
                 dst.pos[0][d] = r.px;
                 dst.pos[1][d] = r.py;
@@ -501,9 +506,9 @@ namespace picstep
         return cudaGetLastError();
     }
 
-    cudaError_t launchScatter(SpeciesDev src, SpeciesDev dst, uint32_t const* key, uint32_t const* nOld, uint32_t nOldUpper, uint32_t const* newOff, uint32_t* cnt, cudaStream_t st)
+    cudaError_t launchScatter(SpeciesDev src, SpeciesDev dst, uint32_t const* key, uint32_t const* nOld, uint32_t nOldUpper, uint32_t const* newOff, uint32_t* cnt, uint32_t capacity, cudaStream_t st)
     {
-        scatterKernel<<<gridFor(nOldUpper), 256, 0, st>>>(src, dst, key, nOld, newOff, cnt);
+        scatterKernel<<<gridFor(nOldUpper), 256, 0, st>>>(src, dst, key, nOld, newOff, cnt, capacity);
         return cudaGetLastError();
     }
 
@@ -519,7 +524,7 @@ namespace picstep
         return cudaGetLastError();
     }
 
-    cudaError_t launchInvertRanked(uint32_t const* key, uint32_t const* rank, uint32_t const* nOld, uint32_t nOldUpper, uint32_t const* newOff, uint32_t const* stayCnt, uint32_t* inv, uint16_t* cellOut, cudaStream_t st)
+    cudaError_t launchInvertRanked(uint32_t const* key, uint32_t const* rank, uint32_t const* nOld, uint32_t nOldUpper, uint32_t const* newOff, uint32_t const* stayCnt, uint32_t* inv, uint16_t* cellOut, uint32_t capacity, cudaStream_t st)
     {
         constexpr int UNROLL = 4;
         long long blocks = (nOldUpper + 256ll * UNROLL - 1) / (256ll * UNROLL);
@@ -527,7 +532,7 @@ namespace picstep
             blocks = 1;
         if(blocks > 148 * 32)
             blocks = 148 * 32;
-        invertRankedKernel<UNROLL><<<int(blocks), 256, 0, st>>>(key, rank, nOld, newOff, stayCnt, inv, cellOut);
+        invertRankedKernel<UNROLL><<<int(blocks), 256, 0, st>>>(key, rank, nOld, newOff, stayCnt, inv, cellOut, capacity);
         return cudaGetLastError();
     }
 
@@ -569,11 +574,11 @@ namespace picstep
         return cudaGetLastError();
     }
 
-    cudaError_t launchScatterRecords(MigRecord const* rec, uint32_t nRec, SpeciesDev dst, uint32_t const* newOff, uint32_t* cnt, cudaStream_t st)
+    cudaError_t launchScatterRecords(MigRecord const* rec, uint32_t nRec, SpeciesDev dst, uint32_t const* newOff, uint32_t* cnt, uint32_t capacity, cudaStream_t st)
     {
         if(nRec == 0)
             return cudaSuccess;
-        scatterRecordsKernel<<<gridFor(nRec), 256, 0, st>>>(rec, nRec, dst, newOff, cnt);
+        scatterRecordsKernel<<<gridFor(nRec), 256, 0, st>>>(rec, nRec, dst, newOff, cnt, capacity);
         return cudaGetLastError();
     }
 

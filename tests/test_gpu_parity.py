@@ -490,21 +490,50 @@ def test_khi_100_steps_vs_oracle(orc, exact):
     s.close()
 
 
-def test_energy_conservation_1000_steps():
-    """Total (field + kinetic) energy of a small warm two-stream free KHI box stays within 1e-3 over 1000 steps and
-    matches between the two builds to 1e-4 (north_star: energies agree within 1e-4 after 1000 steps)."""
+def test_energy_conservation_1000_steps(orc):
+    """north_star gate: total field plus kinetic energy agrees with the reference implementation (the oracle, stepped
+    here from the same initial condition) within 1e-4 after 1000 steps, for both builds.  Energies as the reference's
+    plugins compute them: EnergyFields.x.cpp:198-233 (0.5*eps0*E^2 + 0.5/mue0*B^2 summed over the cells times the cell
+    volume) and EnergyParticles.x.cpp:100-131 + KinEnergy.hpp (per macro particle, summed in double)."""
     p = util.make_params((16, 16, 8))
-    tot = []
+    steps = 1000
+    o, e, i = util.khi_ic(orc, p)
+    sims = []
     for exact in (True, False):
         s = _sim(p, exact)
-        s.init_khi()
-        e0 = s.field_energy().sum() + sum(s.particle_energy(n)[0] for n in ("e", "i"))
-        s.step(1000)
-        e1 = s.field_energy().sum() + sum(s.particle_energy(n)[0] for n in ("e", "i"))
-        assert abs(e1 - e0) / e0 < 1e-3
-        tot.append(e1)
+        for name, sp in (("e", e), ("i", i)):
+            s.upload_particles(name, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+        sims.append(s)
+    E, B, J = o.field(), o.field(), o.field()
+
+    def oracle_energy():
+        return o.field_energy(E, B), o.particle_energy(1.0, e["mom"], e["w"])[0] + o.particle_energy(1836.152672, i["mom"], i["w"])[0]
+
+    f0, k0 = oracle_energy()
+    for s in sims:  # the same start on both sides
+        fg = s.field_energy()
+        kg = sum(s.particle_energy(n)[0] for n in ("e", "i"))
+        assert abs((fg.sum() + kg) - (f0.sum() + k0)) / (f0.sum() + k0) < 1e-6
+        s.step(steps)
+    for _ in range(steps):
+        o.step(E, B, J, [e, i])
+    f1, k1 = oracle_energy()
+    tot_o = f1.sum() + k1
+    assert abs(tot_o - (f0.sum() + k0)) / (f0.sum() + k0) < 1e-3  # the run itself conserves energy
+    for s, label in zip(sims, ("exact", "production")):
+        s.sync()
+        fg = s.field_energy()
+        kg = sum(s.particle_energy(n)[0] for n in ("e", "i"))
+        d_tot = abs((fg.sum() + kg) - tot_o) / tot_o
+        d_field = abs(fg.sum() - f1.sum()) / f1.sum()
+        d_kin = abs(kg - k1) / k1
+        print("1000 steps %-10s |dE_tot|/E_tot=%.3e  field energy %.3e  kinetic %.3e" % (label, d_tot, d_field, d_kin))
+        assert d_tot < 1e-4, "total energy differs from the oracle after 1000 steps"
+        assert d_kin < 1e-4
+        # the field energy is 2e-7 of the total in this start (thermal noise fields), chaotic at the particle level:
+        # its own relative agreement is looser than the north star asks of the total
+        assert d_field < 2e-2
         s.close()
-    assert abs(tot[0] - tot[1]) / tot[0] < 1e-4
 
 
 def test_device_khi_init_matches_oracle_generator(orc):
