@@ -12,7 +12,7 @@ HEADERS = ["common.cuh", "shapes.cuh", "pusher.cuh", "esirkepov.cuh", "f2.cuh", 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 VARIANTS = {
-    "libpicstep.so": [],
+    "libpicstep.so": ["-ftz=true"],  # denormals flushed: MUFU.RCP / RSQ / SQRT without the scaling fix-ups around them
     "libpicstep_exact.so": ["-DPICSTEP_EXACT", "-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
 }
 

@@ -49,25 +49,29 @@ namespace picstep
         static constexpr int NK = WN - 1;
         static constexpr int FR = Sh::SUPP + 1; // entries of the off-support assignment arrays
         static constexpr int NMAX0 = WN - Sh::SUPP; // largest window index of frame entry 0 in a narrow record
-        // record, per axis: {S0[0],S0[1],DS[0],DS[1]}, {S0[2],S0[3],DS[2],DS[3]}, [PQREC: {P[0],P[1],Q[0],Q[1]},
-        // {P[2],P[3],Q[2],Q[3]},] {C[0],C[1],C[2],0}; the 33rd record is all zero.  TSC keeps P = S0 + DS/2 and
-        // Q = S0/2 + DS/3 in the record (measured 0.2 % faster); PQS forms them in phase 2, which shrinks the records from
-        // 63 to 38 KB per CTA and lets two CTAs share an SM next to the larger E/B tile (122 -> 95.5 ms/step).
-        static constexpr bool PQREC = Sh::SUPP != WN;
-        static constexpr int COFF = PQREC ? 16 : 8, AXW = COFF + 4, RECW = 3 * AXW, NREC = 33;
+        // record, per axis: {S0[0],S0[1],DS[0],DS[1]}, {S0[2],S0[3],DS[2],DS[3]}, {C[0],C[1],C[2],0}; the 33rd record is
+        // all zero.  P = S0 + DS/2 and Q = S0/2 + DS/3 are formed in phase 2: the kernel is bound by the shared-memory
+        // data pipe (profiles/), and the compact record costs 1.1 instead of 1.9 wavefronts per particle to write.
+        // (Measured alternative, round 2: records that carry the transverse weights t(a,b) themselves, one record per
+        // pass on 24 lanes -- 4 % fewer instructions, but 5.0 instead of 3.0 wavefronts per particle to read: 26.0
+        // instead of 24.5 ms per launch.)
+        static constexpr int COFF = 8, AXW = COFF + 4, RECW = 3 * AXW, NREC = 33;
         static constexpr int WARPS = 8, CELLS_PER_WARP = SCVOL / WARPS; // 32 cells: 8 x, 4 y, 1 z
         static constexpr int PX = SCX + WN - 1, PY = SCY / 2 + WN - 1, PZ = 1 + WN - 1, PV = PX * PY * PZ;
+        // distance between the component planes of a private tile, padded: fewer bank conflicts of the per-cell flush
+        // (tools/microbench/flush_banks.py; the 24 lanes of the three components cannot be made conflict free)
+        static constexpr int PVC = PV + 4;
         static constexpr int TX = SCX + WN - 1, TY = SCY + WN - 1, TZ = SCZ + WN - 1, TV = TX * TY * TZ;
         static constexpr int EBW = Tile<SHAPE>::WORDS; // E/B tile words (FUSED): two 128-byte aligned TMA destinations
         static_assert(Sh::SUPP <= 4, "narrow window of 4 nodes needs a support of at most 4");
-        static_assert((3 * PV * WARPS) % 4 == 0 && RECW % 4 == 0, "records must stay 16-byte aligned");
+        static_assert((3 * PVC * WARPS) % 4 == 0 && RECW % 4 == 0, "records must stay 16-byte aligned");
     };
 
     template<int SHAPE, bool FUSED>
     constexpr size_t runSmemBytes()
     {
         using C = RunCfg<SHAPE>;
-        return sizeof(float) * ((FUSED ? C::EBW : 0) + C::WARPS * 3 * C::PV + C::WARPS * C::NREC * C::RECW);
+        return sizeof(float) * ((FUSED ? C::EBW : 0) + C::WARPS * 3 * C::PVC + C::WARPS * C::NREC * C::RECW);
     }
 
     template<int SHAPE, int PUSHER, bool FUSED, int SOLVER>
@@ -96,7 +100,7 @@ namespace picstep
         __shared__ uint64_t ebBar;
         float* const ebTile = smem;
         float* const tiles = smem + (FUSED ? C::EBW : 0);
-        float* const recs = tiles + C::WARPS * 3 * C::PV;
+        float* const recs = tiles + C::WARPS * 3 * C::PVC;
 
         int const sc = blockIdx.x;
         int const scx = sc % P.nsc[0], scy = (sc / P.nsc[0]) % P.nsc[1], scz = sc / (P.nsc[0] * P.nsc[1]);
@@ -104,7 +108,7 @@ namespace picstep
         if(scBeg == scEnd)
             return;
         int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        float* const myTile = tiles + warp * 3 * C::PV;
+        float* const myTile = tiles + warp * 3 * C::PVC;
         float* const myRecs = recs + warp * C::NREC * C::RECW;
 
         if constexpr(FUSED)
@@ -121,9 +125,9 @@ namespace picstep
             }
         }
         {
-            static_assert((C::WARPS * 3 * C::PV) % 4 == 0, "tiles are cleared with 16-byte stores");
+            static_assert((C::WARPS * 3 * C::PVC) % 4 == 0, "tiles are cleared with 16-byte stores");
             float4* const t4 = reinterpret_cast<float4*>(tiles);
-            for(int i = threadIdx.x; i < C::WARPS * 3 * C::PV / 4; i += blockDim.x)
+            for(int i = threadIdx.x; i < C::WARPS * 3 * C::PVC / 4; i += blockDim.x)
                 t4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             for(int i = lane; i < C::RECW; i += 32) // record 32 stays all zero
                 myRecs[32 * C::RECW + i] = 0.0f;
@@ -133,6 +137,14 @@ namespace picstep
             mbarWait(&ebBar, 0);
 
         float const rc2 = float(1.0 / double(P.c) / double(P.c));
+        // displacement in cells = v dt / cellSize: the exact build divides as the reference does (MoveParticle's caller,
+        // Esirkepov.hpp:84-90), the production build multiplies with the reciprocal of the (uniform) cell size
+#ifdef PICSTEP_EXACT
+#    define PS_DIV_CELL(a, d) ((a) / P.cell[d])
+#else
+        float const rcell[3] = {1.0f / P.cell[0], 1.0f / P.cell[1], 1.0f / P.cell[2]};
+#    define PS_DIV_CELL(a, d) ((a) * rcell[d])
+#endif
         float const vol = P.cell[0] * P.cell[1] * P.cell[2];
         float const* const tB = ebTile;
         float const* const tE = ebTile + T::HALF;
@@ -143,13 +155,13 @@ namespace picstep
         int const comp = p2active ? (g >> 2) : 0;
         int const ah = (g >> 1) & 1, bh = g & 1;
         int const ai = (comp + 1) % 3, aj = (comp + 2) % 3; // Jx: (i,j) = (y,z); Jy: (z,x); Jz: (x,y)
-        // a lane reads {S0,DS} of axis i at nodes 2ah,2ah+1, {P,Q} of axis j at nodes 2bh,2bh+1 and C of its component
+        // a lane reads {S0,DS} of axis i at nodes 2ah,2ah+1, {S0,DS} of axis j at nodes 2bh,2bh+1 and C of its component
         int const offSD = ai * C::AXW + 4 * ah;
-        int const offPQ = aj * C::AXW + (C::PQREC ? 8 : 0) + 4 * bh; // {P,Q} (or {S0,DS}: P, Q formed in the pass) of axis j
+        int const offPQ = aj * C::AXW + 4 * bh;
         int const offC = comp * C::AXW + C::COFF;
         auto strideOf = [](int a) { return a == 0 ? 1 : (a == 1 ? C::PX : C::PX * C::PY); };
         int const sC = strideOf(comp), sJ = strideOf(aj);
-        int const laneTile = comp * C::PV + (2 * ah + slot) * strideOf(ai) + 2 * bh * sJ;
+        int const laneTile = comp * C::PVC + (2 * ah + slot) * strideOf(ai) + 2 * bh * sJ;
 
         // accumulators of the lane's 2 x 2 x 3 nodes, packed over b: acc[a][k] = {J(a, b=0, k), J(a, b=1, k)}
         F2 acc[2][C::NK];
@@ -187,16 +199,36 @@ namespace picstep
                     acc[a][k] = F2(0.0f);
         };
 
+        // record from the assignment values of start (S0) and end point (S1) on the window, the factors f and the
+        // start value cm of the prefix sums (the node left of the window, SEMI only)
+        auto storeRecord = [&](float* rec, float const(&S0)[3][C::WN], float const(&S1)[3][C::WN], float const(&f)[3], float const(&cm)[3])
+        {
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+            {
+                float4* r4 = reinterpret_cast<float4*>(rec + d * C::AXW);
+                F2 DS[2];
+#pragma unroll
+                for(int j = 0; j < 2; ++j)
+                {
+                    F2 const s0p(S0[d][2 * j], S0[d][2 * j + 1]);
+                    DS[j] = F2(S1[d][2 * j], S1[d][2 * j + 1]) - s0p;
+                    r4[j] = make_float4(s0p.x, s0p.y, DS[j].x, DS[j].y);
+                }
+                float const c0 = cm[d] + DS[0].x, c1 = c0 + DS[0].y, c2 = c1 + DS[1].x;
+                r4[C::COFF / 4] = make_float4(c0 * f[d], c1 * f[d], c2 * f[d], 0.0f);
+            }
+        };
+
         uint32_t const pBeg = cellOff[sc * SCVOL + warp * C::CELLS_PER_WARP];
         uint32_t const pEnd = cellOff[sc * SCVOL + (warp + 1) * C::CELLS_PER_WARP];
 
         // EmZ: record of one on-support segment (start and end values on the same SUPP nodes at window offset o)
         [[maybe_unused]] auto emzRecord = [&](float* rec, F2 const(&t)[3][Sh::SUPP], int const(&o)[3], float const(&f)[3])
         {
+            float S0[3][C::WN], S1[3][C::WN];
 #pragma unroll
             for(int d = 0; d < 3; ++d)
-            {
-                float S0[C::WN], S1[C::WN];
 #pragma unroll
                 for(int n = 0; n < C::WN; ++n)
                 {
@@ -211,27 +243,11 @@ namespace picstep
                             v1 = (o[d] == m) ? t[d][sx].y : v1;
                         }
                     }
-                    S0[n] = v0;
-                    S1[n] = v1;
+                    S0[d][n] = v0;
+                    S1[d][n] = v1;
                 }
-                float4* r4 = reinterpret_cast<float4*>(rec + d * C::AXW);
-                F2 DS[2];
-#pragma unroll
-                for(int j = 0; j < 2; ++j)
-                {
-                    F2 const s0p(S0[2 * j], S0[2 * j + 1]);
-                    DS[j] = F2(S1[2 * j], S1[2 * j + 1]) - s0p;
-                    r4[j] = make_float4(s0p.x, s0p.y, DS[j].x, DS[j].y);
-                    if constexpr(C::PQREC)
-                    {
-                        F2 const Pp = fma2(DS[j], F2(0.5f), s0p);
-                        F2 const Qp = fma2(DS[j], F2(1.0f / 3.0f), s0p * F2(0.5f));
-                        r4[2 + j] = make_float4(Pp.x, Pp.y, Qp.x, Qp.y);
-                    }
-                }
-                float const c0 = DS[0].x, c1 = c0 + DS[0].y, c2 = c1 + DS[1].x;
-                r4[C::COFF / 4] = make_float4(c0 * f[d], c1 * f[d], c2 * f[d], 0.0f);
-            }
+            float const cm[3] = {0.0f, 0.0f, 0.0f};
+            storeRecord(rec, S0, S1, f, cm);
         };
 
         // The particle attributes of a chunk are loaded one chunk ahead: the loads are issued before phase 2 of the
@@ -296,6 +312,7 @@ namespace picstep
                 int dir[3] = {0, 0, 0};
                 bool deposit = true;
                 float vel[3];
+                [[maybe_unused]] float dpv[3] = {0.0f, 0.0f, 0.0f}; // FUSED: displacement of the move, in cells
                 if constexpr(FUSED)
                 {
                     float Bf[3], Ef[3];
@@ -306,7 +323,8 @@ namespace picstep
 #pragma unroll
                     for(int d = 0; d < 3; ++d)
                     {
-                        float q = (x1[d] + ps_div(vel[d] * P.dt, P.cell[d])) - 0.5f;
+                        dpv[d] = PS_DIV_CELL(vel[d] * P.dt, d);
+                        float q = (x1[d] + dpv[d]) - 0.5f;
                         float mv = 0.0f;
                         if(q < -0.5f)
                             mv = -1.0f;
@@ -389,7 +407,7 @@ namespace picstep
 #pragma unroll
                         for(int d = 0; d < 3; ++d)
                         {
-                            float const dp = ps_div(vel[d] * P.dt, P.cell[d]);
+                            float const dp = FUSED ? dpv[d] : PS_DIV_CELL(vel[d] * P.dt, d);
                             float const xe = x1[d], xs = xe - dp;
                             int iS, iE;
                             float const r = relay<even>(iS, iE, xs, xe);
@@ -449,7 +467,7 @@ namespace picstep
 #pragma unroll
                     for(int d = 0; d < 3; ++d)
                     {
-                        float const dp = ps_div(vel[d] * P.dt, P.cell[d]);
+                        float const dp = FUSED ? dpv[d] : PS_DIV_CELL(vel[d] * P.dt, d);
                         float const xe = x1[d], xs = xe - dp;
                         int iS, iE;
                         relay<even>(iS, iE, xs, xe);
@@ -481,10 +499,10 @@ namespace picstep
                     if(narrow)
                     {
                         useRec = true;
+                        float S0[3][C::WN], S1[3][C::WN];
 #pragma unroll
                         for(int d = 0; d < 3; ++d)
                         {
-                            float S0[C::WN], S1[C::WN];
                             if constexpr(SEMI)
                                 if(ext[d] != 0)
                                 {
@@ -513,29 +531,16 @@ namespace picstep
                                         v1 = (o1[d] == m) ? t[d][s].y : v1;
                                     }
                                 }
-                                S0[n] = v0;
-                                S1[n] = v1;
+                                S0[d][n] = v0;
+                                S1[d][n] = v1;
                             }
-                            float4* r4 = reinterpret_cast<float4*>(rec + d * C::AXW);
-                            F2 DS[2];
-#pragma unroll
-                            for(int j = 0; j < 2; ++j)
-                            {
-                                F2 const s0p(S0[2 * j], S0[2 * j + 1]);
-                                DS[j] = F2(S1[2 * j], S1[2 * j + 1]) - s0p;
-                                r4[j] = make_float4(s0p.x, s0p.y, DS[j].x, DS[j].y);
-                                if constexpr(C::PQREC)
-                                {
-                                    F2 const Pp = fma2(DS[j], F2(0.5f), s0p);
-                                    F2 const Qp = fma2(DS[j], F2(1.0f / 3.0f), s0p * F2(0.5f));
-                                    r4[2 + j] = make_float4(Pp.x, Pp.y, Qp.x, Qp.y);
-                                }
-                            }
-                            // prefix sums start at the node left of the window when that one carries weight
-                            float const cm = (SEMI && ext[d] < 0) ? sOut1 - sOut0 : 0.0f;
-                            float const c0 = cm + DS[0].x, c1 = c0 + DS[0].y, c2 = c1 + DS[1].x;
-                            r4[C::COFF / 4] = make_float4(c0 * f[d], c1 * f[d], c2 * f[d], 0.0f);
                         }
+                        // prefix sums start at the node left of the window when that one carries weight
+                        float cm[3];
+#pragma unroll
+                        for(int d = 0; d < 3; ++d)
+                            cm[d] = (SEMI && ext[d] < 0) ? sOut1 - sOut0 : 0.0f;
+                        storeRecord(rec, S0, S1, f, cm);
                         if constexpr(SEMI)
                             if(axOut >= 0)
                             {
@@ -593,7 +598,7 @@ namespace picstep
             if(!useRec)
             {
                 // nothing to add for this record in phase 2 (absorbed / wide trajectory / slot beyond the end of the
-                // piece): C = 0.  The S0/DS/P/Q words are stale but finite, except for a slot that has never been
+                // piece): C = 0.  The other words are stale but finite, except for a slot that has never been
                 // written (first chunk of the piece): that one is cleared completely.
                 float* const rec = myRecs + lane * C::RECW;
                 if(chunk == pBeg)
@@ -609,7 +614,7 @@ namespace picstep
                         *reinterpret_cast<float4*>(rec + d * C::AXW + C::COFF) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 }
             }
-            // ---- phase 2: two records per pass (one per half warp), accumulators flushed when the cell changes ------
+            // ---- phase 2: the records of the chunk are added to the accumulators, which are flushed when the cell changes
             uint32_t const validMask = __ballot_sync(FULL, valid);
             int const n = __popc(validMask);
             int prev = __shfl_up_sync(FULL, lc, 1);
@@ -637,95 +642,82 @@ namespace picstep
             prefetch(chunk + 32);
             prefetchIdx(chunk + 64);
             __syncwarp(); // records are visible
-            // one pass: t(a,b) = S0_i(a) P_j(b) + DS_i(a) Q_j(b), acc(a,b,k) += C_k t(a,b); packed over b (FFMA2 with a
-            // broadcast scalar operand: 10 issue slots for 20 FMAs)
-            auto pass = [&](float const* pSD, float const* pPQ, float const* pC)
+            // runs the records 0..n-1 of the chunk through the accumulators; sMask: a new cell starts at this record.
+            // Two records per pass (one per half warp): t(a,b) = S0_i(a) P_j(b) + DS_i(a) Q_j(b), acc(a,b,k) += C_k t(a,b);
+            // packed over b (FFMA2 with a broadcast scalar operand)
+            auto runPasses = [&](uint32_t sMask)
             {
-                float4 const sd = *reinterpret_cast<float4 const*>(pSD); // {S0[a0], S0[a0+1], DS[a0], DS[a0+1]}
-                float4 const sj = *reinterpret_cast<float4 const*>(pPQ); // PQREC: {P[b0], P[b0+1], Q[b0], Q[b0+1]}, else {S0.., DS..}
-                float4 const c4 = *reinterpret_cast<float4 const*>(pC);
-                F2 pp(sj.x, sj.y), qq(sj.z, sj.w);
-                if constexpr(!C::PQREC)
+                auto pass = [&](float const* pSD, float const* pPQ, float const* pC)
                 {
-                    F2 const s0j = pp, dsj = qq;
-                    pp = fma2(dsj, F2(0.5f), s0j); // P = S0 + DS/2
-                    qq = fma2(dsj, F2(1.0f / 3.0f), s0j * F2(0.5f)); // Q = S0/2 + DS/3
-                }
-                F2 const t0 = fma2(F2(sd.z), qq, F2(sd.x) * pp);
-                F2 const t1 = fma2(F2(sd.w), qq, F2(sd.y) * pp);
-                acc[0][0] = fma2(F2(c4.x), t0, acc[0][0]);
-                acc[0][1] = fma2(F2(c4.y), t0, acc[0][1]);
-                acc[0][2] = fma2(F2(c4.z), t0, acc[0][2]);
-                acc[1][0] = fma2(F2(c4.x), t1, acc[1][0]);
-                acc[1][1] = fma2(F2(c4.y), t1, acc[1][1]);
-                acc[1][2] = fma2(F2(c4.z), t1, acc[1][2]);
-            };
-            float const* const zC = myRecs + 32 * C::RECW + offC; // C words of the all-zero record
-            // records q, q+1 with a cell change at q (bit 0) and / or at q+1 (bit 1)
-            auto passSlow = [&](float const* pSD, float const* pPQ, float const* pC, uint32_t bits, int q)
-            {
-                if(bits & 1u)
+                    float4 const sd = *reinterpret_cast<float4 const*>(pSD); // {S0[a0], S0[a0+1], DS[a0], DS[a0+1]}
+                    float4 const sj = *reinterpret_cast<float4 const*>(pPQ); // {S0[b0], S0[b0+1], DS[b0], DS[b0+1]}
+                    float4 const c4 = *reinterpret_cast<float4 const*>(pC);
+                    F2 const s0j(sj.x, sj.y), dsj(sj.z, sj.w);
+                    F2 const pp = fma2(dsj, F2(0.5f), s0j); // P = S0 + DS/2
+                    F2 const qq = fma2(dsj, F2(1.0f / 3.0f), s0j * F2(0.5f)); // Q = S0/2 + DS/3
+                    F2 const t0 = fma2(F2(sd.z), qq, F2(sd.x) * pp);
+                    F2 const t1 = fma2(F2(sd.w), qq, F2(sd.y) * pp);
+                    acc[0][0] = fma2(F2(c4.x), t0, acc[0][0]);
+                    acc[0][1] = fma2(F2(c4.y), t0, acc[0][1]);
+                    acc[0][2] = fma2(F2(c4.z), t0, acc[0][2]);
+                    acc[1][0] = fma2(F2(c4.x), t1, acc[1][0]);
+                    acc[1][1] = fma2(F2(c4.y), t1, acc[1][1]);
+                    acc[1][2] = fma2(F2(c4.z), t1, acc[1][2]);
+                };
+                float const* const zC = myRecs + 32 * C::RECW + offC; // C words of the all-zero record
+                // records q, q+1 with a cell change at q (bit 0) and / or at q+1 (bit 1)
+                auto passSlow = [&](float const* pSD, float const* pPQ, float const* pC, uint32_t bits, int q)
                 {
-                    if(curCell >= 0)
+                    if(bits & 1u)
+                    {
+                        if(curCell >= 0)
+                            flushCell();
+                        curCell = __shfl_sync(FULL, lc, q);
+                    }
+                    if(bits & 2u)
+                    {
+                        pass(pSD, pPQ, slot ? zC : pC); // record q closes its cell
                         flushCell();
-                    curCell = __shfl_sync(FULL, lc, q);
-                }
-                if(bits & 2u)
-                {
-                    pass(pSD, pPQ, slot ? zC : pC); // record q closes its cell
-                    flushCell();
-                    curCell = __shfl_sync(FULL, lc, q + 1);
-                    pass(pSD, pPQ, slot ? pC : zC); // record q+1 opens the next one
-                }
-                else
-                    pass(pSD, pPQ, pC);
-            };
-            float const* rec = myRecs + slot * C::RECW;
-            float const *pSD = rec + offSD, *pPQ = rec + offPQ, *pC = rec + offC;
+                        curCell = __shfl_sync(FULL, lc, q + 1);
+                        pass(pSD, pPQ, slot ? pC : zC); // record q+1 opens the next one
+                    }
+                    else
+                        pass(pSD, pPQ, pC);
+                };
+                float const* rec = myRecs + slot * C::RECW;
+                float const *pSD = rec + offSD, *pPQ = rec + offPQ, *pC = rec + offC;
+                // groups of eight records (records beyond n carry C = 0): a group without a cell change is four passes of
+                // straight line code, otherwise every pair of records is looked at
 #pragma unroll 1
-            for(int r = 0; r < n; r += 4)
-            {
-                uint32_t const b4 = (startMask >> r) & 0xfu;
-                if(b4 == 0u)
+                for(int r = 0; r < n; r += 8)
                 {
-                    pass(pSD, pPQ, pC);
-                    pass(pSD + 2 * C::RECW, pPQ + 2 * C::RECW, pC + 2 * C::RECW);
+                    uint32_t const b8 = (sMask >> r) & 0xffu;
+                    if(b8 == 0u)
+                    {
+#pragma unroll
+                        for(int q = 0; q < 8; q += 2)
+                            pass(pSD + q * C::RECW, pPQ + q * C::RECW, pC + q * C::RECW);
+                    }
+                    else
+                    {
+#pragma unroll
+                        for(int q = 0; q < 8; q += 2)
+                        {
+                            uint32_t const b2 = (b8 >> q) & 3u;
+                            if(b2 == 0u)
+                                pass(pSD + q * C::RECW, pPQ + q * C::RECW, pC + q * C::RECW);
+                            else
+                                passSlow(pSD + q * C::RECW, pPQ + q * C::RECW, pC + q * C::RECW, b2, r + q);
+                        }
+                    }
+                    pSD += 8 * C::RECW;
+                    pPQ += 8 * C::RECW;
+                    pC += 8 * C::RECW;
                 }
-                else
-                {
-                    passSlow(pSD, pPQ, pC, b4 & 3u, r);
-                    passSlow(pSD + 2 * C::RECW, pPQ + 2 * C::RECW, pC + 2 * C::RECW, b4 >> 2, r + 2);
-                }
-                pSD += 4 * C::RECW;
-                pPQ += 4 * C::RECW;
-                pC += 4 * C::RECW;
-            }
+            };
+            runPasses(startMask);
             if constexpr(SOLVER == 1)
             {
-                // (the pass loop once more; kept out of the Esirkepov instantiation, whose code must not change)
-                auto runPasses = [&](uint32_t sMask)
-                {
-                    float const* q = myRecs + slot * C::RECW;
-                    float const *qSD = q + offSD, *qPQ = q + offPQ, *qC = q + offC;
-#pragma unroll 1
-                    for(int r = 0; r < n; r += 4)
-                    {
-                        uint32_t const b4 = (sMask >> r) & 0xfu;
-                        if(b4 == 0u)
-                        {
-                            pass(qSD, qPQ, qC);
-                            pass(qSD + 2 * C::RECW, qPQ + 2 * C::RECW, qC + 2 * C::RECW);
-                        }
-                        else
-                        {
-                            passSlow(qSD, qPQ, qC, b4 & 3u, r);
-                            passSlow(qSD + 2 * C::RECW, qPQ + 2 * C::RECW, qC + 2 * C::RECW, b4 >> 2, r + 2);
-                        }
-                        qSD += 4 * C::RECW;
-                        qPQ += 4 * C::RECW;
-                        qC += 4 * C::RECW;
-                    }
-                };
                 // second EmZ segment of the trajectories that changed their assignment cell: the same records again
                 if(__ballot_sync(FULL, twoSeg))
                 {
@@ -782,7 +774,7 @@ namespace picstep
                         int const ty = y - h * (SCY / 2);
                         if(tz >= 0 && tz < C::PZ && ty >= 0 && ty < C::PY)
                         {
-                            float const* __restrict__ src = tiles + (zc * 2 + h) * 3 * C::PV + cmp * C::PV + C::PX * (ty + C::PY * tz);
+                            float const* __restrict__ src = tiles + (zc * 2 + h) * 3 * C::PVC + cmp * C::PVC + C::PX * (ty + C::PY * tz);
 #pragma unroll
                             for(int x = 0; x < C::TX; ++x)
                                 v[x] += src[x];

@@ -95,3 +95,56 @@ def khi_scales(p, steps=1, ppc=25, beta_gamma=0.2):
     jscale = ppc * 1.0 * beta_gamma / V
     escale = p.dt / p.eps0 * jscale * steps
     return jscale, escale
+
+
+# ---- one-to-one particle matching across a run (tests/test_gpu_c1.py, test_khi_100_steps_vs_oracle) ----------------
+def tag_weights(p, sp):
+    """w -> the float `tag` ulps above w: tag = ((x0 * 25 + j) * 8 + y0 % 8) * 4 + z0 % 4 with (x0, y0, z0) the start
+    cell and j the index inside the cell.  Two particles share a tag only if their start cells differ by a multiple
+    of 8 in y or of 4 in z — thermal motion over 100 steps does not bridge that."""
+    n = p.grid
+    cell = sp["cell"]
+    order = np.argsort(cell, kind="stable")
+    sorted_cell = cell[order]
+    first = np.searchsorted(sorted_cell, sorted_cell, side="left")
+    j = np.empty(cell.shape[0], np.int64)
+    j[order] = np.arange(cell.shape[0]) - first
+    assert j.max() < 25
+    x0, y0, z0 = cell % n[0], (cell // n[0]) % n[1], cell // (n[0] * n[1])
+    tag = ((x0.astype(np.int64) * 25 + j) * 8 + (y0 % 8)) * 4 + (z0 % 4)
+    sp["w"] = (sp["w"].view(np.uint32) + tag.astype(np.uint32)).view(np.float32).copy()
+
+
+def match_key(p, sp_or_arrays, w0_bits):
+    """(tag, block of the START cell): the tag holds y0 % 8 and z0 % 4, and a particle moves far less than half a block
+    (4 cells in y, 2 in z) in 100 steps, so the block it started in follows from where it is now."""
+    pos, w, cell = sp_or_arrays
+    n = p.grid
+    tag = (w.view(np.uint32) - np.uint32(w0_bits)).astype(np.int64)
+    assert tag.min() >= 0 and tag.max() < 64 * 25 * 8 * 4
+    Y = ((cell // n[0]) % n[1]) + pos[1].astype(np.float64)
+    Z = (cell // (n[0] * n[1])) + pos[2].astype(np.float64)
+    yb = np.rint((Y - ((tag >> 2) & 7) - 0.5) / 8.0).astype(np.int64) % (n[1] // 8)
+    zb = np.rint((Z - (tag & 3) - 0.5) / 4.0).astype(np.int64) % (n[2] // 4)
+    return (tag << 16) | (yb << 8) | zb
+
+
+def global_pos(p, pos, cell):
+    n = p.grid
+    c3 = np.stack([cell % n[0], (cell // n[0]) % n[1], cell // (n[0] * n[1])]).astype(np.float64)
+    return c3 + pos.astype(np.float64)
+
+
+def permuted_copy(species, seed=123):
+    """The same particles stored in another order: only the fp32 summation order of the deposition changes."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for sp in species:
+        c = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in sp.items()}
+        perm = rng.permutation(c["w"].shape[0])
+        for k in ("pos", "mom"):
+            c[k] = np.ascontiguousarray(c[k][:, perm])
+        for k in ("w", "cell"):
+            c[k] = np.ascontiguousarray(c[k][perm])
+        out.append(c)
+    return out
