@@ -114,7 +114,8 @@ extern "C"
         int32_t flags; /* bit0: deposit with the reference-strategy per-particle atomic kernel (cross-check);
                         * bit1: deposit with the warp-per-cell kernel (all shapes, EmZ) instead of the run kernel;
                         * bit2: picstep_step() runs push and deposit as separate kernels (no fusion);
-                        * bit3: picstep_step() keeps the re-sort on the main stream (no overlap with the next kernel) */
+                        * bit3: picstep_step() keeps the re-sort on the main stream (no overlap with the next kernel);
+                        * bit4: Yee update with the one-thread-per-cell kernels instead of the TMA-staged bricks */
         /* --currentInterpolation none|binomial (simulation/stage/CurrentInterpolationAndAdditionToEMF.hpp:60-92,
          * fields/currentInterpolation/Binomial.hpp:41-112) */
         int32_t current_interpolation; /* picstep_current_interpolation */

@@ -80,6 +80,15 @@ namespace picstep
         float const* damp;
     };
 
+    // Supercells covered by one launch of the run kernel: the layers first, first + stride, ... (count of them) along
+    // `axis`, all supercells in the two other axes.  The whole domain is {2, 0, 1, nsc[2]}; with a domain decomposition
+    // the BORDER area (the two layers that face the neighbour ranks, pmacc/type/Area.hpp:36-41,
+    // AreaMappingMethods.hpp:41-120) is launched first and its exchange travels while the CORE area is computed.
+    struct ScArea
+    {
+        int axis, first, stride, count;
+    };
+
     struct SpeciesDev
     {
         float* pos[3];

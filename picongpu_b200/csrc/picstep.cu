@@ -23,7 +23,7 @@ namespace picstep
     cudaError_t launchDeposit(int, int, bool, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
     bool runKernelSupports(int, int);
     cudaError_t launchDepositRun(int, int, DevParams const&, SpeciesDev const&, Field3, uint32_t const*, cudaStream_t);
-    cudaError_t launchPushDeposit(int, int, int, DevParams const&, SpeciesDev const&, SpeciesDev const&, uint32_t const*, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, TileMaps const&, cudaStream_t);
+    cudaError_t launchPushDeposit(int, int, int, DevParams const&, SpeciesDev const&, SpeciesDev const&, uint32_t const*, Field3, Field3, Field3, uint32_t const*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, TileMaps const&, ScArea const&, cudaStream_t);
     cudaError_t launchInvertRanked(uint32_t const*, uint32_t const*, uint32_t const*, uint32_t, uint32_t const*, uint32_t const*, uint32_t*, uint16_t*, uint32_t, cudaStream_t);
     cudaError_t launchAppendRecords(MigRecord const*, uint32_t, uint32_t const*, uint32_t, uint32_t, SpeciesDev, uint32_t const*, uint32_t*, uint32_t*, int*, cudaStream_t);
     cudaError_t launchGatherPerm(SpeciesDev, SpeciesDev, uint32_t const*, uint32_t const*, uint32_t, cudaStream_t);
@@ -38,6 +38,8 @@ namespace picstep
     cudaError_t launchKeysFromCells(DevParams const&, int32_t const*, uint32_t, uint32_t*, uint32_t*, int*, cudaStream_t);
     cudaError_t launchCellsFromRuns(DevParams const&, uint16_t const*, uint32_t const*, int32_t*, cudaStream_t);
     cudaError_t launchSupercellCounts(uint32_t const*, long long*, int, cudaStream_t);
+    void fdtdBox(int*);
+    cudaError_t launchFdtdTma(int, bool, DevParams const&, Field3, Field3, CUtensorMap const&, int, cudaStream_t);
     cudaError_t launchUpdateBHalf(int, DevParams const&, LeheCoeffs const&, Field3, Field3, cudaStream_t);
     cudaError_t launchUpdateE(DevParams const&, LeheCoeffs const&, Field3, Field3, cudaStream_t);
     cudaError_t launchAddCurrent(DevParams const&, Field3, Field3, bool, cudaStream_t);
@@ -99,6 +101,10 @@ struct picstep_ctx
     DevParams P{};
     LeheCoeffs lehe{};
     TileMaps tileMaps{}; // TMA descriptors of E and B for the supercell tile of this shape
+    alignas(64) CUtensorMap fdtdMap[2]; // TMA descriptors of E and B for the brick (+ halo) of the Yee update kernels
+    bool fdtdTma = false;
+    uint32_t* migPinned = nullptr; // pinned readback of the migration counts of all species (overlapped step)
+    cudaEvent_t evBorder = nullptr, evComm = nullptr;
     AbsorberDev absorber{}; // exponential absorber: thickness per face (0 = not absorbing) + attenuation table
     float* dampDev = nullptr;
     bool absorbing = false;
@@ -377,23 +383,112 @@ namespace
 
     // ---- guard exchange of one field along all axes ------------------------------------------------------------
     // mode -1: by field (E,B: guard := neighbour border; J: border += neighbour guard), 0: copy, 1: add;
-    // width >= 0 overrides the margins of picstep_exchange_widths on both sides
-    int exchangeField(picstep_ctx* c, int f, int mode = -1, int width = -1)
+    // width >= 0 overrides the margins of picstep_exchange_widths on both sides.
+    // The pass along the split axis has three phases -- pack into the send buffers, NCCL send/recv, unpack (copy or
+    // add) -- which exchangeField() queues back to back on the compute stream; the overlapped step (stepImpl) queues
+    // the first two for J on the communication stream while the CORE area is still being computed.
+    struct AxisExchange
+    {
+        int a, lo, up;
+        bool add;
+        size_t nSendLo, nSendHi, nRecvLo, nRecvHi; // floats
+    };
+
+    AxisExchange axisExchange(picstep_ctx* c, int f, int a, int mode, int width)
+    {
+        DevParams const& P = c->P;
+        AxisExchange x{};
+        int w[2];
+        picstep_exchange_widths(c->prm.shape, c->prm.field_solver, c->prm.lehe_dir, f, a, w);
+        if(width >= 0)
+            w[0] = w[1] = width;
+        x.a = a;
+        x.lo = w[0];
+        x.up = w[1];
+        x.add = mode < 0 ? (f == PICSTEP_FIELD_J) : (mode == 1);
+        long long const plane = (long long) P.N[(a == 0) ? 1 : 0] * P.N[(a == 2) ? 1 : 2] * 3;
+        if(!x.add)
+        {
+            // my lower border (up planes) -> lower neighbour's upper guard; my upper border (lo planes) -> upper neighbour's lower guard
+            x.nSendLo = size_t(plane * x.up);
+            x.nSendHi = size_t(plane * x.lo);
+            x.nRecvLo = size_t(plane * x.lo); // from lower neighbour: its upper border -> my lower guard
+            x.nRecvHi = size_t(plane * x.up);
+        }
+        else
+        {
+            // my lower guard (lo planes) -> lower neighbour adds to its upper border; my upper guard (up planes) -> upper neighbour
+            x.nSendLo = size_t(plane * x.lo);
+            x.nSendHi = size_t(plane * x.up);
+            x.nRecvLo = size_t(plane * x.up); // lower neighbour's upper guard -> add to my lower border
+            x.nRecvHi = size_t(plane * x.lo);
+        }
+        return x;
+    }
+
+    int axisPack(picstep_ctx* c, Field3 F, AxisExchange const& x, cudaStream_t st)
+    {
+        DevParams const& P = c->P;
+        int const g = P.g[x.a], n = P.n[x.a];
+        if(!x.add)
+        {
+            if(c->rankLo >= 0)
+                KL(c, 1, launchHaloPack(P, F, 3, x.a, g, x.up, c->haloBuf[0], st));
+            if(c->rankHi >= 0)
+                KL(c, 1, launchHaloPack(P, F, 3, x.a, g + n - x.lo, x.lo, c->haloBuf[1], st));
+        }
+        else
+        {
+            if(c->rankLo >= 0)
+                KL(c, 1, launchHaloPack(P, F, 3, x.a, g - x.lo, x.lo, c->haloBuf[0], st));
+            if(c->rankHi >= 0)
+                KL(c, 1, launchHaloPack(P, F, 3, x.a, g + n, x.up, c->haloBuf[1], st));
+        }
+        return PICSTEP_OK;
+    }
+
+    int axisComm(picstep_ctx* c, AxisExchange const& x, cudaStream_t st)
+    {
+        if(!c->comm)
+            return fail(c, PICSTEP_ERR_COMM, "devices > 1 but picstep_comm_init was not called");
+        int const rc = commSendRecv(c->comm, c->haloBuf[0], x.nSendLo * sizeof(float), c->haloBuf[2], x.nRecvLo * sizeof(float), c->rankLo, c->haloBuf[1], x.nSendHi * sizeof(float), c->haloBuf[3], x.nRecvHi * sizeof(float), c->rankHi, st, c->err);
+        return rc ? PICSTEP_ERR_COMM : PICSTEP_OK;
+    }
+
+    int axisUnpack(picstep_ctx* c, Field3 F, AxisExchange const& x, cudaStream_t st)
+    {
+        DevParams const& P = c->P;
+        int const g = P.g[x.a], n = P.n[x.a];
+        if(!x.add)
+        {
+            if(c->rankLo >= 0)
+                KL(c, 1, launchHaloUnpack(false, P, F, 3, x.a, g - x.lo, x.lo, c->haloBuf[2], st));
+            if(c->rankHi >= 0)
+                KL(c, 1, launchHaloUnpack(false, P, F, 3, x.a, g + n, x.up, c->haloBuf[3], st));
+        }
+        else
+        {
+            if(c->rankLo >= 0)
+                KL(c, 1, launchHaloUnpack(true, P, F, 3, x.a, g, x.up, c->haloBuf[2], st));
+            if(c->rankHi >= 0)
+                KL(c, 1, launchHaloUnpack(true, P, F, 3, x.a, g + n - x.lo, x.lo, c->haloBuf[3], st));
+        }
+        return PICSTEP_OK;
+    }
+
+    // skipSplit: the pass along the split axis has been done already (overlapped J exchange)
+    int exchangeField(picstep_ctx* c, int f, int mode = -1, int width = -1, bool skipSplit = false)
     {
         DevParams const& P = c->P;
         Field3 F = fieldOf(c, f);
-        bool const add = mode < 0 ? (f == PICSTEP_FIELD_J) : (mode == 1);
         for(int a = 0; a < 3; ++a)
         {
-            int w[2];
-            picstep_exchange_widths(c->prm.shape, c->prm.field_solver, c->prm.lehe_dir, f, a, w);
-            if(width >= 0)
-                w[0] = w[1] = width;
-            int const lo = w[0], up = w[1];
+            AxisExchange const x = axisExchange(c, f, a, mode, width);
+            int const lo = x.lo, up = x.up;
             int const g = P.g[a], n = P.n[a];
             if(P.wrap[a])
             {
-                if(!add)
+                if(!x.add)
                 {
                     KL(c, 1, launchHaloLocal(false, P, F, 3, a, g + n - lo, g - lo, lo, c->stream)); // lower guard <- upper border
                     KL(c, 1, launchHaloLocal(false, P, F, 3, a, g, g + n, up, c->stream)); // upper guard <- lower border
@@ -404,66 +499,15 @@ namespace
                     KL(c, 1, launchHaloLocal(true, P, F, 3, a, g + n, g, up, c->stream)); // lower border += upper guard
                 }
             }
-            else if(a == P.split_axis && c->nranks > 1)
+            else if(a == P.split_axis && c->nranks > 1 && !skipSplit)
             {
-                if(!c->comm)
-                    return fail(c, PICSTEP_ERR_COMM, "devices > 1 but picstep_comm_init was not called");
-                long long const plane = (long long) P.N[(a == 0) ? 1 : 0] * P.N[(a == 2) ? 1 : 2] * 3;
-                size_t nSendLo, nSendHi, nRecvLo, nRecvHi;
-                if(!add)
-                {
-                    // my lower border (up planes) -> lower neighbour's upper guard; my upper border (lo planes) -> upper neighbour's lower guard
-                    nSendLo = size_t(plane * up);
-                    nSendHi = size_t(plane * lo);
-                    nRecvLo = size_t(plane * lo); // from lower neighbour: its upper border -> my lower guard
-                    nRecvHi = size_t(plane * up);
-                    if(c->rankLo >= 0)
-                        KL(c, 1, launchHaloPack(P, F, 3, a, g, up, c->haloBuf[0], c->stream));
-                    if(c->rankHi >= 0)
-                        KL(c, 1, launchHaloPack(P, F, 3, a, g + n - lo, lo, c->haloBuf[1], c->stream));
-                }
-                else
-                {
-                    // my lower guard (lo planes) -> lower neighbour adds to its upper border; my upper guard (up planes) -> upper neighbour
-                    nSendLo = size_t(plane * lo);
-                    nSendHi = size_t(plane * up);
-                    nRecvLo = size_t(plane * up); // lower neighbour's upper guard -> add to my lower border
-                    nRecvHi = size_t(plane * lo);
-                    if(c->rankLo >= 0)
-                        KL(c, 1, launchHaloPack(P, F, 3, a, g - lo, lo, c->haloBuf[0], c->stream));
-                    if(c->rankHi >= 0)
-                        KL(c, 1, launchHaloPack(P, F, 3, a, g + n, up, c->haloBuf[1], c->stream));
-                }
-                int const rc = commSendRecv(
-                    c->comm,
-                    c->haloBuf[0],
-                    nSendLo * sizeof(float),
-                    c->haloBuf[2],
-                    nRecvLo * sizeof(float),
-                    c->rankLo,
-                    c->haloBuf[1],
-                    nSendHi * sizeof(float),
-                    c->haloBuf[3],
-                    nRecvHi * sizeof(float),
-                    c->rankHi,
-                    c->stream,
-                    c->err);
+                int rc = axisPack(c, F, x, c->stream);
+                if(!rc)
+                    rc = axisComm(c, x, c->stream);
+                if(!rc)
+                    rc = axisUnpack(c, F, x, c->stream);
                 if(rc)
-                    return PICSTEP_ERR_COMM;
-                if(!add)
-                {
-                    if(c->rankLo >= 0)
-                        KL(c, 1, launchHaloUnpack(false, P, F, 3, a, g - lo, lo, c->haloBuf[2], c->stream));
-                    if(c->rankHi >= 0)
-                        KL(c, 1, launchHaloUnpack(false, P, F, 3, a, g + n, up, c->haloBuf[3], c->stream));
-                }
-                else
-                {
-                    if(c->rankLo >= 0)
-                        KL(c, 1, launchHaloUnpack(true, P, F, 3, a, g, up, c->haloBuf[2], c->stream));
-                    if(c->rankHi >= 0)
-                        KL(c, 1, launchHaloUnpack(true, P, F, 3, a, g + n - lo, lo, c->haloBuf[3], c->stream));
-                }
+                    return rc;
             }
             // else: open boundary, guards stay as they are
         }
@@ -770,6 +814,8 @@ extern "C"
         CUC(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
         CUC(cudaEventCreateWithFlags(&c->evFused, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->evFlags, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&c->evBorder, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&c->evComm, cudaEventDisableTiming));
         int tbox[3], tlo = 0;
         tileBox(p->shape, tbox, &tlo);
         c->tileMaps.lead = tlo & 3;
@@ -790,6 +836,17 @@ extern "C"
                     picstep_destroy(c);
                     return fail(nullptr, PICSTEP_ERR_CUDA, msg);
                 }
+        }
+        {
+            // Yee update through TMA-staged bricks (fields.cu); the Lehe stencil and a driver that refuses the box
+            // (e.g. a grid narrower than the box) keep the one-thread-per-cell kernels
+            int fbox[3];
+            fdtdBox(fbox);
+            char msg[128];
+            c->fdtdTma = p->field_solver == PICSTEP_SOLVER_YEE && !(p->flags & 16);
+            for(int f = 0; f < 2 && c->fdtdTma; ++f)
+                if(makeTileMap(&c->fdtdMap[f], c->fieldAlloc[f], P.N, P.vol, fbox, msg, sizeof(msg)))
+                    c->fdtdTma = false;
         }
         CUC(cudaMalloc(&c->dampDev, sizeof(float) * damp.size()));
         CUC(cudaMemcpy(c->dampDev, damp.data(), sizeof(float) * damp.size(), cudaMemcpyHostToDevice));
@@ -841,6 +898,12 @@ extern "C"
         cudaFree(c->flags);
         if(c->hostPinned)
             cudaFreeHost(c->hostPinned);
+        if(c->migPinned)
+            cudaFreeHost(c->migPinned);
+        if(c->evBorder)
+            cudaEventDestroy(c->evBorder);
+        if(c->evComm)
+            cudaEventDestroy(c->evComm);
         for(auto& sp : c->spans)
         {
             cudaEventDestroy(sp.a);
@@ -1211,18 +1274,40 @@ extern "C"
         return exchangeField(c, f);
     }
 
+    // B -= curl E * dt/2 (updateBFirstHalf / updateBSecondHalf)
+    static int updateBHalf(picstep_ctx* c)
+    {
+        Field3 E = fieldOf(c, PICSTEP_FIELD_E), B = fieldOf(c, PICSTEP_FIELD_B);
+        if(c->fdtdTma)
+            KL(c, 1, launchFdtdTma(0, false, c->P, B, B, c->fdtdMap[PICSTEP_FIELD_E], c->tileMaps.lead, c->stream));
+        else
+            KL(c, 1, launchUpdateBHalf(c->prm.field_solver, c->P, c->lehe, E, B, c->stream));
+        return PICSTEP_OK;
+    }
+
+    // update_beforeCurrent; addJ: the current term E += coeff * J rides in the E update kernel (J already reduced)
+    static int fieldUpdateBeforeCurrent(picstep_ctx* c, bool addJ)
+    {
+        StageTimer t(c, 3);
+        Field3 E = fieldOf(c, PICSTEP_FIELD_E), B = fieldOf(c, PICSTEP_FIELD_B);
+        int rc = updateBHalf(c); // updateBSecondHalf
+        if(rc)
+            return rc;
+        rc = exchangeField(c, PICSTEP_FIELD_B);
+        if(rc)
+            return rc;
+        if(c->fdtdTma)
+            KL(c, 1, launchFdtdTma(1, addJ, c->P, E, fieldOf(c, PICSTEP_FIELD_J), c->fdtdMap[PICSTEP_FIELD_B], c->tileMaps.lead, c->stream));
+        else
+            KL(c, 1, launchUpdateE(c->P, c->lehe, E, B, c->stream));
+        return PICSTEP_OK;
+    }
+
     int picstep_field_update_before_current(picstep_ctx* c, uint32_t)
     {
         if(!c)
             return PICSTEP_ERR_INVALID;
-        StageTimer t(c, 3);
-        Field3 E = fieldOf(c, PICSTEP_FIELD_E), B = fieldOf(c, PICSTEP_FIELD_B);
-        KL(c, 1, launchUpdateBHalf(c->prm.field_solver, c->P, c->lehe, E, B, c->stream)); // updateBSecondHalf
-        int rc = exchangeField(c, PICSTEP_FIELD_B);
-        if(rc)
-            return rc;
-        KL(c, 1, launchUpdateE(c->P, c->lehe, E, B, c->stream));
-        return PICSTEP_OK;
+        return fieldUpdateBeforeCurrent(c, false);
     }
 
     int picstep_deposit(picstep_ctx* c, int32_t sp)
@@ -1244,23 +1329,81 @@ extern "C"
 
     /* fused ParticlePush + CurrentDeposition of one species (fast path of picstep_step): the current of the move
      * is deposited by the kernel that performs the move, from the cell the particle started in */
-    static int pushDepositFused(picstep_ctx* c, int32_t sp)
+    static int pushDepositFused(picstep_ctx* c, int32_t sp, ScArea const& area)
     {
         StageTimer t(c, 1);
         SpeciesHost& s = c->species[sp];
         if(s.capacity == 0)
             return PICSTEP_OK;
-        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->prm.current_solver, c->P, devOf(c, s, s.cur), devOf(c, s, s.cur ^ 1), s.lazy ? s.inv : nullptr, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, c->tileMaps, c->stream));
+        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->prm.current_solver, c->P, devOf(c, s, s.cur), devOf(c, s, s.cur ^ 1), s.lazy ? s.inv : nullptr, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, c->tileMaps, area, c->stream));
         s.ranked = true;
         return PICSTEP_OK;
     }
 
-    int picstep_add_current(picstep_ctx* c)
+    /* Overlapped step, communication-stream part (Simulation.hpp:537 `__setTransactionEvent(commEvent)` joins the
+     * reference's asynchronous particle / field communication the same way): the BORDER area of every species has
+     * been pushed, so the particles that leave the rank (only border supercells can lose any) are packed and exchanged
+     * and the J guard strips along the split axis (only border-supercell particles deposit there) are sent while the
+     * compute stream works on the CORE area.  The host waits ONCE, on the communication stream only, for the record
+     * counts of all species -- the CORE kernels are queued by then, so the device does not idle. */
+    static int exchangeBorderOverlapped(picstep_ctx* c, cudaStream_t st, std::vector<uint32_t>& nRecLo, std::vector<uint32_t>& nRecHi, AxisExchange const& xj)
     {
-        if(!c)
-            return PICSTEP_ERR_INVALID;
+        int const ns = int(c->species.size());
+        if(!c->comm)
+            return fail(c, PICSTEP_ERR_COMM, "devices > 1 but picstep_comm_init was not called");
+        if(!c->migPinned)
+            CU(c, cudaMallocHost(&c->migPinned, sizeof(uint32_t) * 8 * 64));
+        if(ns > 64)
+            return fail(c, PICSTEP_ERR_INVALID, "more than 64 species");
+        for(int i = 0; i < ns; ++i)
+        {
+            SpeciesHost& s = c->species[i];
+            if(s.capacity == 0)
+                continue;
+            CU(c, cudaMemsetAsync(s.sendCnt, 0, sizeof(uint32_t) * 2, st));
+            KL(c, 1, launchPackLeavers(c->P, devOf(c, s, s.cur ^ 1), s.key, s.cellOff[s.cur], s.sendLo, s.sendHi, s.sendCnt, s.capRec, c->flags + 2, st));
+            if(commSendRecv(c->comm, s.sendCnt, sizeof(uint32_t), s.scSum, sizeof(uint32_t), c->rankLo, s.sendCnt + 1, sizeof(uint32_t), s.scSum + 1, sizeof(uint32_t), c->rankHi, st, c->err))
+                return PICSTEP_ERR_COMM;
+            CU(c, cudaMemcpyAsync(c->migPinned + 8 * i, s.sendCnt, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
+            CU(c, cudaMemcpyAsync(c->migPinned + 8 * i + 2, s.scSum, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
+            CU(c, cudaMemcpyAsync(c->migPinned + 8 * i + 4, s.nDev + s.cur, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        }
+        // J guard strips: pack and send before the host wait, they do not depend on the counts
+        int rc = axisPack(c, fieldOf(c, PICSTEP_FIELD_J), xj, st);
+        if(!rc)
+            rc = axisComm(c, xj, st);
+        if(rc)
+            return rc;
+        CU(c, cudaStreamSynchronize(st));
+        bool overflow = false;
+        for(int i = 0; i < ns; ++i)
+        {
+            SpeciesHost& s = c->species[i];
+            if(s.capacity == 0)
+                continue;
+            uint32_t const* h = c->migPinned + 8 * i;
+            uint32_t nSendLo = c->rankLo >= 0 ? h[0] : 0u, nSendHi = c->rankHi >= 0 ? h[1] : 0u;
+            nRecLo[i] = c->rankLo >= 0 ? h[2] : 0u;
+            nRecHi[i] = c->rankHi >= 0 ? h[3] : 0u;
+            overflow = overflow || nSendLo > s.capRec || nSendHi > s.capRec || nRecLo[i] > s.capRec || nRecHi[i] > s.capRec;
+            nSendLo = std::min(nSendLo, s.capRec);
+            nSendHi = std::min(nSendHi, s.capRec);
+            nRecLo[i] = std::min(nRecLo[i], s.capRec);
+            nRecHi[i] = std::min(nRecHi[i], s.capRec);
+            if(commSendRecv(c->comm, s.sendLo, sizeof(MigRecord) * nSendLo, s.recvLo, sizeof(MigRecord) * nRecLo[i], c->rankLo, s.sendHi, sizeof(MigRecord) * nSendHi, s.recvHi, sizeof(MigRecord) * nRecHi[i], c->rankHi, st, c->err))
+                return PICSTEP_ERR_COMM;
+            s.nUpper = h[4];
+        }
+        if(overflow)
+            return fail(c, PICSTEP_ERR_CAPACITY, "migration record buffer overflow");
+        return PICSTEP_OK;
+    }
+
+    // skipSplit: the J guard reduction along the split axis has been done already (overlapped step)
+    static int addCurrentImpl(picstep_ctx* c, bool skipSplit)
+    {
         StageTimer t(c, 5);
-        int rc = exchangeField(c, PICSTEP_FIELD_J);
+        int rc = exchangeField(c, PICSTEP_FIELD_J, -1, -1, skipSplit);
         if(rc)
             return rc;
         bool const binomial = c->prm.current_interpolation == PICSTEP_CURRENT_INTERPOLATION_BINOMIAL;
@@ -1269,6 +1412,13 @@ extern "C"
                 return rc;
         KL(c, 1, launchAddCurrent(c->P, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_J), binomial, c->stream));
         return PICSTEP_OK;
+    }
+
+    int picstep_add_current(picstep_ctx* c)
+    {
+        if(!c)
+            return PICSTEP_ERR_INVALID;
+        return addCurrentImpl(c, false);
     }
 
     int picstep_field_update_after_current(picstep_ctx* c, uint32_t)
@@ -1282,7 +1432,9 @@ extern "C"
         int rc = exchangeField(c, PICSTEP_FIELD_E);
         if(rc)
             return rc;
-        KL(c, 1, launchUpdateBHalf(c->prm.field_solver, c->P, c->lehe, E, B, c->stream)); // updateBFirstHalf
+        rc = updateBHalf(c); // updateBFirstHalf
+        if(rc)
+            return rc;
         if(c->absorbing) // exponentialImpl.run(B) (FDTDBase.hpp:175-179)
             KL(c, 1, launchAbsorb(c->P, B, c->absorber, c->stream));
         return exchangeField(c, PICSTEP_FIELD_B);
@@ -1386,6 +1538,11 @@ extern "C"
         // stream the re-sort finishes early but the step gets 0.5 ms longer.  Kept for one rank (no NCCL calls from two
         // streams), default priority.
         bool const overlap = fused && !(c->prm.flags & 8) && c->nranks == 1;
+        // Several ranks: the BORDER area (the two supercell layers that face the neighbours) is pushed first; its
+        // leaving particles and the J guard strips travel on the second stream while the CORE area is computed
+        // (pmacc/type/Area.hpp:36-41; FDTDBase.hpp:107-120 and Simulation.hpp:537 overlap the same way).
+        bool const commOverlap = fused && !(c->prm.flags & 8) && c->nranks > 1 && c->P.split_axis >= 0;
+        std::vector<uint32_t> recLo(size_t(ns), 0u), recHi(size_t(ns), 0u);
         while(int(c->evMig.size()) < ns)
         {
             cudaEvent_t e;
@@ -1398,7 +1555,56 @@ extern "C"
         {
             uint32_t const step = first + it;
             rc = picstep_current_reset(c);
-            for(int s = 0; s < ns && !rc; ++s)
+            bool jSplitDone = false;
+            if(commOverlap && !rc)
+            {
+                int const a = c->P.split_axis;
+                ScArea const border{a, 0, c->P.nsc[a] - 1, 2}, core{a, 1, 1, c->P.nsc[a] - 2};
+                for(int s = 0; s < ns && !rc; ++s)
+                {
+                    if(it == 0)
+                        rc = hook(s);
+                    if(!rc)
+                        rc = pushDepositFused(c, s, border);
+                }
+                if(rc)
+                    break;
+                CU(c, cudaEventRecord(c->evBorder, c->stream));
+                CU(c, cudaStreamWaitEvent(c->side, c->evBorder, 0));
+                for(int s = 0; s < ns && !rc; ++s)
+                    rc = pushDepositFused(c, s, core);
+                if(rc)
+                    break;
+                AxisExchange const xj = axisExchange(c, PICSTEP_FIELD_J, a, -1, -1);
+                rc = exchangeBorderOverlapped(c, c->side, recLo, recHi, xj);
+                if(rc)
+                    break;
+                CU(c, cudaEventRecord(c->evComm, c->side));
+                CU(c, cudaStreamWaitEvent(c->stream, c->evComm, 0));
+                {
+                    StageTimer t(c, 2);
+                    for(int s = 0; s < ns && !rc; ++s)
+                    {
+                        SpeciesHost& sp = c->species[s];
+                        if(sp.capacity == 0)
+                            continue;
+                        if(int64_t(sp.nUpper) + recLo[s] + recHi[s] > sp.capacity)
+                        {
+                            int64_t const want = int64_t(sp.nUpper) + recLo[s] + recHi[s];
+                            rc = growSpeciesBuffers(c, sp, want + want / 4 + 4096);
+                        }
+                        if(!rc)
+                            rc = resortSpecies(c, sp, recLo[s], recHi[s]);
+                    }
+                }
+                if(!rc)
+                {
+                    StageTimer t(c, 5);
+                    rc = axisUnpack(c, fieldOf(c, PICSTEP_FIELD_J), xj, c->stream); // border += the neighbours' guard strips
+                }
+                jSplitDone = true;
+            }
+            for(int s = 0; s < ns && !rc && !commOverlap; ++s)
             {
                 if(it == 0 && (rc = hook(s)))
                     break;
@@ -1414,7 +1620,7 @@ extern "C"
                     CU(c, cudaStreamWaitEvent(c->stream, c->evMig[s], 0));
                     pendingMig[s] = false;
                 }
-                rc = pushDepositFused(c, s);
+                rc = pushDepositFused(c, s, ScArea{2, 0, 1, c->P.nsc[2]});
                 if(rc)
                     break;
                 if(overlap)
@@ -1431,12 +1637,21 @@ extern "C"
                 else
                     rc = picstep_migrate(c, s);
             }
+            // With the deposition fused into the push J is complete before the field update starts: its guard reduction
+            // is done first and the current term rides in the E update kernel (FDTD.hpp:84-85: E += coeff * J after
+            // E += curl B c^2 dt, the same two roundings in the same order) instead of a second pass over E.
+            bool const fuseJ = fused && c->fdtdTma && c->prm.current_interpolation == PICSTEP_CURRENT_INTERPOLATION_NONE;
+            if(!rc && fuseJ)
+            {
+                StageTimer t(c, 5);
+                rc = exchangeField(c, PICSTEP_FIELD_J, -1, -1, jSplitDone);
+            }
             if(!rc)
-                rc = picstep_field_update_before_current(c, step);
+                rc = fieldUpdateBeforeCurrent(c, fuseJ);
             for(int s = 0; s < ns && !rc && !fused; ++s)
                 rc = picstep_deposit(c, s);
-            if(!rc)
-                rc = picstep_add_current(c);
+            if(!rc && !fuseJ)
+                rc = addCurrentImpl(c, jSplitDone);
             if(!rc)
                 rc = picstep_field_update_after_current(c, step);
             if(rc)

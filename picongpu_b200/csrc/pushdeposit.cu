@@ -88,7 +88,8 @@ namespace picstep
         uint32_t* __restrict__ stayCnt, // FUSED: per cell, number of particles that stay in it
         uint32_t* __restrict__ key, // FUSED: destination supercell * 256 + cell (+ leave flags)
         uint32_t* __restrict__ rank, // FUSED: slot inside the destination cell: stayers first, then arrivals (bit 31)
-        const __grid_constant__ TileMaps maps) // FUSED: TMA descriptors of E and B
+        const __grid_constant__ TileMaps maps, // FUSED: TMA descriptors of E and B
+        ScArea area) // the supercells this launch covers
     {
         using Sh = Shape<SHAPE>;
         using C = RunCfg<SHAPE>;
@@ -102,8 +103,17 @@ namespace picstep
         float* const tiles = smem + (FUSED ? C::EBW : 0);
         float* const recs = tiles + C::WARPS * 3 * C::PVC;
 
-        int const sc = blockIdx.x;
-        int const scx = sc % P.nsc[0], scy = (sc / P.nsc[0]) % P.nsc[1], scz = sc / (P.nsc[0] * P.nsc[1]);
+        int sc3[3];
+        {
+            int const a1 = (area.axis + 1) % 3, a2 = (area.axis + 2) % 3;
+            int b = blockIdx.x;
+            sc3[a1] = b % P.nsc[a1];
+            b /= P.nsc[a1];
+            sc3[a2] = b % P.nsc[a2];
+            sc3[area.axis] = area.first + (b / P.nsc[a2]) * area.stride;
+        }
+        int const scx = sc3[0], scy = sc3[1], scz = sc3[2];
+        int const sc = scx + P.nsc[0] * (scy + P.nsc[1] * scz);
         uint32_t const scBeg = cellOff[sc * SCVOL], scEnd = cellOff[(sc + 1) * SCVOL];
         if(scBeg == scEnd)
             return;
@@ -791,14 +801,16 @@ namespace picstep
     }
 
     template<int SHAPE, int PUSHER, bool FUSED, int SOLVER = 0>
-    cudaError_t launchRunT(DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, TileMaps const& maps, cudaStream_t st)
+    cudaError_t launchRunT(DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, TileMaps const& maps, ScArea const& area, cudaStream_t st)
     {
-        int const nscTot = P.nsc[0] * P.nsc[1] * P.nsc[2];
+        int const nscTot = P.nsc[(area.axis + 1) % 3] * P.nsc[(area.axis + 2) % 3] * area.count;
+        if(nscTot <= 0)
+            return cudaSuccess;
         constexpr size_t smem = runSmemBytes<SHAPE, FUSED>();
         cudaError_t e = cudaFuncSetAttribute(runKernel<SHAPE, PUSHER, FUSED, SOLVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if(e != cudaSuccess)
             return e;
-        runKernel<SHAPE, PUSHER, FUSED, SOLVER><<<nscTot, 256, smem, st>>>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps);
+        runKernel<SHAPE, PUSHER, FUSED, SOLVER><<<nscTot, 256, smem, st>>>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps, area);
         return cudaGetLastError();
     }
 
@@ -813,9 +825,10 @@ namespace picstep
     {
         Field3 none{};
         TileMaps const noMaps{};
+        ScArea const whole{2, 0, 1, P.nsc[2]};
 #define PS_CASE(SH, SO)                                                                                               \
     if(shape == SH && solver == SO)                                                                                   \
-        return launchRunT<SH, 0, false, SO>(P, S, S, nullptr, none, none, J, cellOff, nullptr, nullptr, nullptr, nullptr, noMaps, st);
+        return launchRunT<SH, 0, false, SO>(P, S, S, nullptr, none, none, J, cellOff, nullptr, nullptr, nullptr, nullptr, noMaps, whole, st);
         PS_CASE(0, 0)
         PS_CASE(1, 0)
         PS_CASE(2, 0)
@@ -828,13 +841,13 @@ namespace picstep
     }
 
     /** fused gather + push + move + deposit of one species (picstep_step fast path) */
-    cudaError_t launchPushDeposit(int shape, int pusher, int solver, DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, TileMaps const& maps, cudaStream_t st)
+    cudaError_t launchPushDeposit(int shape, int pusher, int solver, DevParams const& P, SpeciesDev const& S, SpeciesDev const& D, uint32_t const* inv, Field3 E, Field3 B, Field3 J, uint32_t const* cellOff, uint32_t* cellCnt, uint32_t* stayCnt, uint32_t* key, uint32_t* rank, TileMaps const& maps, ScArea const& area, cudaStream_t st)
     {
 #define PS_CASE(SH, PU)                                                                                               \
     if(shape == SH && pusher == PU && solver == 0)                                                                    \
-        return launchRunT<SH, PU, true, 0>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps, st);         \
+        return launchRunT<SH, PU, true, 0>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps, area, st);   \
     if(shape == SH && pusher == PU && solver == 1 && SH >= 1)                                                         \
-        return launchRunT<(SH >= 1 ? SH : 1), PU, true, 1>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps, st);
+        return launchRunT<(SH >= 1 ? SH : 1), PU, true, 1>(P, S, D, inv, E, B, J, cellOff, cellCnt, stayCnt, key, rank, maps, area, st);
         PS_CASE(0, 0)
         PS_CASE(1, 0)
         PS_CASE(2, 0)

@@ -202,13 +202,13 @@ class Simulation:
     issuing the stage calls in the order of Simulation::runOneStep.
     """
 
-    def __init__(self, params, device=0, exact=False, atomic_deposit=False, cell_deposit=False, unfused=False):
+    def __init__(self, params, device=0, exact=False, atomic_deposit=False, cell_deposit=False, unfused=False, no_fdtd_tma=False):
         self.p = params
         self.L = load(exact)
         self.ctx = C.c_void_p()
         # picstep_params.flags: bit0 reference-strategy atomic deposit, bit1 warp-per-cell deposit kernel,
-        # bit2 picstep_step without push+deposit fusion
-        cp = to_c_params(params, device, (1 if atomic_deposit else 0) | (2 if cell_deposit else 0) | (4 if unfused else 0))
+        # bit2 picstep_step without push+deposit fusion, bit4 Yee update with the one-thread-per-cell kernels (no TMA bricks)
+        cp = to_c_params(params, device, (1 if atomic_deposit else 0) | (2 if cell_deposit else 0) | (4 if unfused else 0) | (16 if no_fdtd_tma else 0))
         rc = self.L.picstep_create(C.byref(cp), C.byref(self.ctx))
         if rc:
             raise PicstepError("picstep_create failed (%d): %s" % (rc, self.L.picstep_last_error(None).decode()))

@@ -343,6 +343,74 @@ def test_field_solver(orc, solver, dir, exact):
     s.close()
 
 
+@pytest.mark.parametrize("exact", [True, False])
+def test_yee_tma_bricks_equal_per_cell_kernels(orc, exact):
+    """The TMA-staged brick kernels of the Yee update (fields.cu: fdtdTmaKernel, incl. the E update with the current
+    term fused in) against the one-thread-per-cell kernels and the oracle, on a grid that needs several bricks in
+    every direction and masked brick columns at both x ends (136 = 2 x 64 + 8 cells)."""
+    p = util.make_params((136, 24, 12))
+    E, B = util.smooth_fields(p, seed=51)
+    rng = np.random.RandomState(4)
+    J = util.pad_periodic(rng.normal(size=(3, 12, 24, 136)).astype(np.float32), p.guard_cells)
+    Jz = np.zeros_like(J)
+    o = orc.Oracle(p)
+    o.interior(Jz)[...] = o.interior(J)
+    res = []
+    for no_tma in (False, True):
+        s = _sim(p, exact, no_fdtd_tma=no_tma)
+        s.upload_field(FE, E)
+        s.upload_field(FB, B)
+        for _ in range(2):
+            s.upload_field(FJ, Jz)
+            s.field_update_before_current()
+            s.add_current()
+            s.field_update_after_current()
+        res.append((s.download_field(FE), s.download_field(FB)))
+        s.close()
+    Eo, Bo = E.copy(), B.copy()
+    for _ in range(2):
+        o.update_b_half(Eo, Bo)
+        o.guard_copy(Bo)
+        o.update_e(Eo, Bo)
+        o.add_current(Eo, J)
+        o.guard_copy(Eo)
+        o.update_b_half(Eo, Bo)
+        o.guard_copy(Bo)
+    for Eg, Bg in res:
+        if exact:
+            assert np.array_equal(o.interior(Eg), o.interior(Eo)) and np.array_equal(o.interior(Bg), o.interior(Bo))
+        else:
+            assert _relerr(o.interior(Eg), o.interior(Eo)) < 2e-6 and _relerr(o.interior(Bg), o.interior(Bo)) < 2e-6
+    if exact:
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_fused_current_term_equals_separate_pass(orc, exact):
+    """picstep_step adds the current inside the E update kernel (J is complete before the field update when the
+    deposition is fused into the push); the stage calls add it in a separate pass like the reference.  Same two
+    roundings in the same order: bit-identical E in the exact build."""
+    p = util.make_params((24, 16, 8))
+    o, e, i = util.khi_ic(orc, p)
+    res = []
+    for staged in (False, True):
+        s = _sim(p, exact)
+        for name, sp in (("e", e), ("i", i)):
+            s.upload_particles(name, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+        if staged:
+            for _ in range(3):
+                s.run_one_step()
+        else:
+            s.step(3)
+        s.sync()
+        res.append((s.download_field(FE), s.download_field(FB)))
+        s.close()
+    _, escale = util.khi_scales(p, 3)
+    for a, b in zip(res[0], res[1]):
+        # J itself is summed in another order by the stand-alone deposition (run order vs processing order)
+        assert np.abs(o.interior(a) - o.interior(b)).max() / escale < 1e-5
+
+
 def test_plane_wave_dispersion():
     """Known answer: a vacuum plane wave along x keeps its energy and advances with the Yee phase velocity."""
     p = util.make_params((64, 8, 8))
