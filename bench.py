@@ -86,20 +86,54 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-VARIANT = {"shape": "TSC", "pusher": "Boris", "current": "Esirkepov", "solver": "Yee", "interp": "none"}
+VARIANT = {"shape": "TSC", "pusher": "Boris", "current": "Esirkepov", "solver": "Yee", "interp": "none", "config": "khi"}
+
+# BASELINE.json configurations.  khi = C2 (the headline, C1 at 64^3); the others are the same kernels with other
+# template arguments / boundaries and are benchmark lines kept under profiles/, not the driver's default:
+#   thermal   C5  share/picongpu/benchmarks/Thermal: electrons only, uniform, T = 17.5 * 511 keV (relativistic: c dt / dx = 0.5,
+#                 every particle crosses cells all the time), Boris as the north star says (the benchmark default is HigueraCary)
+#   lwfa_like C3  LaserWakefield's kernels and boundaries (CIC, open + absorbing y, cell sizes with c dt / dy = 0.94) on the KHI
+#                 plasma -- WITHOUT the laser (incident-field source not built): it measures the step, not wakefield physics
+#   foil_like C4  PQS + Lehe + Binomial current smoothing (the "high-order deposition stress test") on the KHI plasma
+CONFIGS = {
+    "khi": {},
+    "thermal": dict(shape="TSC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
+    "lwfa_like": dict(shape="CIC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
+    "foil_like": dict(shape="PQS", pusher="Boris", current="Esirkepov", solver="Lehe", interp="binomial"),
+}
+
+
+def n_species():
+    return 1 if VARIANT["config"] == "thermal" else 2
 
 
 def workload_name(grid, ppc, n):
     v = VARIANT
     extra = "" if v["interp"] == "none" else "_Binomial"
-    return "KelvinHelmholtz3D_%dx%dx%d_per_gpu_%d+%dppc_%s_%s_%s_%s%s_periodic_d1x%dx1" % (
-        grid[0], grid[1], grid[2], ppc, ppc, v["shape"], v["pusher"], v["current"], v["solver"], extra, n)
+    if v["config"] == "thermal":
+        return "Thermal3D_%dx%dx%d_per_gpu_%dppc_electrons_T17.5mc2_%s_%s_%s_%s%s_periodic_d1x%dx1" % (
+            grid[0], grid[1], grid[2], ppc, v["shape"], v["pusher"], v["current"], v["solver"], extra, n)
+    head = {"khi": "KelvinHelmholtz3D", "lwfa_like": "LaserWakefieldLike3D_noLaser_KHIplasma_open_y", "foil_like": "FoilLCTLike3D_KHIplasma"}[v["config"]]
+    return "%s_%dx%dx%d_per_gpu_%d+%dppc_%s_%s_%s_%s%s_%s_d1x%dx1" % (
+        head, grid[0], grid[1], grid[2], ppc, ppc, v["shape"], v["pusher"], v["current"], v["solver"], extra,
+        "periodic" if v["config"] != "lwfa_like" else "absorbing_y", n)
 
 
 def variant_kwargs():
     v = VARIANT
-    return dict(shape=prm.SHAPE_NAMES[v["shape"]], pusher=prm.PUSHER_NAMES[v["pusher"]], current_solver=prm.CURRENT_NAMES[v["current"]],
-                field_solver=prm.SOLVER_NAMES[v["solver"]], current_interpolation=1 if v["interp"] == "binomial" else 0)
+    kw = dict(shape=prm.SHAPE_NAMES[v["shape"]], pusher=prm.PUSHER_NAMES[v["pusher"]], current_solver=prm.CURRENT_NAMES[v["current"]],
+              field_solver=prm.SOLVER_NAMES[v["solver"]], current_interpolation=1 if v["interp"] == "binomial" else 0)
+    if v["config"] == "lwfa_like":
+        # share/picongpu/examples/LaserWakefield/include/picongpu/param/simulation.param: dt = 1.39e-16 s, cells 0.1772 um x
+        # 0.4430e-7 m x 0.1772 um (c dt / dy = 0.94); --periodic 1 0 1, exponential absorber on the open axis
+        kw.update(periodic=(1, 0, 1), absorber_kind=1, delta_t_si=1.39e-16, cell_si=(0.1772e-6, 0.4430e-7, 0.1772e-6))
+    return kw
+
+
+def make_params(grid, **kw):
+    if VARIANT["config"] == "thermal":
+        return prm.thermal_params(grid=grid, **kw)
+    return prm.khi_params(grid=grid, **kw)
 
 
 # -------------------------------------------------------------------------------------------------------------------
@@ -277,7 +311,7 @@ def run_ours(args):
         if grid[1] % (8 * world) or grid[1] // world < 16:
             raise SystemExit("strong scaling: the global y extent must split into >= 2 supercells per GPU")
         grid = (grid[0], grid[1] // world, grid[2])
-    p = prm.khi_params(grid=grid, devices=(1, world, 1), rank_pos=(0, rank, 0), **variant_kwargs())
+    p = make_params(grid, devices=(1, world, 1), rank_pos=(0, rank, 0), **variant_kwargs())
     sim = picstep.Simulation(p, device=local, exact=False)
     if world > 1:
         if rank == 0:
@@ -287,11 +321,18 @@ def run_ours(args):
         t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
         dist.broadcast(t, 0)
         sim.comm_init(bytes(t.cpu().tolist()), rank, world)
-    ppc_dim = {25: (5, 5, 1), 16: (4, 4, 1), 9: (3, 3, 1), 8: (2, 2, 2), 4: (2, 2, 1), 1: (1, 1, 1)}[args.ppc]
-    sim.init_khi(ppc_dim=ppc_dim)
+    ppc_dim = {25: (5, 5, 1), 16: (4, 4, 1), 9: (3, 3, 1), 8: (2, 2, 2), 4: (2, 2, 1), 3: (3, 1, 1), 2: (2, 1, 1), 1: (1, 1, 1)}[args.ppc]
+    names = [sp.name for sp in p.species]
+
+    def init(sm):
+        if VARIANT["config"] == "thermal":
+            sm.init_thermal("e", args.ppc)
+        else:
+            sm.init_khi(ppc_dim=ppc_dim)
+
+    init(sim)
     ncell = grid[0] * grid[1] * grid[2]
-    n_e, n_i = sim.particle_count("e"), sim.particle_count("i")
-    npart = n_e + n_i
+    npart = sum(sim.particle_count(nm) for nm in names)
     stream = torch.cuda.ExternalStream(sim.stream(), device=dev)
 
     def barrier():
@@ -303,6 +344,7 @@ def run_ours(args):
     # ---- device resident: W warm-up + K timed steps ------------------------------------------------------------
     sim.step(args.warmup)
     barrier()
+    sim.slow_path_counts()  # reset
     sim.stage_times(True)  # reset + enable asynchronous per-stage events
     l0 = sim.launch_count()
     sampler = ClockSampler(local)
@@ -321,26 +363,32 @@ def run_ours(args):
         tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
-        cnt = torch.tensor([float(sim.particle_count("e") + sim.particle_count("i"))], device=dev, dtype=torch.float64)
+        cnt = torch.tensor([float(sum(sim.particle_count(nm) for nm in names))], device=dev, dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         npart_total = float(cnt.item())
     else:
-        npart_total = float(sim.particle_count("e") + sim.particle_count("i"))
+        npart_total = float(sum(sim.particle_count(nm) for nm in names))
     ms_step = ms_total / args.steps
     value = npart_total / (ms_step * 1e-3)
 
+    wide, plane = sim.slow_path_counts()
+    slow_path = {"wide_trajectories_per_update": wide / (npart * args.steps), "pqs_plane_trajectories_per_update": plane / (npart * args.steps),
+                 "note": "fraction of macro-particle updates of this rank whose current went through the global-atomic path of the fused kernel"}
     # size independent properties at the benchmark size: particle conservation (periodic), Gauss residual at round-off
     checks = {"particles_conserved": bool(abs(npart_total - npart * world) < 0.5)}
+    if VARIANT["config"] == "lwfa_like":
+        checks["particles_conserved"] = None  # open y faces absorb particles
+        checks["particles_left"] = npart_total / (npart * world)
     checks["multi_gpu_vs_oracle"] = parity
     try:
         gr = sim.gauss_residual()
-        checks["gauss_residual_over_cell_charge"] = gr / (25.0 * abs(p.base_charge) * p.typical_num_particles_per_macro)
+        checks["gauss_residual_over_cell_charge"] = gr / (float(args.ppc) * abs(p.base_charge) * p.real_particles_per_cell / args.ppc)
     except Exception as ex:  # pragma: no cover
         checks["gauss_error"] = str(ex)
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------
     peak, peak_kind = measured_peaks()
-    nspec = 2
+    nspec = n_species()
     fused = stage["deposit"] == 0.0  # picstep_step fast path: gather+push+move+deposit in one kernel (runKernel)
     if fused:
         per_launch = {
@@ -388,14 +436,14 @@ def run_ours(args):
                 egrid[1] //= 2
             if tuple(egrid) != grid:
                 sim.close()
-                p = prm.khi_params(grid=tuple(egrid), devices=(1, world, 1), rank_pos=(0, rank, 0), **variant_kwargs())
+                p = make_params(tuple(egrid), devices=(1, world, 1), rank_pos=(0, rank, 0), **variant_kwargs())
                 sim = picstep.Simulation(p, device=local, exact=False)
                 if world > 1:
                     uid = sim.comm_unique_id() if rank == 0 else bytes(128)
                     t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
                     dist.broadcast(t, 0)
                     sim.comm_init(bytes(t.cpu().tolist()), rank, world)
-                sim.init_khi(ppc_dim=ppc_dim)
+                init(sim)
                 sim.step(3)
                 sim.sync()
                 stream = torch.cuda.ExternalStream(sim.stream(), device=dev)
@@ -439,6 +487,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),
+            "slow_path": slow_path,
             "clocks": sampler.summary(),
             "checks": checks,
         }
@@ -457,7 +506,7 @@ def run_e2e(sim, p, args, stream, world, local, dev):
     from picongpu_b200 import picstep
 
     sp = []
-    for name in ("e", "i"):
+    for name in [sp.name for sp in p.species]:
         n = sim.particle_count(name)
         arrs = [torch.empty((3, n), dtype=torch.float32).pin_memory(), torch.empty((3, n), dtype=torch.float32).pin_memory(),
                 torch.empty((n,), dtype=torch.float32).pin_memory(), torch.empty((n,), dtype=torch.int32).pin_memory()]
@@ -508,10 +557,15 @@ def main():
     ap.add_argument("--current", default="Esirkepov", choices=["Esirkepov", "EmZ"])
     ap.add_argument("--solver", default="Yee", choices=sorted(prm.SOLVER_NAMES))
     ap.add_argument("--interp", default="none", choices=["none", "binomial"])
+    ap.add_argument("--config", default="khi", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: the KHI headline)")
     args = ap.parse_args()
-    VARIANT.update(shape=args.shape, pusher=args.pusher, current=args.current, solver=args.solver, interp=args.interp)
+    VARIANT.update(shape=args.shape, pusher=args.pusher, current=args.current, solver=args.solver, interp=args.interp, config=args.config)
+    VARIANT.update(CONFIGS[args.config])
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.config != "khi":  # the CPU arm and the N-rank oracle check are the KHI headline's
+        args.no_cpu = True
+        args.no_parity = True
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

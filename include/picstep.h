@@ -85,7 +85,10 @@ extern "C"
         PICSTEP_REDUCE_FIELD_ENERGY = 0, /* out[0]=B energy, out[1]=E energy   (plugins/EnergyFields.x.cpp:198-233) */
         PICSTEP_REDUCE_PARTICLE_ENERGY = 1, /* out[0]=kinetic, out[1]=total, needs `species` (EnergyParticles.x.cpp:100-131) */
         PICSTEP_REDUCE_GAUSS = 2, /* out[0]=max|eps0 div E - rho|*V     (plugins/ChargeConservation.tpp:181-259) */
-        PICSTEP_REDUCE_PARTICLE_COUNT = 3 /* out[0]=number of macro particles of `species` */
+        PICSTEP_REDUCE_PARTICLE_COUNT = 3, /* out[0]=number of macro particles of `species` */
+        /* out[0]=trajectories the fused kernel deposited through its global-atomic path since the last call (too wide for
+         * the four-node window), out[1]=PQS trajectories that sent one plane of nodes that way; resets the counters */
+        PICSTEP_REDUCE_SLOW_PATH = 4
     };
 
     /* The `.param` surface of the hot path as runtime values (all physical values in PIC units, i.e. what
@@ -165,6 +168,10 @@ extern "C"
     /* Synthetic KelvinHelmholtz initial condition generated on the device (bench input; same recipe and Philox
      * stream as the oracle's orc_khi_init): species 0 = electrons, 1 = ions; ppc = ppc_dim[0]*[1]*[2] each. */
     int picstep_init_khi(picstep_ctx* ctx, const int32_t* ppc_dim, float real_particles_per_cell, double gamma_drift, double temperature_keV, double ev_pic, uint32_t seed);
+    /* Synthetic uniform warm plasma of one species generated on the device (bench input for the Thermal benchmark,
+     * share/picongpu/benchmarks/Thermal/include/picongpu/param/{particle,speciesInitialization}.param: `ppc` particles
+     * per cell at random in-cell positions, Maxwellian momenta of the given temperature, no drift). */
+    int picstep_init_thermal(picstep_ctx* ctx, int32_t species, int32_t ppc, float real_particles_per_cell, double temperature_keV, double ev_pic, uint32_t seed);
 
     /* ---- stage calls, in the order of Simulation::runOneStep (Simulation.hpp:526-541) ---- */
     /* CurrentReset              (simulation/stage/CurrentReset.hpp:45-52) */

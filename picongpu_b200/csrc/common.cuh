@@ -69,6 +69,10 @@ namespace picstep
         // axis is periodic / has a neighbour rank on that side, only the active cells where it ends at an open boundary
         // (the reference has no edge / corner exchange across a missing neighbour, Mask::getRelativeDirections)
         int tlo[3], thi[3];
+        // [0] trajectories deposited through the global-atomic path of the run kernel (too wide for the node window),
+        // [1] PQS trajectories that sent one plane of nodes through global atomics; read and reset by
+        // picstep_reduce(PICSTEP_REDUCE_SLOW_PATH)
+        unsigned long long* stats;
     };
 
     // exponential field absorber: thickness per [axis][side] (0 where the face is not absorbing) and the tabulated

@@ -87,6 +87,55 @@ namespace picstep
         }
     }
 
+    // Uniform warm plasma of ONE species (share/picongpu/benchmarks/Thermal: homogeneous density, `ppc` particles per cell
+    // at random in-cell positions (startPosition::Random, RandomImpl.hpp), Maxwellian momenta with standard deviation
+    // `stddev` per axis (Temperature.hpp:63-87)).  Philox counters: (global particle id, 0) momenta as in the KHI
+    // generator, (global particle id, 1) positions.  Written directly in frame-run order.
+    __global__ void __launch_bounds__(256) thermalInitKernel(DevParams P, SpeciesDev S, uint32_t* __restrict__ off, KhiArgs A)
+    {
+        int const ncell = P.nsc[0] * P.nsc[1] * P.nsc[2] * SCVOL;
+        int const key = blockIdx.x * blockDim.x + threadIdx.x;
+        int const ppc = A.ppc[0];
+        if(key == 0)
+            off[ncell] = uint32_t(ncell) * ppc;
+        if(key >= ncell)
+            return;
+        off[key] = uint32_t(key) * ppc;
+        int const sc = key / SCVOL, lc = key % SCVOL;
+        int const scx = sc % P.nsc[0], scy = (sc / P.nsc[0]) % P.nsc[1], scz = sc / (P.nsc[0] * P.nsc[1]);
+        int const cx = scx * SCX + lc % SCX, cy = scy * SCY + (lc / SCX) % SCY, cz = scz * SCZ + lc / (SCX * SCY);
+        unsigned long long const gcell = (unsigned long long) (cx + A.globalOff[0])
+            + (unsigned long long) A.globalN[0] * ((unsigned long long) (cy + A.globalOff[1]) + (unsigned long long) A.globalN[1] * (unsigned long long) (cz + A.globalOff[2]));
+        for(int k = 0; k < ppc; ++k)
+        {
+            uint32_t const i = uint32_t(key) * ppc + k;
+            unsigned long long const gid = gcell * (unsigned long long) ppc + (unsigned long long) k;
+            uint32_t ctr[4] = {uint32_t(gid), uint32_t(gid >> 32), 1u, 0u};
+            philox4x32_10(ctr, A.seed, 0u);
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+                S.pos[d][i] = fminf(u01(ctr[d]), 1.0f - 1.0f / 16777216.0f);
+            S.w[i] = A.weighting;
+            S.cell[i] = uint16_t(lc);
+            uint32_t c2[4] = {uint32_t(gid), uint32_t(gid >> 32), 0u, 0u};
+            philox4x32_10(c2, A.seed, 0u);
+            float const r0 = sqrtf(-2.0f * logf(u01(c2[0])));
+            float const r1 = sqrtf(-2.0f * logf(u01(c2[2])));
+            float const a0 = 6.283185307179586f * u01(c2[1]);
+            float const a1 = 6.283185307179586f * u01(c2[3]);
+            S.mom[0][i] = (r0 * cosf(a0)) * A.stddev;
+            S.mom[1][i] = (r0 * sinf(a0)) * A.stddev;
+            S.mom[2][i] = (r1 * cosf(a1)) * A.stddev;
+        }
+    }
+
+    cudaError_t launchThermalInit(DevParams const& P, SpeciesDev S, uint32_t* off, KhiArgs const& A, cudaStream_t st)
+    {
+        int const ncell = P.nsc[0] * P.nsc[1] * P.nsc[2] * SCVOL;
+        thermalInitKernel<<<(ncell + 255) / 256, 256, 0, st>>>(P, S, off, A);
+        return cudaGetLastError();
+    }
+
     cudaError_t launchKhiInit(DevParams const& P, SpeciesDev E, SpeciesDev I, uint32_t* offE, uint32_t* offI, KhiArgs const& A, cudaStream_t st)
     {
         int const ncell = P.nsc[0] * P.nsc[1] * P.nsc[2] * SCVOL;

@@ -54,6 +54,7 @@ namespace picstep
     cudaError_t launchChargeDensity(int, DevParams const&, SpeciesDev, uint32_t const*, float*, cudaStream_t);
     cudaError_t launchGaussResidual(DevParams const&, Field3, float const*, int*, cudaStream_t);
     cudaError_t launchKhiInit(DevParams const&, SpeciesDev, SpeciesDev, uint32_t*, uint32_t*, KhiArgs const&, cudaStream_t);
+    cudaError_t launchThermalInit(DevParams const&, SpeciesDev, uint32_t*, KhiArgs const&, cudaStream_t);
 
     // NCCL transport (comm.cu)
     struct Comm;
@@ -852,6 +853,8 @@ extern "C"
         CUC(cudaMemcpy(c->dampDev, damp.data(), sizeof(float) * damp.size(), cudaMemcpyHostToDevice));
         c->absorber.damp = c->dampDev;
         CUC(cudaMalloc(&c->redBuf, sizeof(double) * 4));
+        CUC(cudaMalloc(&c->P.stats, sizeof(unsigned long long) * 4));
+        CUC(cudaMemsetAsync(c->P.stats, 0, sizeof(unsigned long long) * 4, c->stream));
         CUC(cudaMalloc(&c->flags, sizeof(int) * 4));
         CUC(cudaMemsetAsync(c->flags, 0, sizeof(int) * 4, c->stream));
         CUC(cudaMallocHost(&c->hostPinned, sizeof(double) * 8)); // 16 words: [0..7] readbacks, [8..10] peekFlags
@@ -894,6 +897,7 @@ extern "C"
         for(int b = 0; b < 4; ++b)
             cudaFree(c->haloBuf[b]);
         cudaFree(c->redBuf);
+        cudaFree(c->P.stats);
         cudaFree(c->dampDev);
         cudaFree(c->flags);
         if(c->hostPinned)
@@ -1184,6 +1188,42 @@ extern "C"
         A.stddev = stddev;
         A.seed = seed;
         KL(c, 1, launchKhiInit(c->P, devOf(c, e, e.cur), devOf(c, i, i.cur), e.cellOff[e.cur], i.cellOff[i.cur], A, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        return PICSTEP_OK;
+    }
+
+    int picstep_init_thermal(picstep_ctx* c, int32_t sp, int32_t ppc, float realPPC, double temperature_keV, double ev_pic, uint32_t seed)
+    {
+        if(!c || sp < 0 || sp >= int(c->species.size()) || ppc < 1)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        SpeciesHost& s = c->species[sp];
+        int64_t const n = int64_t(numCells(c)) * ppc;
+        if(n > s.capacity)
+        {
+            // a relativistic thermal plasma piles up / thins out by a few per cent only: 12 % head room
+            int const rc = allocSpeciesBuffers(c, s, n + n / 8);
+            if(rc)
+                return rc;
+        }
+        s.nUpper = uint32_t(n);
+        s.lazy = false;
+        s.ranked = false;
+        uint32_t const n32 = uint32_t(n);
+        CU(c, cudaMemcpyAsync(s.nDev + s.cur, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        KhiArgs A{};
+        for(int d = 0; d < 3; ++d)
+        {
+            A.ppc[d] = d == 0 ? ppc : 1;
+            A.globalN[d] = c->prm.grid[d] * c->prm.devices[d];
+            A.globalOff[d] = c->prm.grid[d] * c->prm.rank_pos[d];
+        }
+        A.weighting = realPPC / float(ppc);
+        float const mass = (c->prm.base_mass * s.massRatio) * A.weighting;
+        float const energy = float(ev_pic * (temperature_keV * 1.0e3));
+        A.stddev = std::sqrt((A.weighting * energy) * mass); // Temperature.hpp:75-80
+        A.seed = seed;
+        KL(c, 1, launchThermalInit(c->P, devOf(c, s, s.cur), s.cellOff[s.cur], A, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
         return PICSTEP_OK;
     }
@@ -1776,7 +1816,7 @@ extern "C"
             return PICSTEP_OK;
         }
         if(sp < 0 || sp >= int(c->species.size()))
-            if(what != PICSTEP_REDUCE_GAUSS)
+            if(what != PICSTEP_REDUCE_GAUSS && what != PICSTEP_REDUCE_SLOW_PATH)
                 return PICSTEP_ERR_INVALID;
         if(what == PICSTEP_REDUCE_PARTICLE_ENERGY)
         {
@@ -1789,6 +1829,16 @@ extern "C"
             double const* r = reinterpret_cast<double const*>(c->hostPinned);
             out[0] = r[0];
             out[1] = r[1];
+            return PICSTEP_OK;
+        }
+        if(what == PICSTEP_REDUCE_SLOW_PATH)
+        {
+            CU(c, cudaMemcpyAsync(c->hostPinned, c->P.stats, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaMemsetAsync(c->P.stats, 0, sizeof(unsigned long long) * 2, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            unsigned long long const* r = reinterpret_cast<unsigned long long const*>(c->hostPinned);
+            out[0] = double(r[0]);
+            out[1] = double(r[1]);
             return PICSTEP_OK;
         }
         if(what == PICSTEP_REDUCE_PARTICLE_COUNT)

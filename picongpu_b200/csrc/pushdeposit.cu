@@ -446,6 +446,7 @@ namespace picstep
                         else
                         {
                             // wide trajectory: the reference loops with global atomics, per segment
+                            atomicAdd(P.stats, 1ull);
                             long long const sY = P.N[0], sZ = (long long) P.N[0] * P.N[1];
                             long long const oa = fidx(P, scx * SCX + P.g[0] + lx + dir[0] + cA[0], scy * SCY + P.g[1] + ly + dir[1] + cA[1], scz * SCZ + P.g[2] + lz + dir[2] + cA[2]);
                             emzSegmentGlobal<SHAPE>(J.c[0] + oa, J.c[1] + oa, J.c[2] + oa, sY, sZ, a0[0], a0[1], a0[2], a1[0], a1[1], a1[2], csd * P.cell[0], csd * P.cell[1], csd * P.cell[2]);
@@ -554,6 +555,7 @@ namespace picstep
                         if constexpr(SEMI)
                             if(axOut >= 0)
                             {
+                                atomicAdd(P.stats + 1, 1ull);
                                 // the plane of nodes outside the window: J_A at the node next to it along A (16 values)
                                 // and the two transverse components on the plane itself (2 x 12 values)
                                 int const A = axOut, iA = (A + 1) % 3, jA = (A + 2) % 3;
@@ -598,6 +600,7 @@ namespace picstep
                     else
                     {
                         // wide trajectory: reference loop with global atomics, in the frame of the particle's new cell
+                        atomicAdd(P.stats, 1ull);
                         int const baseG[3]
                             = {scx * SCX + P.g[0] + lx + dir[0] + gs3[0], scy * SCY + P.g[1] + ly + dir[1] + gs3[1], scz * SCZ + P.g[2] + lz + dir[2] + gs3[2]};
                         long long const origin = fidx(P, baseG[0], baseG[1], baseG[2]);

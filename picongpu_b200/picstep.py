@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBS = {}
 
 FIELD_E, FIELD_B, FIELD_J = 0, 1, 2
-REDUCE_FIELD_ENERGY, REDUCE_PARTICLE_ENERGY, REDUCE_GAUSS, REDUCE_PARTICLE_COUNT = 0, 1, 2, 3
+REDUCE_FIELD_ENERGY, REDUCE_PARTICLE_ENERGY, REDUCE_GAUSS, REDUCE_PARTICLE_COUNT, REDUCE_SLOW_PATH = 0, 1, 2, 3, 4
 STAGES = ["current_reset", "push", "migrate", "field_before", "deposit", "add_current", "field_after"]
 
 # every symbol include/picstep.h declares (checked by tests/test_abi.py)
@@ -23,7 +23,7 @@ SYMBOLS = [
     "picstep_version", "picstep_last_error", "picstep_create", "picstep_destroy", "picstep_species_add",
     "picstep_fields_upload", "picstep_fields_download", "picstep_fields_upload_soa", "picstep_fields_download_soa",
     "picstep_particles_upload", "picstep_particles_count", "picstep_particles_download", "picstep_supercell_counts",
-    "picstep_init_khi", "picstep_current_reset", "picstep_push", "picstep_migrate",
+    "picstep_init_khi", "picstep_init_thermal", "picstep_current_reset", "picstep_push", "picstep_migrate",
     "picstep_field_update_before_current", "picstep_deposit", "picstep_add_current",
     "picstep_field_update_after_current", "picstep_field_exchange", "picstep_step", "picstep_step_host",
     "picstep_sync", "picstep_reduce", "picstep_debug_gather", "picstep_comm_unique_id", "picstep_comm_init",
@@ -102,6 +102,7 @@ def load(exact=False):
     L.picstep_particles_download.argtypes = [vp, i32, i64, vp, vp, vp, vp, C.POINTER(i64)]
     L.picstep_supercell_counts.argtypes = [vp, i32, vp]
     L.picstep_init_khi.argtypes = [vp, C.POINTER(i32 * 3), f32, C.c_double, C.c_double, C.c_double, u32]
+    L.picstep_init_thermal.argtypes = [vp, i32, i32, f32, C.c_double, C.c_double, u32]
     L.picstep_current_reset.argtypes = [vp]
     L.picstep_push.argtypes = [vp, i32, u32]
     L.picstep_migrate.argtypes = [vp, i32]
@@ -287,6 +288,11 @@ class Simulation:
         p = self.p
         self._chk(self.L.picstep_init_khi(self.ctx, C.byref((C.c_int32 * 3)(*ppc_dim)), p.real_particles_per_cell, gamma, temperature_keV, p.ev_pic, seed), "init_khi")
 
+    def init_thermal(self, species, ppc, temperature_keV=17.5 * 510.998950, seed=42):
+        """Uniform warm plasma (Thermal benchmark: `temperature = 17.5 * 510.998950` keV, particle.param:77)."""
+        p = self.p
+        self._chk(self.L.picstep_init_thermal(self.ctx, self._sid(species), ppc, p.real_particles_per_cell, temperature_keV, p.ev_pic, seed), "init_thermal")
+
     # -- fields --------------------------------------------------------------------------------------------------
     def upload_field(self, field, soa):
         soa = np.ascontiguousarray(soa, np.float32)
@@ -378,7 +384,7 @@ class Simulation:
     # -- diagnostics ---------------------------------------------------------------------------------------------
     def reduce(self, what, species=0):
         out = (C.c_double * 2)()
-        self._chk(self.L.picstep_reduce(self.ctx, what, self._sid(species) if what != REDUCE_GAUSS else 0, out), "reduce")
+        self._chk(self.L.picstep_reduce(self.ctx, what, self._sid(species) if what not in (REDUCE_GAUSS, REDUCE_SLOW_PATH) else 0, out), "reduce")
         return np.array([out[0], out[1]])
 
     def field_energy(self):
@@ -386,6 +392,11 @@ class Simulation:
 
     def particle_energy(self, species):
         return self.reduce(REDUCE_PARTICLE_ENERGY, species)
+
+    def slow_path_counts(self):
+        """(wide trajectories, PQS one-plane trajectories) deposited through global atomics since the last call."""
+        r = self.reduce(REDUCE_SLOW_PATH)
+        return int(r[0]), int(r[1])
 
     def gauss_residual(self):
         return float(self.reduce(REDUCE_GAUSS)[0])

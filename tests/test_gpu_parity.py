@@ -662,6 +662,35 @@ def test_device_khi_init_matches_oracle_generator(orc):
     s.close()
 
 
+def test_device_thermal_init_statistics():
+    """picstep_init_thermal (bench input of the Thermal benchmark): ppc particles in every cell, positions uniform in
+    the cell, momenta Maxwellian with sqrt(weighting * kT * mass) per axis (Temperature.hpp:75-80), and the
+    relativistic plasma steps (cell crossings on every axis, trajectories up to half a cell per step)."""
+    p = prm.thermal_params(grid=(32, 16, 8))
+    s = _sim(p, False)
+    ppc = 6
+    s.init_thermal("e", ppc)
+    pos, mom, w, cell = s.download_particles("e")
+    ncell = 32 * 16 * 8
+    assert w.shape[0] == ncell * ppc and np.array_equal(np.bincount(cell, minlength=ncell), np.full(ncell, ppc))
+    assert pos.min() >= 0.0 and pos.max() < 1.0 and abs(pos.mean() - 0.5) < 0.01
+    weighting = p.real_particles_per_cell / ppc
+    assert np.allclose(w, weighting, rtol=1e-6)
+    kT = p.ev_pic * 17.5 * 510.998950e3
+    sigma = np.sqrt(weighting * kT * p.base_mass * weighting)
+    for c in range(3):
+        assert abs(mom[c].std() / sigma - 1.0) < 0.02 and abs(mom[c].mean()) < 0.03 * sigma
+    e0 = s.field_energy().sum() + s.particle_energy("e")[0]
+    s.step(20)
+    s.sync()
+    assert s.particle_count("e") == ncell * ppc
+    wide, _ = s.slow_path_counts()
+    e1 = s.field_energy().sum() + s.particle_energy("e")[0]
+    print("thermal: wide trajectories per update %.4f, energy drift %.2e" % (wide / (20.0 * ncell * ppc), (e1 - e0) / e0))
+    assert abs(e1 - e0) / e0 < 1e-3
+    s.close()
+
+
 def test_step_host_matches_device_resident(orc):
     p = util.make_params((16, 16, 8))
     o, e, i = util.khi_ic(orc, p)
