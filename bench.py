@@ -100,18 +100,22 @@ CONFIGS = {
     "thermal": dict(shape="TSC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
     "lwfa_like": dict(shape="CIC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
     "foil_like": dict(shape="PQS", pusher="Boris", current="Esirkepov", solver="Lehe", interp="binomial"),
+    # the slow-path cliff: relativistic electrons (the Thermal plasma) on LaserWakefield's cells, c dt / dy = 0.94 -- most
+    # trajectories are too wide for the four-node window of the fused kernel and are deposited with global atomics
+    "lwfa_hot": dict(shape="CIC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
 }
 
 
 def n_species():
-    return 1 if VARIANT["config"] == "thermal" else 2
+    return 1 if VARIANT["config"] in ("thermal", "lwfa_hot") else 2
 
 
 def workload_name(grid, ppc, n):
     v = VARIANT
     extra = "" if v["interp"] == "none" else "_Binomial"
-    if v["config"] == "thermal":
-        return "Thermal3D_%dx%dx%d_per_gpu_%dppc_electrons_T17.5mc2_%s_%s_%s_%s%s_periodic_d1x%dx1" % (
+    if v["config"] in ("thermal", "lwfa_hot"):
+        return "%s_%dx%dx%d_per_gpu_%dppc_electrons_T17.5mc2_%s_%s_%s_%s%s_periodic_d1x%dx1" % (
+            "Thermal3D" if v["config"] == "thermal" else "ThermalOnLaserWakefieldCells3D_cdt_over_dy_0.94",
             grid[0], grid[1], grid[2], ppc, v["shape"], v["pusher"], v["current"], v["solver"], extra, n)
     head = {"khi": "KelvinHelmholtz3D", "lwfa_like": "LaserWakefieldLike3D_noLaser_KHIplasma_open_y", "foil_like": "FoilLCTLike3D_KHIplasma"}[v["config"]]
     return "%s_%dx%dx%d_per_gpu_%d+%dppc_%s_%s_%s_%s%s_%s_d1x%dx1" % (
@@ -127,11 +131,13 @@ def variant_kwargs():
         # share/picongpu/examples/LaserWakefield/include/picongpu/param/simulation.param: dt = 1.39e-16 s, cells 0.1772 um x
         # 0.4430e-7 m x 0.1772 um (c dt / dy = 0.94); --periodic 1 0 1, exponential absorber on the open axis
         kw.update(periodic=(1, 0, 1), absorber_kind=1, delta_t_si=1.39e-16, cell_si=(0.1772e-6, 0.4430e-7, 0.1772e-6))
+    if v["config"] == "lwfa_hot":
+        kw.update(delta_t_si=1.39e-16, cell_si=(0.1772e-6, 0.4430e-7, 0.1772e-6), base_density_si=1.0e25)
     return kw
 
 
 def make_params(grid, **kw):
-    if VARIANT["config"] == "thermal":
+    if VARIANT["config"] in ("thermal", "lwfa_hot"):
         return prm.thermal_params(grid=grid, **kw)
     return prm.khi_params(grid=grid, **kw)
 
@@ -325,7 +331,7 @@ def run_ours(args):
     names = [sp.name for sp in p.species]
 
     def init(sm):
-        if VARIANT["config"] == "thermal":
+        if VARIANT["config"] in ("thermal", "lwfa_hot"):
             sm.init_thermal("e", args.ppc)
         else:
             sm.init_khi(ppc_dim=ppc_dim)
@@ -383,6 +389,8 @@ def run_ours(args):
     try:
         gr = sim.gauss_residual()
         checks["gauss_residual_over_cell_charge"] = gr / (float(args.ppc) * abs(p.base_charge) * p.real_particles_per_cell / args.ppc)
+        if n_species() == 1:  # electrons without a neutralising species: rho != eps0 div E = 0 from the start, by construction
+            checks["gauss_residual_over_cell_charge"] = None
     except Exception as ex:  # pragma: no cover
         checks["gauss_error"] = str(ex)
 
@@ -552,15 +560,16 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --grid is the grid per GPU (default, what the driver runs); strong: --grid is the GLOBAL grid, split in y over the GPUs")
     # other BASELINE.json configurations are the same kernels with other template arguments (defaults = the headline)
-    ap.add_argument("--shape", default="TSC", choices=sorted(prm.SHAPE_NAMES))
-    ap.add_argument("--pusher", default="Boris", choices=sorted(prm.PUSHER_NAMES))
-    ap.add_argument("--current", default="Esirkepov", choices=["Esirkepov", "EmZ"])
-    ap.add_argument("--solver", default="Yee", choices=sorted(prm.SOLVER_NAMES))
-    ap.add_argument("--interp", default="none", choices=["none", "binomial"])
+    ap.add_argument("--shape", default=None, choices=sorted(prm.SHAPE_NAMES))
+    ap.add_argument("--pusher", default=None, choices=sorted(prm.PUSHER_NAMES))
+    ap.add_argument("--current", default=None, choices=["Esirkepov", "EmZ"])
+    ap.add_argument("--solver", default=None, choices=sorted(prm.SOLVER_NAMES))
+    ap.add_argument("--interp", default=None, choices=["none", "binomial"])
     ap.add_argument("--config", default="khi", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: the KHI headline)")
     args = ap.parse_args()
-    VARIANT.update(shape=args.shape, pusher=args.pusher, current=args.current, solver=args.solver, interp=args.interp, config=args.config)
-    VARIANT.update(CONFIGS[args.config])
+    VARIANT.update(config=args.config)
+    VARIANT.update(CONFIGS[args.config])  # the configuration's kernels ...
+    VARIANT.update({k: v for k, v in dict(shape=args.shape, pusher=args.pusher, current=args.current, solver=args.solver, interp=args.interp).items() if v is not None})  # ... unless given explicitly
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.config != "khi":  # the CPU arm and the N-rank oracle check are the KHI headline's

@@ -146,6 +146,11 @@ extern "C"
     /* `Particles<Name, Flags, Attributes>` with massRatio<> / chargeRatio<> (speciesDefinition.param).
      * `capacity` = number of particle slots to reserve per buffer (0: sized at the first upload * 1.25). */
     int picstep_species_add(picstep_ctx* ctx, const char* name, float mass_ratio, float charge_ratio, int64_t capacity, int32_t* species_id);
+    /* Per-species policy flags `shape<>`, `particlePusher<>`, `current<>` of the species definition
+     * (include/picongpu/param/speciesAttributes.param:195-256; examples/KelvinHelmholtz/include/picongpu/param/
+     * speciesDefinition.param:64-70).  Default: the values of picstep_params; a negative argument keeps the current
+     * value.  Shapes whose lower interpolation margins agree modulo four cells can be mixed (NGP | CIC, TSC | PQS, PCS). */
+    int picstep_species_set_policy(picstep_ctx* ctx, int32_t species, int32_t shape, int32_t pusher, int32_t current_solver);
 
     /* Field transfer in the reference's own layout: AoS float3, x fastest, guards included
      * (dims = grid + 2*supercell*guard_supercells; include/pmacc/memory/buffers/DeviceBuffer.hpp:111-119). */

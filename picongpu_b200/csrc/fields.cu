@@ -143,14 +143,16 @@ namespace picstep
         float const c2 = P.c * P.c;
         [[maybe_unused]] float const coeff = -(1.0f / P.eps0) * P.dt;
         bool const full = xa >= xlo && xa + 3 < xhi; // all four cells active: 16-byte accesses
-        // the destination values are requested before the wait for the box, so that both travel together (J is not:
-        // 24 more registers would cost the third resident CTA; measured 233 instead of 197 us at 256^3)
+        // The destination values are requested before the wait for the box, so that both travel together -- except in
+        // the E update with the current term, where the 24 registers cost a resident CTA (measured at 256^3: B update
+        // 175 -> 152 us with the early request, E + J update 197 -> 230 us).
+        constexpr bool EARLY = !ADDJ;
         float4 dpre[FD_TZ / 2][3];
 #pragma unroll
         for(int zz = 0; zz < FD_TZ; zz += 2)
         {
             int const z = zz + tz;
-            if(full && yok && Z0 + z < P.g[2] + P.n[2])
+            if(EARLY && full && yok && Z0 + z < P.g[2] + P.n[2])
             {
                 long long const gi = ((long long) (Z0 + z) * P.N[1] + (Y0 + ty)) * P.N[0] + (xa - lead);
 #pragma unroll
@@ -227,7 +229,11 @@ namespace picstep
                 for(int c = 0; c < 3; ++c)
                 {
                     float4* const dp = reinterpret_cast<float4*>(D.c[c] + gi);
-                    float4 d = dpre[zz / 2][c];
+                    float4 d;
+                    if constexpr(EARLY)
+                        d = dpre[zz / 2][c];
+                    else
+                        d = *dp;
                     if constexpr(KIND == 0)
                     {
                         d.x -= upd[c][0];

@@ -68,6 +68,10 @@ namespace picstep
     {
         std::string name;
         float massRatio = 1, chargeRatio = 1;
+        // per-species policies: shape<>, particlePusher<>, current<> flags of the species definition
+        // (param/speciesAttributes.param:195-256); default = picstep_params
+        int shape = 0, pusher = 0, current = 0;
+        TileMaps tileMaps{}; // TMA descriptors of the E/B supercell tile of this species' shape
         int64_t capacity = 0;
         float* attr[2][7] = {}; // px,py,pz,ux,uy,uz,w per buffer
         uint16_t* cell[2] = {};
@@ -104,6 +108,7 @@ struct picstep_ctx
     TileMaps tileMaps{}; // TMA descriptors of E and B for the supercell tile of this shape
     alignas(64) CUtensorMap fdtdMap[2]; // TMA descriptors of E and B for the brick (+ halo) of the Yee update kernels
     bool fdtdTma = false;
+    int widthShape = 0; // the widest shape of any species: guard exchange margins follow it
     uint32_t* migPinned = nullptr; // pinned readback of the migration counts of all species (overlapped step)
     cudaEvent_t evBorder = nullptr, evComm = nullptr;
     AbsorberDev absorber{}; // exponential absorber: thickness per face (0 = not absorbing) + attenuation table
@@ -400,7 +405,7 @@ namespace
         DevParams const& P = c->P;
         AxisExchange x{};
         int w[2];
-        picstep_exchange_widths(c->prm.shape, c->prm.field_solver, c->prm.lehe_dir, f, a, w);
+        picstep_exchange_widths(c->widthShape, c->prm.field_solver, c->prm.lehe_dir, f, a, w);
         if(width >= 0)
             w[0] = w[1] = width;
         x.a = a;
@@ -793,6 +798,7 @@ extern "C"
         std::vector<float> damp;
         setupBoundaries(c, damp);
         computeLehe(*p, c->lehe);
+        c->widthShape = p->shape;
         if((long long) numCells(c) >= (1ll << 30))
         {
             delete c;
@@ -940,6 +946,10 @@ extern "C"
         s.name = name;
         s.massRatio = mass_ratio;
         s.chargeRatio = charge_ratio;
+        s.shape = c->prm.shape;
+        s.pusher = c->prm.pusher;
+        s.current = c->prm.current_solver;
+        s.tileMaps = c->tileMaps;
         int const ncell = numCells(c);
         int const nsc = ncell / SCVOL;
         for(int b = 0; b < 2; ++b)
@@ -970,6 +980,43 @@ extern "C"
         c->species.push_back(s);
         if(species_id)
             *species_id = int32_t(c->species.size()) - 1;
+        return PICSTEP_OK;
+    }
+
+    /* Per-species policies, the `shape<>`, `particlePusher<>` and `current<>` flags of a species definition
+     * (param/speciesAttributes.param:195-256, e.g. examples/KelvinHelmholtz/.../speciesDefinition.param:64-70); a
+     * negative value keeps the current one.  Shapes can be mixed as long as their lower interpolation margins agree
+     * modulo four cells (NGP | CIC, TSC | PQS, PCS): the 16-byte alignment of the TMA tile origins is a property of
+     * the field allocation, fixed by picstep_params.shape. */
+    int picstep_species_set_policy(picstep_ctx* c, int32_t sp, int32_t shape, int32_t pusher, int32_t current_solver)
+    {
+        if(!c || sp < 0 || sp >= int(c->species.size()))
+            return PICSTEP_ERR_INVALID;
+        SpeciesHost& s = c->species[sp];
+        int const sh = shape < 0 ? s.shape : shape, pu = pusher < 0 ? s.pusher : pusher, cu = current_solver < 0 ? s.current : current_solver;
+        if(sh > 4 || pu > 2 || cu > 1)
+            return fail(c, PICSTEP_ERR_INVALID, "unknown shape / pusher / current solver");
+        if(cu == PICSTEP_CURRENT_EMZ && sh == PICSTEP_SHAPE_NGP)
+            return fail(c, PICSTEP_ERR_INVALID, "EmZ needs at least CIC");
+        CU(c, cudaSetDevice(c->device));
+        if(sh != s.shape)
+        {
+            int tbox[3], tlo = 0;
+            tileBox(sh, tbox, &tlo);
+            if((tlo & 3) != c->tileMaps.lead)
+                return fail(c, PICSTEP_ERR_INVALID, "this shape's lower margin does not match the field alignment chosen by picstep_params.shape (mix NGP | CIC, TSC | PQS, PCS)");
+            char msg[128];
+            s.tileMaps.lead = c->tileMaps.lead;
+            for(int f = 0; f < 2; ++f)
+                if(makeTileMap(f == PICSTEP_FIELD_E ? &s.tileMaps.E : &s.tileMaps.B, c->fieldAlloc[f], c->P.N, c->P.vol, tbox, msg, sizeof(msg)))
+                    return fail(c, PICSTEP_ERR_CUDA, msg);
+        }
+        s.shape = sh;
+        s.pusher = pu;
+        s.current = cu;
+        c->widthShape = c->prm.shape;
+        for(auto const& o : c->species)
+            c->widthShape = std::max(c->widthShape, o.shape);
         return PICSTEP_OK;
     }
 
@@ -1250,7 +1297,7 @@ extern "C"
         s.ranked = false;
         if(int rc = ensureSorted(c, s))
             return rc;
-        KL(c, 1, launchPush(c->prm.shape, c->prm.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], s.cellCnt, s.key, c->tileMaps, c->stream));
+        KL(c, 1, launchPush(s.shape, s.pusher, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], s.cellCnt, s.key, s.tileMaps, c->stream));
         return PICSTEP_OK;
     }
 
@@ -1360,10 +1407,10 @@ extern "C"
             return PICSTEP_OK;
         if(int rc = ensureSorted(c, s))
             return rc;
-        if(runKernelSupports(c->prm.shape, c->prm.current_solver) && !(c->prm.flags & 3))
-            KL(c, 1, launchDepositRun(c->prm.shape, c->prm.current_solver, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
+        if(runKernelSupports(s.shape, s.current) && !(c->prm.flags & 3))
+            KL(c, 1, launchDepositRun(s.shape, s.current, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
         else
-            KL(c, 1, launchDeposit(c->prm.shape, c->prm.current_solver, (c->prm.flags & 1) != 0, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
+            KL(c, 1, launchDeposit(s.shape, s.current, (c->prm.flags & 1) != 0, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], c->stream));
         return PICSTEP_OK;
     }
 
@@ -1375,7 +1422,7 @@ extern "C"
         SpeciesHost& s = c->species[sp];
         if(s.capacity == 0)
             return PICSTEP_OK;
-        KL(c, 1, launchPushDeposit(c->prm.shape, c->prm.pusher, c->prm.current_solver, c->P, devOf(c, s, s.cur), devOf(c, s, s.cur ^ 1), s.lazy ? s.inv : nullptr, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, c->tileMaps, area, c->stream));
+        KL(c, 1, launchPushDeposit(s.shape, s.pusher, s.current, c->P, devOf(c, s, s.cur), devOf(c, s, s.cur ^ 1), s.lazy ? s.inv : nullptr, fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), fieldOf(c, PICSTEP_FIELD_J), s.cellOff[s.cur], s.cellCnt, s.stayCnt, s.key, s.rank, s.tileMaps, area, c->stream));
         s.ranked = true;
         return PICSTEP_OK;
     }
@@ -1572,7 +1619,10 @@ extern "C"
             }
             staleGuardsRead = anyOpen && anyExchange;
         }
-        bool const fused = runKernelSupports(c->prm.shape, c->prm.current_solver) && !(c->prm.flags & 7) && !staleGuardsRead;
+        bool allRun = true; // every species' (shape, current solver) pair has a fused kernel instantiation
+        for(auto const& sp : c->species)
+            allRun = allRun && runKernelSupports(sp.shape, sp.current);
+        bool const fused = allRun && !(c->prm.flags & 7) && !staleGuardsRead;
         // Measured on B200 (KHI 256^3): 54.63 -> 54.41 ms/step only.  The fused kernel fills every SM (2 CTAs x 115 KB shared
         // memory, 60 K registers), so the re-sort kernels time-share instead of co-running; with a high-priority second
         // stream the re-sort finishes early but the step gets 0.5 ms longer.  Kept for one rank (no NCCL calls from two
@@ -1858,7 +1908,7 @@ extern "C"
                     return rc;
             for(auto& s : c->species)
                 if(s.capacity)
-                    KL(c, 1, launchChargeDensity(c->prm.shape, P, devOf(c, s, s.cur), s.cellOff[s.cur], c->rho, c->stream));
+                    KL(c, 1, launchChargeDensity(s.shape, P, devOf(c, s, s.cur), s.cellOff[s.cur], c->rho, c->stream));
             // guard reduction of rho with the J machinery: temporarily view rho as a 3-component field whose
             // components 1,2 are zero (FieldTmp::asyncCommunication in the reference)
             float* saved = c->fieldMem[PICSTEP_FIELD_J];
@@ -1897,7 +1947,7 @@ extern "C"
             return rc2;
         float* tmp = nullptr;
         CU(c, cudaMalloc(&tmp, sizeof(float) * 6 * std::max<int64_t>(n, 1)));
-        KL(c, 1, launchGather(c->prm.shape, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], tmp, n, c->stream));
+        KL(c, 1, launchGather(s.shape, c->P, devOf(c, s, s.cur), fieldOf(c, PICSTEP_FIELD_E), fieldOf(c, PICSTEP_FIELD_B), s.cellOff[s.cur], tmp, n, c->stream));
         for(int k = 0; k < 6; ++k)
             CU(c, cudaMemcpyAsync(out + k * capacity, tmp + k * n, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));

@@ -20,7 +20,7 @@ STAGES = ["current_reset", "push", "migrate", "field_before", "deposit", "add_cu
 
 # every symbol include/picstep.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "picstep_version", "picstep_last_error", "picstep_create", "picstep_destroy", "picstep_species_add",
+    "picstep_version", "picstep_last_error", "picstep_create", "picstep_destroy", "picstep_species_add", "picstep_species_set_policy",
     "picstep_fields_upload", "picstep_fields_download", "picstep_fields_upload_soa", "picstep_fields_download_soa",
     "picstep_particles_upload", "picstep_particles_count", "picstep_particles_download", "picstep_supercell_counts",
     "picstep_init_khi", "picstep_init_thermal", "picstep_current_reset", "picstep_push", "picstep_migrate",
@@ -95,6 +95,7 @@ def load(exact=False):
     L.picstep_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
     L.picstep_destroy.argtypes = [vp]
     L.picstep_species_add.argtypes = [vp, C.c_char_p, f32, f32, i64, C.POINTER(i32)]
+    L.picstep_species_set_policy.argtypes = [vp, i32, i32, i32, i32]
     for n in ("picstep_fields_upload", "picstep_fields_download", "picstep_fields_upload_soa", "picstep_fields_download_soa"):
         getattr(L, n).argtypes = [vp, i32, vp]
     L.picstep_particles_upload.argtypes = [vp, i32, i64, vp, vp, vp, vp]
@@ -242,6 +243,10 @@ class Simulation:
         self._chk(self.L.picstep_species_add(self.ctx, name.encode(), mass_ratio, charge_ratio, capacity, C.byref(sid)), "species_add")
         self.species[name] = sid.value
         return sid.value
+
+    def set_policy(self, species, shape=-1, pusher=-1, current_solver=-1):
+        """shape<> / particlePusher<> / current<> flags of one species (default: the values of the parameters)."""
+        self._chk(self.L.picstep_species_set_policy(self.ctx, self._sid(species), shape, pusher, current_solver), "species_set_policy")
 
     def _sid(self, s):
         return self.species[s] if isinstance(s, str) else int(s)

@@ -662,6 +662,57 @@ def test_device_khi_init_matches_oracle_generator(orc):
     s.close()
 
 
+@pytest.mark.parametrize("exact", [True, False])
+def test_per_species_policies(orc, exact):
+    """shape<>, particlePusher<> and current<> are flags of the SPECIES in the reference (speciesDefinition.param:64-70):
+    electrons TSC + Boris + Esirkepov, ions CIC + Vay + EmZ in one run, against the oracle stepping each species with
+    its own policy."""
+    p = util.make_params((16, 16, 8))
+    o, e, i = util.khi_ic(orc, p)
+    rng = np.random.RandomState(8)
+    for sp in (e, i):
+        sp["mom"] += (rng.normal(size=sp["mom"].shape) * 0.05).astype(np.float32) * (np.float32(p.base_mass) * np.float32(sp["massRatio"]) * sp["w"] * np.float32(p.c))
+    s = _sim(p, exact)
+    s.set_policy("i", shape=prm.SHAPE_CIC, pusher=prm.PUSHER_VAY, current_solver=prm.CURRENT_EMZ)
+    with pytest.raises(picstep.PicstepError, match="lower margin"):
+        s.set_policy("i", shape=prm.SHAPE_PQS)  # TSC fields (margin 1) cannot host PQS tiles (margin 2)
+    for name, sp in (("e", e), ("i", i)):
+        s.upload_particles(name, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+    pi = util.make_params((16, 16, 8), shape=prm.SHAPE_CIC, pusher=prm.PUSHER_VAY, current_solver=prm.CURRENT_EMZ)
+    oi = orc.Oracle(pi)
+    E, B, J = o.field(), o.field(), o.field()
+    steps = 10
+    for _ in range(steps):
+        # Simulation::runOneStep with the species' own functors (the field part is common)
+        J[...] = 0
+        o.push(e["massRatio"], e["chargeRatio"], E, B, e["pos"], e["mom"], e["w"], e["cell"])
+        oi.push(i["massRatio"], i["chargeRatio"], E, B, i["pos"], i["mom"], i["w"], i["cell"])
+        o.update_b_half(E, B)
+        o.guard_copy(B)
+        o.update_e(E, B)
+        o.deposit(e["massRatio"], e["chargeRatio"], J, e["pos"], e["mom"], e["w"], e["cell"])
+        oi.deposit(i["massRatio"], i["chargeRatio"], J, i["pos"], i["mom"], i["w"], i["cell"])
+        o.guard_add(J)
+        o.add_current(E, J)
+        o.guard_copy(E)
+        o.update_b_half(E, B)
+        o.guard_copy(B)
+    s.step(steps)
+    s.sync()
+    Eg, Bg = s.download_field(FE), s.download_field(FB)
+    _, escale = util.khi_scales(p, 1)
+    dE = np.abs(o.interior(Eg) - o.interior(E)).max() / escale
+    dB = np.abs(o.interior(Bg) - o.interior(B)).max() / escale
+    print("per-species policies %s: dE %.2e dB %.2e" % ("exact" if exact else "production", dE, dB))
+    assert dE < 2e-5 and dB < 2e-5
+    for name, sp in (("e", e), ("i", i)):
+        got = s.download_particles(name)
+        pm = np.abs(sp["mom"]).max()
+        for c in range(3):
+            assert np.abs(np.sort(got[1][c]) - np.sort(sp["mom"][c])).max() / pm < 1e-5
+    s.close()
+
+
 def test_device_thermal_init_statistics():
     """picstep_init_thermal (bench input of the Thermal benchmark): ppc particles in every cell, positions uniform in
     the cell, momenta Maxwellian with sqrt(weighting * kT * mass) per axis (Temperature.hpp:75-80), and the
