@@ -411,16 +411,32 @@ def run_ours(args):
     ms_k, bytes_k, kname = per_launch[dom]
     achieved = bytes_k / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
     traffic = None
+    smem_wavefronts = inst_executed = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel at the default workload, from the committed ncu capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if kname in tj and grid == (256, 256, 256) and args.ppc == 25:
             traffic = float(tj[kname]["dram_bytes_per_launch"])
+            smem_wavefronts = tj[kname].get("smem_wavefronts_per_launch")
+            inst_executed = tj[kname].get("inst_executed_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
                 "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": bytes_k,
                 "share_of_step": ms_k * nspec / ms_step if ms_step > 0 else None}
+    # The limiter of the dominant kernel is not HBM but the SM's shared-memory / LSU data pipe (one 128-byte wavefront per
+    # cycle and SM) together with the issue slots (4 warp instructions per cycle and SM): both reported next to the HBM
+    # fraction.  Wavefronts and instructions per launch come from the committed ncu capture of the same workload
+    # (profiles/traffic.json), the duration and the SM clock from this run.
+    clk = sampler.summary()
+    limiter = None
+    if smem_wavefronts and inst_executed and clk.get("sm_mhz") and ms_k > 0:
+        cyc = ms_k * 1e-3 * clk["sm_mhz"] * 1e6 * 148
+        limiter = {"bound": "smem_pipe", "kernel": kname, "achieved": smem_wavefronts / cyc, "peak": 1.0, "unit": "wavefronts/cycle/SM",
+                   "frac": smem_wavefronts / cyc, "wavefronts_per_update": smem_wavefronts / (npart / nspec),
+                   "issue": {"achieved": inst_executed / cyc, "peak": 4.0, "unit": "warp instructions/cycle/SM", "frac": inst_executed / cyc / 4.0,
+                             "warp_instructions_per_update": inst_executed / (npart / nspec)},
+                   "source": "wavefronts / instructions: ncu --set full (profiles/traffic.json); cycles: this run's CUDA-event duration x sampled SM clock x 148 SMs"}
     step_bytes = npart * BYTES_PER_UPDATE + ncell * BYTES_PER_CELL
     step_roofline = {"bound": "hbm", "achieved": step_bytes / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step_per_gpu": step_bytes,
@@ -492,6 +508,7 @@ def run_ours(args):
             "stage_note": "spans per stage on the stream the stage runs on; at N=1 the re-sort (migrate) runs on a second stream next to the following push / field update, so its span overlaps theirs and the spans do not add up to ms_per_step",
             "roofline": roofline,
             "step_roofline": step_roofline,
+            "limiter_roofline": limiter,
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),

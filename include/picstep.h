@@ -132,6 +132,22 @@ extern "C"
         /* -m / --moving: the sliding window is active (simulation/control/MovingWindow.hpp): y must be non-periodic,
          * the +y absorber is switched off (Exponential.hpp:97-101) and picstep_slide() may be called */
         int32_t moving_window;
+        /* incidentField.param (fields/incidentField/Solver.hpp:547-575, called from FDTDBase.hpp:108-117,161-166): a
+         * `profiles::PlaneWave<>` (profiles/PlaneWave.hpp) entering through the YMin Huygens surface, Yee solver,
+         * x and z periodic (the surface spans them).  All values are the profile's unitless parameters
+         * (PlaneWaveUnitless / BaseParamUnitless, PIC units).  The source is switched off once the moving window has
+         * slid (Solver.hpp: "After the sliding window started moving, does nothing for the y boundaries"). */
+        int32_t laser_enabled; /* 0: profiles::None on all boundaries */
+        int32_t laser_polarisation; /* PolarisationType: 0 Linear, 1 Circular */
+        int32_t laser_offset_ymin; /* POSITION[1][0]: cells between the global y-min boundary and the surface */
+        float laser_amplitude; /* AMPLITUDE */
+        float laser_omega; /* w = 2 pi c / WAVE_LENGTH */
+        float laser_pulse_duration; /* PULSE_DURATION */
+        float laser_nofocus_constant; /* LASER_NOFOCUS_CONSTANT (plateau) */
+        float laser_ramp_init; /* RAMP_INIT */
+        float laser_phase; /* LASER_PHASE */
+        float laser_pol_dir[3]; /* POLARISATION_DIRECTION (unit, orthogonal to y) */
+        float laser_time_delay; /* TIME_DELAY */
     } picstep_params;
 
     /* library / build information: returns e.g. "picstep sm_100a fmad=on" */

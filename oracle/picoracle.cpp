@@ -1527,6 +1527,157 @@ extern "C"
         }
     }
 
+    // ---------------------------------------------------------------------------------------------
+    // Incident field (laser) through the YMin Huygens surface: P/fields/incidentField/Solver.hpp:190-395 (updateField),
+    // Solver.kernel:101-404 (UpdateFunctor for the Yee solver: margin 1, one derivative coefficient = 1),
+    // Functors.hpp (BaseFunctorE::getCurrentTime, BaseSeparableFunctorE::operator(), ApproximateIncidentB),
+    // profiles/PlaneWave.hpp:93-130 (getLongitudinal), calculatePhaseVelocity.hpp + DispersionRelationSolver (Yee,
+    // propagation along y).  Transversal axes are periodic, so the surface spans them completely
+    // (MakePeriodicTransversalHuygensSurfaceContiguous<PlaneWave> = true, PlaneWave.def:71).
+    // ---------------------------------------------------------------------------------------------
+    struct OrcLaser
+    {
+        int polarisation; // PolarisationType: 0 Linear, 1 Circular
+        int offset_ymin; // POSITION[1][0]
+        float amplitude, omega, pulse_duration, nofocus_constant, ramp_init, phase; // PlaneWaveUnitless
+        float pol[3]; // POLARISATION_DIRECTION (unit, orthogonal to y)
+        float time_delay; // TIME_DELAY
+        int global_y_offset; // totalCellOffset[1] of this domain
+    };
+
+    static float orc_laser_phase_velocity(OrcParams const& P, OrcLaser const& L)
+    {
+        // Yee dispersion relation along y: sin(w dt/2)/(c dt) = sin(k dy/2)/dy (DispersionRelationSolver.hpp), in fp64
+        double const w = double(L.omega), dt = double(P.dt), c = double(P.c), dy = double(P.cell[1]);
+        double const k = 2.0 / dy * std::asin(dy * std::sin(0.5 * w * dt) / (c * dt));
+        return float(w / k / c);
+    }
+
+    // PlaneWaveFunctorIncidentE::getLongitudinal (profiles/PlaneWave.hpp:93-130)
+    static float orc_laser_longitudinal(OrcLaser const& L, float time, float phaseShift)
+    {
+        float envelope = L.amplitude;
+        float const mue = 0.5f * L.ramp_init * L.pulse_duration;
+        float const tau = L.pulse_duration * std::sqrt(2.0f);
+        float const endUpramp = mue;
+        float const startDownramp = mue + L.nofocus_constant;
+        float integrationCorrectionFactor = 0.0f;
+        if(time > startDownramp)
+        {
+            float const exponent = (time - startDownramp) / tau;
+            envelope *= std::exp(-0.5f * exponent * exponent);
+            integrationCorrectionFactor = (time - startDownramp) / (L.omega * tau * tau);
+        }
+        else if(time < endUpramp)
+        {
+            float const exponent = (time - endUpramp) / tau;
+            envelope *= std::exp(-0.5f * exponent * exponent);
+            integrationCorrectionFactor = (time - endUpramp) / (L.omega * tau * tau);
+        }
+        float const timeOszi = time - endUpramp;
+        float const phase = L.omega * timeOszi + L.phase + phaseShift;
+        return (std::sin(phase) + std::cos(phase) * integrationCorrectionFactor) * envelope;
+    }
+
+    // incident E at a (fractional) total cell index: BaseFunctorE::getCurrentTime + BaseSeparableFunctorE::operator()
+    static void orc_laser_incident_e(OrcParams const& P, OrcLaser const& L, float phaseVelocity, float currentStep, float const idx[3], float out[3])
+    {
+        float const originY = (float(L.offset_ymin) + 0.75f) * P.cell[1]; // getOrigin(): projection onto the YMin surface
+        float const distance = idx[1] * P.cell[1] - originY; // dot(shiftFromOrigin, (0,1,0))
+        float const timeDelay = distance / phaseVelocity + L.time_delay;
+        float const time = currentStep * P.dt - timeDelay;
+        out[0] = out[1] = out[2] = 0.0f;
+        if(time < 0.0f)
+            return;
+        float const transversal = 1.0f;
+        if(L.polarisation == 0)
+        {
+            float const v = orc_laser_longitudinal(L, time, 0.0f) * transversal;
+            for(int d = 0; d < 3; ++d)
+                out[d] = L.pol[d] * v;
+        }
+        else
+        {
+            float const rs2 = std::sqrt(2.0f);
+            float const p1[3] = {L.pol[0] / rs2, L.pol[1] / rs2, L.pol[2] / rs2};
+            // cross(axis0 = (0,1,0), p1)
+            float const p2[3] = {1.0f * p1[2] - 0.0f * p1[1], 0.0f * p1[0] - 0.0f * p1[2], 0.0f * p1[1] - 1.0f * p1[0]};
+            float const a = orc_laser_longitudinal(L, time, 1.57079632679489661923f) * transversal;
+            float const b = orc_laser_longitudinal(L, time, 0.0f) * transversal;
+            for(int d = 0; d < 3; ++d)
+                out[d] = p1[d] * a + p2[d] * b;
+        }
+    }
+
+    /** incidentField::Solver::updateE (updatedIsE = 1, uses B_inc = cross(dir, E_inc) / c) or ::updateBHalf (0, uses
+     * E_inc) for a PlaneWave profile on YMin.  currentStep is fractional (FDTDBase.hpp:108-117,161-166). */
+    void orc_incident_update(OrcParams const* Pp, OrcLaser const* Lp, float* F, int updatedIsE, float currentStep)
+    {
+        OrcParams const& P = *Pp;
+        OrcLaser const& L = *Lp;
+        Dom const D(P);
+        // Solver.hpp:230-236: the updated plane in user (total) coordinates; E sits in the total-field region
+        int const planeTotal = L.offset_ymin + 1 - (updatedIsE ? 0 : 1);
+        int const yl = planeTotal - L.global_y_offset; // local, without guards
+        if(yl < 0 || yl >= D.n[1])
+            return;
+        float const vph = orc_laser_phase_velocity(P, L);
+        float const c2 = P.c * P.c;
+        float const curlCoefficient = updatedIsE ? P.dt * c2 : -(0.5f * P.dt);
+        float const baseCoefficient = curlCoefficient / P.cell[1] * 1.0f; // direction +1
+        // in-cell shifts (Solver.hpp:360-372): base shift -1 (E updated) / +1 (B updated) along y plus the Yee position of
+        // the incident component: incident component 1 = x, 2 = z (Solver.kernel:222-223 for axis y)
+        float const baseShift = updatedIsE ? -1.0f : 1.0f;
+        float shift1[3], shift2[3];
+        if(updatedIsE)
+        {
+            // incident field B: Bx at (0, .5, .5), Bz at (.5, .5, 0)   (YeeCell.hpp:70-130)
+            shift1[0] = 0.0f, shift1[1] = baseShift + 0.5f, shift1[2] = 0.5f;
+            shift2[0] = 0.5f, shift2[1] = baseShift + 0.5f, shift2[2] = 0.0f;
+        }
+        else
+        {
+            // incident field E: Ex at (.5, 0, 0), Ez at (0, 0, .5)
+            shift1[0] = 0.5f, shift1[1] = baseShift + 0.0f, shift1[2] = 0.0f;
+            shift2[0] = 0.0f, shift2[1] = baseShift + 0.0f, shift2[2] = 0.5f;
+        }
+        float* fx = F;
+        float* fz = F + 2 * D.vol;
+        int const y = yl + D.g[1];
+#pragma omp parallel for schedule(static)
+        for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
+            for(int x = D.g[0]; x < D.g[0] + D.n[0]; ++x)
+            {
+                // total cell index of the Huygens surface cell = the updated cell (margin 1)
+                float const base[3] = {float(x - D.g[0]), float(planeTotal), float(z - D.g[2])};
+                float const i1[3] = {base[0] + shift1[0], base[1] + shift1[1], base[2] + shift1[2]};
+                float const i2[3] = {base[0] + shift2[0], base[1] + shift2[1], base[2] + shift2[2]};
+                float e1[3], e2[3], inc1, inc2;
+                orc_laser_incident_e(P, L, vph, currentStep, i1, e1);
+                orc_laser_incident_e(P, L, vph, currentStep, i2, e2);
+                if(updatedIsE)
+                {
+                    // ApproximateIncidentB: cross((0,1,0), E) / c = (Ez, 0, -Ex) / c
+                    inc1 = (1.0f * e1[2] - 0.0f * e1[1]) / P.c; // B_inc,x
+                    inc2 = (0.0f * e2[1] - 1.0f * e2[0]) / P.c; // B_inc,z
+                }
+                else
+                {
+                    inc1 = e1[0];
+                    inc2 = e2[2];
+                }
+                // Solver.kernel:318-337: result[dir1 = z] = +base * inc1, result[dir2 = x] = -base * inc2
+                float rz = 0.0f, rx = 0.0f;
+                rz += 1.0f * inc1;
+                rx += 1.0f * inc2;
+                rz *= baseCoefficient;
+                rx *= -baseCoefficient;
+                int64_t const i = D.idx(x, y, z);
+                fz[i] += rz;
+                fx[i] += rx;
+            }
+    }
+
     /** ChargeConservation (P/plugins/ChargeConservation.tpp:122-136,205-259): max |div E * eps0 - rho| * V.
      * rho must already be guard-reduced. */
     double orc_gauss_residual(OrcParams const* Pp, float const* E, float const* rho)

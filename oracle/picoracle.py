@@ -43,6 +43,41 @@ class OrcParams(C.Structure):
     ]
 
 
+class OrcLaser(C.Structure):
+    """PlaneWave incident field on the YMin Huygens surface (oracle/picoracle.cpp: struct OrcLaser)"""
+
+    _fields_ = [
+        ("polarisation", C.c_int),
+        ("offset_ymin", C.c_int),
+        ("amplitude", C.c_float),
+        ("omega", C.c_float),
+        ("pulse_duration", C.c_float),
+        ("nofocus_constant", C.c_float),
+        ("ramp_init", C.c_float),
+        ("phase", C.c_float),
+        ("pol", C.c_float * 3),
+        ("time_delay", C.c_float),
+        ("global_y_offset", C.c_int),
+    ]
+
+
+def make_laser(cfg):
+    """cfg.laser: dict with the PlaneWave parameters in PIC units (picongpu_b200.param.plane_wave_laser) or None"""
+    las = cfg.get("laser") if isinstance(cfg, dict) else getattr(cfg, "laser", None)
+    if not las:
+        return None
+    L = OrcLaser()
+    L.polarisation = int(las["polarisation"])
+    L.offset_ymin = int(las["offset_ymin"])
+    for k in ("amplitude", "omega", "pulse_duration", "nofocus_constant", "ramp_init", "phase", "time_delay"):
+        setattr(L, k, float(las[k]))
+    for d in range(3):
+        L.pol[d] = float(las["pol"][d])
+    go = cfg["global_offset"] if isinstance(cfg, dict) else getattr(cfg, "global_offset", (0, 0, 0))
+    L.global_y_offset = int(go[1])
+    return L
+
+
 class OrcSpecies(C.Structure):
     _fields_ = [
         ("massRatio", C.c_float),
@@ -107,6 +142,7 @@ def lib():
     L.orc_khi_init.argtypes = [P, i32p, i32p, i32p, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double, C.c_uint32,
                                f32p, f32p, f32p, i32p, f32p, f32p, f32p, i32p]
     L.orc_absorb.argtypes = [P, f32p]
+    L.orc_incident_update.argtypes = [P, C.POINTER(OrcLaser), f32p, C.c_int, C.c_float]
     L.orc_num_threads.restype = C.c_int
     L.orc_set_num_threads.argtypes = [C.c_int]
     _LIB = L
@@ -159,6 +195,8 @@ class Oracle:
         self.n = tuple(self.p.n)
         self.g = tuple(self.p.g)
         self.N = tuple(self.p.n[d] + 2 * self.p.g[d] for d in range(3))
+        self.laser = make_laser(cfg)
+        self.step_index = 0  # step_open counts the steps (the incident field is a function of time)
 
     def field(self):
         return np.zeros((3, self.N[2], self.N[1], self.N[0]), np.float32)
@@ -218,6 +256,11 @@ class Oracle:
     def absorb(self, F):
         self.L.orc_absorb(C.byref(self.p), F)
 
+    def incident_update(self, F, updated_is_e, step):
+        """incidentField::Solver::updateE / updateBHalf at the (fractional) step `step`; no-op without a laser"""
+        if self.laser is not None:
+            self.L.orc_incident_update(C.byref(self.p), C.byref(self.laser), F, 1 if updated_is_e else 0, float(step))
+
     def step_open(self, E, B, J, species):
         """One PIC step for a single domain with any mix of periodic and open (absorbing) axes, composed of the stage
         calls in the order of Simulation::runOneStep (Simulation.hpp:526-541).  Particles that leave through an open
@@ -242,8 +285,11 @@ class Oracle:
                     w = g[a] if width is None else width
                     self.halo_axis(F, a, w, w, add=False)
 
+        # update_beforeCurrent (FDTDBase.hpp:97-121) with the incident field source (:108-117)
         self.update_b_half(E, B)
+        self.incident_update(B, False, self.step_index)
         copy_guards(B)
+        self.incident_update(E, True, self.step_index + 0.5)
         self.update_e(E, B)
         for s in species:
             if s["w"].shape[0]:
@@ -255,10 +301,12 @@ class Oracle:
             copy_guards(J, 1)
         self.add_current(E, J)
         self.absorb(E)
+        self.incident_update(B, False, self.step_index + 1.0)  # FDTDBase.hpp:161-166
         copy_guards(E)
         self.update_b_half(E, B)
         self.absorb(B)
         copy_guards(B)
+        self.step_index += 1
 
     def field_energy(self, E, B):
         out = np.zeros(2, np.float64)

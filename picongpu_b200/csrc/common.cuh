@@ -93,6 +93,20 @@ namespace picstep
         int axis, first, stride, count;
     };
 
+    // PlaneWave incident field on the YMin Huygens surface (fields.cu: incidentKernel), unitless profile parameters
+    struct LaserDev
+    {
+        int polarisation, plane; // plane: padded-grid y index of the updated plane of this call
+        float planeTotal; // its total (global) cell index along y
+        float amplitude, omega, pulseDuration, nofocusConstant, rampInit, phase, timeDelay;
+        float pol[3];
+        float originY; // (POSITION[1][0] + 0.75) * cellSize.y
+        float phaseVelocity; // Yee numerical phase velocity along y, in units of c
+        float currentTimeOrigin; // currentStep * dt (fractional step)
+        float baseCoefficient; // curl coefficient / cellSize.y (direction +1)
+        int updatedIsE;
+    };
+
     struct SpeciesDev
     {
         float* pos[3];

@@ -283,6 +283,97 @@ namespace picstep
         }
     }
 
+    // ---- incident field (laser): PlaneWave profile through the YMin Huygens surface, Yee solver --------------------
+    // Reference: fields/incidentField/Solver.hpp:190-395 (updateField: which plane, in-cell shifts, coefficients),
+    // Solver.kernel:101-404 (UpdateFunctor; Yee: margin 1, single derivative coefficient 1), Functors.hpp
+    // (BaseFunctorE::getCurrentTime, BaseSeparableFunctorE::operator(), ApproximateIncidentB), profiles/PlaneWave.hpp:93-130.
+    // One thread per cell of the updated plane.  Same float operations in the same order as the oracle's restatement;
+    // sin / cos / exp are the device's (1-2 ulp from the host's).
+    __device__ __forceinline__ float laserLongitudinal(LaserDev const& L, float time, float phaseShift)
+    {
+        float envelope = L.amplitude;
+        float const mue = 0.5f * L.rampInit * L.pulseDuration;
+        float const tau = L.pulseDuration * sqrtf(2.0f);
+        float const endUpramp = mue;
+        float const startDownramp = mue + L.nofocusConstant;
+        float integrationCorrectionFactor = 0.0f;
+        if(time > startDownramp)
+        {
+            float const exponent = (time - startDownramp) / tau;
+            envelope *= expf(-0.5f * exponent * exponent);
+            integrationCorrectionFactor = (time - startDownramp) / (L.omega * tau * tau);
+        }
+        else if(time < endUpramp)
+        {
+            float const exponent = (time - endUpramp) / tau;
+            envelope *= expf(-0.5f * exponent * exponent);
+            integrationCorrectionFactor = (time - endUpramp) / (L.omega * tau * tau);
+        }
+        float const timeOszi = time - endUpramp;
+        float const phase = L.omega * timeOszi + L.phase + phaseShift;
+        return (sinf(phase) + cosf(phase) * integrationCorrectionFactor) * envelope;
+    }
+
+    __device__ __forceinline__ void laserIncidentE(DevParams const& P, LaserDev const& L, float idxY, float out[3])
+    {
+        float const distance = idxY * P.cell[1] - L.originY;
+        float const timeDelay = distance / L.phaseVelocity + L.timeDelay;
+        float const time = L.currentTimeOrigin - timeDelay;
+        out[0] = out[1] = out[2] = 0.0f;
+        if(time < 0.0f)
+            return;
+        if(L.polarisation == 0)
+        {
+            float const v = laserLongitudinal(L, time, 0.0f) * 1.0f;
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+                out[d] = L.pol[d] * v;
+        }
+        else
+        {
+            float const rs2 = sqrtf(2.0f);
+            float const p1[3] = {L.pol[0] / rs2, L.pol[1] / rs2, L.pol[2] / rs2};
+            float const p2[3] = {1.0f * p1[2] - 0.0f * p1[1], 0.0f * p1[0] - 0.0f * p1[2], 0.0f * p1[1] - 1.0f * p1[0]};
+            float const a = laserLongitudinal(L, time, 1.57079632679489661923f) * 1.0f;
+            float const b = laserLongitudinal(L, time, 0.0f) * 1.0f;
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+                out[d] = p1[d] * a + p2[d] * b;
+        }
+    }
+
+    __global__ void __launch_bounds__(256) incidentKernel(DevParams P, Field3 F, LaserDev L)
+    {
+        int const x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+        if(x >= P.n[0] || z >= P.n[2])
+            return;
+        // the plane-wave profile depends on y only: the in-cell shifts along x and z drop out, the one along y is
+        // -1 + 0.5 for the E update (B_inc on its Yee position) and +1 + 0 for the B update (Solver.hpp:360-372)
+        float const shiftY = L.updatedIsE ? (-1.0f + 0.5f) : (1.0f + 0.0f);
+        float e[3];
+        laserIncidentE(P, L, L.planeTotal + shiftY, e);
+        float inc1, inc2; // incident components x and z
+        if(L.updatedIsE)
+        {
+            // ApproximateIncidentB: cross((0,1,0), E) / c
+            inc1 = (1.0f * e[2] - 0.0f * e[1]) / P.c;
+            inc2 = (0.0f * e[1] - 1.0f * e[0]) / P.c;
+        }
+        else
+        {
+            inc1 = e[0];
+            inc2 = e[2];
+        }
+        float rz = 0.0f, rx = 0.0f;
+        rz += 1.0f * inc1;
+        rx += 1.0f * inc2;
+        rz *= L.baseCoefficient;
+        rx *= -L.baseCoefficient;
+        long long const i = fidx(P, x + P.g[0], L.plane, z + P.g[2]);
+        F.c[2][i] += rz;
+        F.c[0][i] += rx;
+    }
+
     // KernelAddCurrentDensity + None: E += (-(1/eps0) * dt) * J   (FDTD.hpp:84-85)
     __global__ void __launch_bounds__(256) addCurrentKernel(DevParams P, Field3 E, Field3 J)
     {
@@ -641,6 +732,13 @@ namespace picstep
     static inline dim3 cellGrid(DevParams const& P, dim3 b)
     {
         return dim3((P.n[0] + b.x - 1) / b.x, (P.n[1] + b.y - 1) / b.y, (P.n[2] + b.z - 1) / b.z);
+    }
+
+    cudaError_t launchIncident(DevParams const& P, Field3 F, LaserDev const& L, cudaStream_t st)
+    {
+        dim3 const grid((P.n[0] + 255) / 256, P.n[2]);
+        incidentKernel<<<grid, 256, 0, st>>>(P, F, L);
+        return cudaGetLastError();
     }
 
     void fdtdBox(int box[3])

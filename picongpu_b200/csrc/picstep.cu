@@ -40,6 +40,7 @@ namespace picstep
     cudaError_t launchSupercellCounts(uint32_t const*, long long*, int, cudaStream_t);
     void fdtdBox(int*);
     cudaError_t launchFdtdTma(int, bool, DevParams const&, Field3, Field3, CUtensorMap const&, int, cudaStream_t);
+    cudaError_t launchIncident(DevParams const&, Field3, LaserDev const&, cudaStream_t);
     cudaError_t launchUpdateBHalf(int, DevParams const&, LeheCoeffs const&, Field3, Field3, cudaStream_t);
     cudaError_t launchUpdateE(DevParams const&, LeheCoeffs const&, Field3, Field3, cudaStream_t);
     cudaError_t launchAddCurrent(DevParams const&, Field3, Field3, bool, cudaStream_t);
@@ -743,6 +744,17 @@ extern "C"
             return fail(nullptr, PICSTEP_ERR_INVALID, "unknown shape / pusher / current solver / field solver");
         if(p->current_solver == PICSTEP_CURRENT_EMZ && p->shape == PICSTEP_SHAPE_NGP)
             return fail(nullptr, PICSTEP_ERR_INVALID, "EmZ needs at least CIC");
+        if(p->laser_enabled)
+        {
+            if(p->field_solver != PICSTEP_SOLVER_YEE || p->periodic[1] || !p->periodic[0] || !p->periodic[2])
+                return fail(nullptr, PICSTEP_ERR_INVALID, "the incident field source is built for the Yee solver, a non-periodic y axis and periodic x, z");
+            // Solver.hpp:133-159 (checkRequirements): the surface keeps clear of the absorber and of the local domain border
+            int const minOffset = p->absorber_kind ? p->absorber_cells[1][0] : 0;
+            if(p->laser_offset_ymin < minOffset || p->laser_offset_ymin + 2 > p->grid[1])
+                return fail(nullptr, PICSTEP_ERR_INVALID, "incident field POSITION[1][0] is too close to the boundary / outside of the first local domain");
+            if(p->laser_polarisation < 0 || p->laser_polarisation > 1 || !(p->laser_omega > 0.0f) || !(p->laser_pulse_duration > 0.0f))
+                return fail(nullptr, PICSTEP_ERR_INVALID, "bad incident field parameters");
+        }
         if(p->current_interpolation < 0 || p->current_interpolation > 1 || p->absorber_kind < 0 || p->absorber_kind > 1)
             return fail(nullptr, PICSTEP_ERR_INVALID, "unknown current interpolation / absorber kind");
         for(int d = 0; d < 3; ++d)
@@ -1361,6 +1373,49 @@ extern "C"
         return exchangeField(c, f);
     }
 
+    /* incidentField::Solver::updateE (updatedIsE) / ::updateBHalf at the fractional step `currentStep`
+     * (Solver.hpp:547-575; call sites FDTDBase.hpp:108-117,161-166).  PlaneWave on YMin only; nothing to do on a rank that
+     * does not hold the updated plane, or once the moving window has slid. */
+    static int incidentUpdate(picstep_ctx* c, bool updatedIsE, float currentStep)
+    {
+        picstep_params const& p = c->prm;
+        if(!p.laser_enabled || c->slides > 0)
+            return PICSTEP_OK;
+        DevParams const& P = c->P;
+        // Solver.hpp:230-236: E sits in the total-field region, B (scattered) one plane closer to the boundary
+        int const planeTotal = p.laser_offset_ymin + 1 - (updatedIsE ? 0 : 1);
+        int const yl = planeTotal - p.grid[1] * p.rank_pos[1];
+        if(yl < 0 || yl >= P.n[1])
+            return PICSTEP_OK;
+        LaserDev L{};
+        L.polarisation = p.laser_polarisation;
+        L.plane = yl + P.g[1];
+        L.planeTotal = float(planeTotal);
+        L.amplitude = p.laser_amplitude;
+        L.omega = p.laser_omega;
+        L.pulseDuration = p.laser_pulse_duration;
+        L.nofocusConstant = p.laser_nofocus_constant;
+        L.rampInit = p.laser_ramp_init;
+        L.phase = p.laser_phase;
+        L.timeDelay = p.laser_time_delay;
+        for(int d = 0; d < 3; ++d)
+            L.pol[d] = p.laser_pol_dir[d];
+        L.originY = (float(p.laser_offset_ymin) + 0.75f) * P.cell[1];
+        {
+            // Yee dispersion relation along y (calculatePhaseVelocity.hpp, DispersionRelationSolver), fp64
+            double const w = double(p.laser_omega), dt = double(P.dt), cc = double(P.c), dy = double(P.cell[1]);
+            double const k = 2.0 / dy * std::asin(dy * std::sin(0.5 * w * dt) / (cc * dt));
+            L.phaseVelocity = float(w / k / cc);
+        }
+        L.currentTimeOrigin = currentStep * P.dt;
+        float const c2 = P.c * P.c;
+        float const curlCoefficient = updatedIsE ? P.dt * c2 : -(0.5f * P.dt);
+        L.baseCoefficient = curlCoefficient / P.cell[1] * 1.0f;
+        L.updatedIsE = updatedIsE ? 1 : 0;
+        KL(c, 1, launchIncident(P, fieldOf(c, updatedIsE ? PICSTEP_FIELD_E : PICSTEP_FIELD_B), L, c->stream));
+        return PICSTEP_OK;
+    }
+
     // B -= curl E * dt/2 (updateBFirstHalf / updateBSecondHalf)
     static int updateBHalf(picstep_ctx* c)
     {
@@ -1373,14 +1428,18 @@ extern "C"
     }
 
     // update_beforeCurrent; addJ: the current term E += coeff * J rides in the E update kernel (J already reduced)
-    static int fieldUpdateBeforeCurrent(picstep_ctx* c, bool addJ)
+    static int fieldUpdateBeforeCurrent(picstep_ctx* c, bool addJ, uint32_t step)
     {
         StageTimer t(c, 3);
         Field3 E = fieldOf(c, PICSTEP_FIELD_E), B = fieldOf(c, PICSTEP_FIELD_B);
         int rc = updateBHalf(c); // updateBSecondHalf
+        if(!rc)
+            rc = incidentUpdate(c, false, float(step)); // B by half a step with E_inc at t = step
         if(rc)
             return rc;
         rc = exchangeField(c, PICSTEP_FIELD_B);
+        if(!rc)
+            rc = incidentUpdate(c, true, float(step) + 0.5f); // E with B_inc at t = step + 1/2, before the E update
         if(rc)
             return rc;
         if(c->fdtdTma)
@@ -1390,11 +1449,11 @@ extern "C"
         return PICSTEP_OK;
     }
 
-    int picstep_field_update_before_current(picstep_ctx* c, uint32_t)
+    int picstep_field_update_before_current(picstep_ctx* c, uint32_t step)
     {
         if(!c)
             return PICSTEP_ERR_INVALID;
-        return fieldUpdateBeforeCurrent(c, false);
+        return fieldUpdateBeforeCurrent(c, false, step);
     }
 
     int picstep_deposit(picstep_ctx* c, int32_t sp)
@@ -1508,7 +1567,7 @@ extern "C"
         return addCurrentImpl(c, false);
     }
 
-    int picstep_field_update_after_current(picstep_ctx* c, uint32_t)
+    int picstep_field_update_after_current(picstep_ctx* c, uint32_t step)
     {
         if(!c)
             return PICSTEP_ERR_INVALID;
@@ -1516,7 +1575,9 @@ extern "C"
         Field3 E = fieldOf(c, PICSTEP_FIELD_E), B = fieldOf(c, PICSTEP_FIELD_B);
         if(c->absorbing) // exponentialImpl.run(E) (FDTDBase.hpp:153-158)
             KL(c, 1, launchAbsorb(c->P, E, c->absorber, c->stream));
-        int rc = exchangeField(c, PICSTEP_FIELD_E);
+        int rc = incidentUpdate(c, false, float(step) + 1.0f); // B by half a step with E_inc at t = step + 1 (FDTDBase.hpp:161-166)
+        if(!rc)
+            rc = exchangeField(c, PICSTEP_FIELD_E);
         if(rc)
             return rc;
         rc = updateBHalf(c); // updateBFirstHalf
@@ -1737,7 +1798,7 @@ extern "C"
                 rc = exchangeField(c, PICSTEP_FIELD_J, -1, -1, jSplitDone);
             }
             if(!rc)
-                rc = fieldUpdateBeforeCurrent(c, fuseJ);
+                rc = fieldUpdateBeforeCurrent(c, fuseJ, step);
             for(int s = 0; s < ns && !rc && !fused; ++s)
                 rc = picstep_deposit(c, s);
             if(!rc && !fuseJ)

@@ -67,6 +67,8 @@ class SimParams:
     absorber_cells: tuple = ((12, 12), (12, 12), (12, 12))
     absorber_strength: tuple = ((1.0e-3, 1.0e-3), (1.0e-3, 1.0e-3), (1.0e-3, 1.0e-3))
     moving_window: int = 0  # -m: sliding window along y (needs a non-periodic y axis)
+    # incidentField.param: PlaneWave profile on YMin (dict from plane_wave_laser(), PIC units) or None = profiles::None
+    laser: dict = None
     # --- runtime (-d, --periodic) ---
     periodic: tuple = (1, 1, 1)
     devices: tuple = (1, 1, 1)
@@ -151,3 +153,26 @@ def thermal_params(grid=(64, 64, 64), **kw):
     p = SimParams(grid=tuple(grid), **kw)
     p.species = [Species("e", 1.0, 1.0)]
     return p
+
+
+def plane_wave_laser(p, a0=1.0, wavelength_si=0.8e-6, pulse_duration_si=5.0e-15, nofocus_constant_si=0.0, ramp_init=8.0, phase=0.0,
+                     polarisation="linear", pol_dir=(1.0, 0.0, 0.0), offset_ymin=16, time_delay_si=0.0):
+    """incidentField.param for a `profiles::PlaneWave<>` entering through YMin (include/picongpu/fields/incidentField/
+    profiles/PlaneWave.def:36-60, BaseParam.hpp): the SI parameters converted to the unitless values of
+    `PlaneWaveUnitless` / `BaseParamUnitless` (float_X).  AMPLITUDE_SI = a0 * (-2 pi / wavelength * m_e c^2 / e) as in
+    examples/LaserWakefield/include/picongpu/param/incidentField.param."""
+    amplitude_si = a0 * (-2.0 * math.pi / wavelength_si * ELECTRON_MASS_SI * SPEED_OF_LIGHT_SI**2 / ELECTRON_CHARGE_SI)
+    wave_length = _f32(wavelength_si / p.unit_length)
+    f = _f32(np.float32(p.c) / np.float32(wave_length))
+    return dict(
+        polarisation=0 if polarisation == "linear" else 1,
+        offset_ymin=int(offset_ymin),
+        amplitude=_f32(amplitude_si / p.unit_efield),
+        omega=_f32(np.float32(2.0 * math.pi) * np.float32(f)),
+        pulse_duration=_f32(pulse_duration_si / p.unit_time),
+        nofocus_constant=_f32(nofocus_constant_si / p.unit_time),
+        ramp_init=_f32(ramp_init),
+        phase=_f32(phase),
+        pol=tuple(_f32(v) for v in pol_dir),
+        time_delay=_f32(time_delay_si / p.unit_time),
+    )

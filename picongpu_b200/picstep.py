@@ -65,6 +65,17 @@ class Params(C.Structure):
         ("absorber_cells", (C.c_int32 * 2) * 3),
         ("absorber_strength", (C.c_float * 2) * 3),
         ("moving_window", C.c_int32),
+        ("laser_enabled", C.c_int32),
+        ("laser_polarisation", C.c_int32),
+        ("laser_offset_ymin", C.c_int32),
+        ("laser_amplitude", C.c_float),
+        ("laser_omega", C.c_float),
+        ("laser_pulse_duration", C.c_float),
+        ("laser_nofocus_constant", C.c_float),
+        ("laser_ramp_init", C.c_float),
+        ("laser_phase", C.c_float),
+        ("laser_pol_dir", C.c_float * 3),
+        ("laser_time_delay", C.c_float),
     ]
 
 
@@ -148,6 +159,16 @@ def to_c_params(p, device=0, flags=0):
     cp.current_interpolation = int(getattr(p, "current_interpolation", 0))
     cp.absorber_kind = int(getattr(p, "absorber_kind", 0))
     cp.moving_window = int(getattr(p, "moving_window", 0))
+    las = getattr(p, "laser", None)
+    if las:
+        cp.laser_enabled = 1
+        cp.laser_polarisation = int(las["polarisation"])
+        cp.laser_offset_ymin = int(las["offset_ymin"])
+        cp.laser_amplitude, cp.laser_omega = las["amplitude"], las["omega"]
+        cp.laser_pulse_duration, cp.laser_nofocus_constant = las["pulse_duration"], las["nofocus_constant"]
+        cp.laser_ramp_init, cp.laser_phase, cp.laser_time_delay = las["ramp_init"], las["phase"], las["time_delay"]
+        for d in range(3):
+            cp.laser_pol_dir[d] = las["pol"][d]
     for d in range(3):
         for sd in range(2):
             cp.absorber_cells[d][sd] = int(getattr(p, "absorber_cells", ((0, 0),) * 3)[d][sd])

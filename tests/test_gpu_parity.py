@@ -818,6 +818,57 @@ def test_open_boundary_steps_vs_oracle(orc, exact, periodic, interp):
     s.close()
 
 
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("polarisation", ["linear", "circular"])
+def test_incident_plane_wave_vs_oracle(orc, exact, polarisation):
+    """Incident-field laser (fields/incidentField/Solver.hpp, profiles/PlaneWave.hpp) through the YMin Huygens surface,
+    the configuration of examples/LaserWakefield (--periodic 1 0 1, exponential absorber): fields against the oracle's
+    restatement after 150 coupled steps with a KHI plasma in the box, and the defining property of the
+    total-field / scattered-field source on vacuum: the pulse has the requested amplitude inside and nothing leaks
+    behind the surface."""
+    kw = dict(periodic=(1, 0, 1), absorber_kind=1, absorber_cells=((0, 0), (12, 12), (0, 0)), absorber_strength=((0, 0), (1e-3, 1e-3), (0, 0)))
+    p = util.make_params((16, 128, 8), **kw)
+    p.laser = prm.plane_wave_laser(p, a0=0.5, pulse_duration_si=4e-15, ramp_init=6.0, polarisation=polarisation, offset_ymin=16)
+    amp = abs(p.laser["amplitude"])
+    # (a) vacuum: known answer
+    s = _sim(p, exact)
+    s.step(150)
+    s.sync()
+    Eg, Bg = s.download_field(FE), s.download_field(FB)
+    o = orc.Oracle(p)
+    E, B, J = o.field(), o.field(), o.field()
+    for _ in range(150):
+        o.step_open(E, B, J, [])
+    g = p.guard_cells
+    inside = np.sqrt((o.interior(Eg)[:, :, 18:, :] ** 2).sum(axis=0)).max()
+    behind = np.abs(o.interior(Eg)[:, :, :16, :]).max()
+    print("laser %s %s: peak |E| / amplitude %.4f, leak behind the surface %.2e of the amplitude" % (polarisation, "exact" if exact else "production", inside / amp, behind / amp))
+    assert abs(inside / amp - 1.0) < 0.03 and behind / amp < 1e-3
+    assert np.abs(o.interior(Eg) - o.interior(E)).max() / amp < 2e-5
+    assert np.abs(o.interior(Bg) - o.interior(B)).max() / (amp / p.c) < 2e-5
+    s.close()
+    # (b) with plasma: the coupled step (push in the laser field, current back into E)
+    o2, e, i = util.khi_ic(orc, p, ppc_dim=(2, 2, 1))
+    s = _sim(p, exact)
+    for name, sp in (("e", e), ("i", i)):
+        s.upload_particles(name, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+    steps = 120
+    s.step(steps)
+    s.sync()
+    E, B, J = o2.field(), o2.field(), o2.field()
+    sps = [e, i]
+    for _ in range(steps):
+        o2.step_open(E, B, J, sps)
+    Eg, Bg = s.download_field(FE), s.download_field(FB)
+    dE = np.abs(o2.interior(Eg) - o2.interior(E)).max() / amp
+    dB = np.abs(o2.interior(Bg) - o2.interior(B)).max() / (amp / p.c)
+    print("laser + plasma: dE %.2e dB %.2e of the amplitude" % (dE, dB))
+    assert dE < 1e-4 and dB < 1e-4
+    ne = s.particle_count("e")
+    assert abs(ne - sps[0]["w"].shape[0]) <= (0 if exact else 2)
+    s.close()
+
+
 def test_absorber_damps_outgoing_wave():
     """Physics check of the absorber: a pulse leaving through an absorbing face loses energy, the same pulse in a
     periodic box does not."""

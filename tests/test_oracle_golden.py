@@ -445,3 +445,29 @@ def test_deposition_continuity_property(shape, current, pos, vel_frac):
     # div J and of d(rho)/dt are of that size even when the net change is tiny)
     unit = 1.0 / (float(np.prod(cs)) * float(p.dt))
     assert np.abs(div + drho).max() <= 5e-5 * np.abs(drho).max() + 5e-7 * unit
+
+
+def test_incident_plane_wave_known_answer(orc):
+    """Oracle restatement of the incident-field source (fields/incidentField/Solver.hpp + profiles/PlaneWave.hpp): a
+    total-field / scattered-field Huygens surface on vacuum emits the pulse with the requested amplitude into the
+    total-field region and nothing (to the accuracy of the matched numerical phase velocity) into the region behind it;
+    the reference holds no golden vector for it, so this defining property is the pin."""
+    from picongpu_b200 import param as prm
+
+    p = prm.khi_params(grid=(8, 128, 4), periodic=(1, 0, 1), absorber_kind=1, absorber_cells=((0, 0), (12, 12), (0, 0)),
+                       absorber_strength=((0, 0), (1e-3, 1e-3), (0, 0)))
+    p.laser = prm.plane_wave_laser(p, a0=0.5, pulse_duration_si=4e-15, ramp_init=6.0, offset_ymin=16)
+    amp = abs(p.laser["amplitude"])
+    o = orc.Oracle(p)
+    E, B, J = o.field(), o.field(), o.field()
+    peak = 0.0
+    for _ in range(150):
+        o.step_open(E, B, J, [])
+        peak = max(peak, float(np.abs(o.interior(E)[0, :, 18:, :]).max()))
+    assert abs(peak / amp - 1.0) < 0.03
+    assert np.abs(o.interior(E)[:, :, :16, :]).max() / amp < 1e-3
+    # |B| = |E| / c inside the pulse (plane wave in vacuum; the two are staggered by half a cell, so peak against peak)
+    # and the Poynting vector points along +y: S_y = (Ez Bx - Ex Bz) / mue0 > 0 where the pulse is
+    Ex, Bz = o.interior(E)[0], o.interior(B)[2]
+    assert abs(np.abs(Bz).max() * p.c / np.abs(Ex).max() - 1.0) < 0.05
+    assert (-(Ex * Bz)).sum() > 0.0
