@@ -100,6 +100,11 @@ CONFIGS = {
     "thermal": dict(shape="TSC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
     "lwfa_like": dict(shape="CIC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
     "foil_like": dict(shape="PQS", pusher="Boris", current="Esirkepov", solver="Lehe", interp="binomial"),
+    # C3 with its laser and its moving window: examples/LaserWakefield's grid, boundaries, CIC / Boris / Esirkepov / Yee,
+    # a0 = 8, 0.8 um, 5 fs pulse entering through the YMin Huygens surface (profiles::PlaneWave stands in for the example's
+    # GaussianPulse: the transversal envelope is not built), cold electron + ion plasma, the window slides (here from the
+    # start: --windowMovePoint 0) and the slab that enters is re-initialised; N >= 2 GPUs
+    "lwfa": dict(shape="CIC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
     # the slow-path cliff: relativistic electrons (the Thermal plasma) on LaserWakefield's cells, c dt / dy = 0.94 -- most
     # trajectories are too wide for the four-node window of the fused kernel and are deposited with global atomics
     "lwfa_hot": dict(shape="CIC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
@@ -117,20 +122,23 @@ def workload_name(grid, ppc, n):
         return "%s_%dx%dx%d_per_gpu_%dppc_electrons_T17.5mc2_%s_%s_%s_%s%s_periodic_d1x%dx1" % (
             "Thermal3D" if v["config"] == "thermal" else "ThermalOnLaserWakefieldCells3D_cdt_over_dy_0.94",
             grid[0], grid[1], grid[2], ppc, v["shape"], v["pusher"], v["current"], v["solver"], extra, n)
-    head = {"khi": "KelvinHelmholtz3D", "lwfa_like": "LaserWakefieldLike3D_noLaser_KHIplasma_open_y", "foil_like": "FoilLCTLike3D_KHIplasma"}[v["config"]]
+    head = {"khi": "KelvinHelmholtz3D", "lwfa_like": "LaserWakefieldLike3D_noLaser_KHIplasma_open_y", "foil_like": "FoilLCTLike3D_KHIplasma",
+            "lwfa": "LaserWakefield3D_a0_8_PlaneWaveLaser_movingWindow_coldPlasma"}[v["config"]]
     return "%s_%dx%dx%d_per_gpu_%d+%dppc_%s_%s_%s_%s%s_%s_d1x%dx1" % (
         head, grid[0], grid[1], grid[2], ppc, ppc, v["shape"], v["pusher"], v["current"], v["solver"], extra,
-        "periodic" if v["config"] != "lwfa_like" else "absorbing_y", n)
+        "periodic" if v["config"] not in ("lwfa_like", "lwfa") else "absorbing_y", n)
 
 
 def variant_kwargs():
     v = VARIANT
     kw = dict(shape=prm.SHAPE_NAMES[v["shape"]], pusher=prm.PUSHER_NAMES[v["pusher"]], current_solver=prm.CURRENT_NAMES[v["current"]],
               field_solver=prm.SOLVER_NAMES[v["solver"]], current_interpolation=1 if v["interp"] == "binomial" else 0)
-    if v["config"] == "lwfa_like":
+    if v["config"] in ("lwfa_like", "lwfa"):
         # share/picongpu/examples/LaserWakefield/include/picongpu/param/simulation.param: dt = 1.39e-16 s, cells 0.1772 um x
         # 0.4430e-7 m x 0.1772 um (c dt / dy = 0.94); --periodic 1 0 1, exponential absorber on the open axis
         kw.update(periodic=(1, 0, 1), absorber_kind=1, delta_t_si=1.39e-16, cell_si=(0.1772e-6, 0.4430e-7, 0.1772e-6))
+    if v["config"] == "lwfa":
+        kw.update(moving_window=1)
     if v["config"] == "lwfa_hot":
         kw.update(delta_t_si=1.39e-16, cell_si=(0.1772e-6, 0.4430e-7, 0.1772e-6), base_density_si=1.0e25)
     return kw
@@ -139,7 +147,13 @@ def variant_kwargs():
 def make_params(grid, **kw):
     if VARIANT["config"] in ("thermal", "lwfa_hot"):
         return prm.thermal_params(grid=grid, **kw)
-    return prm.khi_params(grid=grid, **kw)
+    p = prm.khi_params(grid=grid, **kw)
+    if VARIANT["config"] == "lwfa":
+        # examples/LaserWakefield/include/picongpu/param/incidentField.param: a0 = 8, 0.8 um, 5 fs, circular, RAMP_INIT of
+        # the PlaneWave default (PlaneWave.def:44); surface 16 cells inside (POSITION[1][0], incidentField.param)
+        p.laser = prm.plane_wave_laser(p, a0=8.0, wavelength_si=0.8e-6, pulse_duration_si=5.0e-15, ramp_init=20.6146,
+                                       polarisation="circular", offset_ymin=16)
+    return p
 
 
 # -------------------------------------------------------------------------------------------------------------------
@@ -333,6 +347,9 @@ def run_ours(args):
     def init(sm):
         if VARIANT["config"] in ("thermal", "lwfa_hot"):
             sm.init_thermal("e", args.ppc)
+        elif VARIANT["config"] == "lwfa":
+            sm.init_thermal("e", args.ppc, temperature_keV=1.0e-3, seed=42 + 2 * sm.slides)
+            sm.init_thermal("i", args.ppc, temperature_keV=1.0e-3, seed=43 + 2 * sm.slides)
         else:
             sm.init_khi(ppc_dim=ppc_dim)
 
@@ -357,7 +374,20 @@ def run_ours(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    sim.step(args.steps)
+    slides = 0
+    if VARIANT["config"] == "lwfa":
+        # Simulation::runOneStep + movingWindowCheck (Simulation.hpp:522-593): step by step, slide when the window passes a
+        # local-domain border; the rank that becomes the top of the window starts empty and gets fresh plasma
+        for k in range(args.steps):
+            step = sim.step_index
+            do_slide, _ = picstep.moving_window_info(p.global_grid[1], p.grid[1], p.cell_size[1], p.c * p.dt, 0.0, step)
+            sim.step(1)
+            if do_slide:
+                slides += 1
+                if sim.slide():
+                    init(sim)
+    else:
+        sim.step(args.steps)
     ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -382,7 +412,10 @@ def run_ours(args):
                  "note": "fraction of macro-particle updates of this rank whose current went through the global-atomic path of the fused kernel"}
     # size independent properties at the benchmark size: particle conservation (periodic), Gauss residual at round-off
     checks = {"particles_conserved": bool(abs(npart_total - npart * world) < 0.5)}
-    if VARIANT["config"] == "lwfa_like":
+    if VARIANT["config"] == "lwfa":
+        checks["window_slides_in_timed_region"] = slides
+        checks["laser_field_energy"] = float(sim.field_energy().sum())
+    if VARIANT["config"] in ("lwfa_like", "lwfa"):
         checks["particles_conserved"] = None  # open y faces absorb particles
         checks["particles_left"] = npart_total / (npart * world)
     checks["multi_gpu_vs_oracle"] = parity

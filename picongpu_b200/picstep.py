@@ -237,6 +237,7 @@ class Simulation:
             raise PicstepError("picstep_create failed (%d): %s" % (rc, self.L.picstep_last_error(None).decode()))
         self.species = {}
         self.step_index = 0
+        self.slides = 0  # number of moving-window slides so far
         N = params.padded
         self.field_shape = (3, N[2], N[1], N[0])
         for s in params.species:
@@ -388,6 +389,7 @@ class Simulation:
         """GridController::slide + Simulation::slide: returns True when this rank became the (empty) top of the window."""
         r = C.c_int32(0)
         self._chk(self.L.picstep_slide(self.ctx, C.byref(r)), "slide")
+        self.slides += 1
         n = self.p.devices[1]
         self.p.rank_pos = (self.p.rank_pos[0], (self.p.rank_pos[1] - 1 + n) % n, self.p.rank_pos[2])
         return bool(r.value)

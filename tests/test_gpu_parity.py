@@ -843,7 +843,12 @@ def test_incident_plane_wave_vs_oracle(orc, exact, polarisation):
     inside = np.sqrt((o.interior(Eg)[:, :, 18:, :] ** 2).sum(axis=0)).max()
     behind = np.abs(o.interior(Eg)[:, :, :16, :]).max()
     print("laser %s %s: peak |E| / amplitude %.4f, leak behind the surface %.2e of the amplitude" % (polarisation, "exact" if exact else "production", inside / amp, behind / amp))
-    assert abs(inside / amp - 1.0) < 0.03 and behind / amp < 1e-3
+    # one snapshot: the crest of a linearly polarised carrier (8.6 cells per wavelength) may sit between two nodes; a
+    # circularly polarised pulse has the constant modulus amplitude / sqrt(2) (getCircularPolarizationVector1, 2)
+    # (leak: the cosine component of the circular pulse switches on with 0.1 of the amplitude at RAMP_INIT = 6, a
+    # broadband transient the single matched phase velocity cannot cancel; the oracle shows the same 2.4e-3)
+    expect, tol, leak = (1.0, 0.08, 1e-3) if polarisation == "linear" else (2.0**-0.5, 0.03, 5e-3)
+    assert abs(inside / amp / expect - 1.0) < tol and behind / amp < leak
     assert np.abs(o.interior(Eg) - o.interior(E)).max() / amp < 2e-5
     assert np.abs(o.interior(Bg) - o.interior(B)).max() / (amp / p.c) < 2e-5
     s.close()
