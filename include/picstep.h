@@ -66,11 +66,12 @@ extern "C"
         PICSTEP_CURRENT_INTERPOLATION_NONE = 0,
         PICSTEP_CURRENT_INTERPOLATION_BINOMIAL = 1
     };
-    /* fields::absorber::Absorber::Kind (include/picongpu/fields/absorber/Absorber.hpp); PML is not built */
+    /* fields::absorber::Absorber::Kind (include/picongpu/fields/absorber/Absorber.hpp) */
     enum picstep_absorber
     {
         PICSTEP_ABSORBER_NONE = 0,
-        PICSTEP_ABSORBER_EXPONENTIAL = 1
+        PICSTEP_ABSORBER_EXPONENTIAL = 1,
+        PICSTEP_ABSORBER_PML = 2
     };
     /* FieldE / FieldB / FieldJ, as named through DataConnector ("E","B","J") */
     enum picstep_field
@@ -148,6 +149,14 @@ extern "C"
         float laser_phase; /* LASER_PHASE */
         float laser_pol_dir[3]; /* POLARISATION_DIRECTION (unit, orthogonal to y) */
         float laser_time_delay; /* TIME_DELAY */
+        /* absorber_kind = PICSTEP_ABSORBER_PML: convolutional PML (fields/absorber/pml/Pml.kernel, hook FDTDBase.hpp:244-298),
+         * thickness = absorber_cells; the pml:: values of param/fieldAbsorber.param:98-158 as normalised in
+         * unitless/fieldAbsorber.unitless:72-104 */
+        float pml_sigma_max[3]; /* NORMALIZED_SIGMA_MAX */
+        float pml_kappa_max[3]; /* KAPPA_MAX */
+        float pml_alpha_max[3]; /* NORMALIZED_ALPHA_MAX */
+        float pml_sigma_kappa_grading_order; /* SIGMA_KAPPA_GRADING_ORDER */
+        float pml_alpha_grading_order; /* ALPHA_GRADING_ORDER */
     } picstep_params;
 
     /* library / build information: returns e.g. "picstep sm_100a fmad=on" */

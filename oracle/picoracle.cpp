@@ -1528,6 +1528,157 @@ extern "C"
     }
 
     // ---------------------------------------------------------------------------------------------
+    // PML absorber (convolutional PML, [Taflove, Hagness] ch. 7): P/fields/absorber/pml/Pml.kernel:60-160 (relative depth,
+    // graded sigma / kappa / alpha, coefficients b and c), :420-476 (UpdateEFunctor), :520-582 (UpdateBHalfFunctor; psiB
+    // is advanced in the first half update only, FDTDBase.hpp:200-211), Pml.hpp:120-150 (local thickness: zero at faces
+    // with a neighbour).  Yee curls.  psi: six planes yx, zx, xy, zy, xz, yz over the padded grid.
+    // ---------------------------------------------------------------------------------------------
+    struct OrcPml
+    {
+        int thickness[3][2]; // local thickness in cells per [axis][negative, positive]
+        float sigmaMax[3], kappaMax[3], alphaMax[3]; // NORMALIZED_SIGMA_MAX, KAPPA_MAX, NORMALIZED_ALPHA_MAX
+        float sigmaKappaGradingOrder, alphaGradingOrder;
+    };
+
+    static inline float pml_relative_depth(float cellIdx, float nNeg, float nPos, int numLocalDomainCells, int numGuardCells)
+    {
+        float const zeroBasedIdx = cellIdx - float(numGuardCells);
+        if(zeroBasedIdx < nNeg)
+            return (nNeg - zeroBasedIdx) / nNeg;
+        float const zeroBasedRightPMLStart = float(numLocalDomainCells - 2 * numGuardCells) - nPos;
+        if(zeroBasedIdx > zeroBasedRightPMLStart)
+            return (zeroBasedIdx - zeroBasedRightPMLStart) / nPos;
+        return 0.0f;
+    }
+
+    struct PmlCoeff
+    {
+        float kappa[3], b[3], c[3];
+        bool inPml;
+    };
+
+    static inline PmlCoeff pml_coefficients(Dom const& D, OrcPml const& M, float const idx[3], float dt)
+    {
+        PmlCoeff q;
+        float prod = 1.0f;
+        for(int d = 0; d < 3; ++d)
+        {
+            float sigma = 0.0f, alpha = 0.0f;
+            q.kappa[d] = 1.0f;
+            float const depth = pml_relative_depth(idx[d], float(M.thickness[d][0]), float(M.thickness[d][1]), D.N[d], D.g[d]);
+            if(depth != 0.0f)
+            {
+                float const sk = std::pow(depth, M.sigmaKappaGradingOrder);
+                sigma = M.sigmaMax[d] * sk;
+                q.kappa[d] = 1.0f + (M.kappaMax[d] - 1.0f) * sk;
+                float const ag = std::pow(1.0f - depth, M.alphaGradingOrder);
+                alpha = M.alphaMax[d] * ag;
+            }
+            q.b[d] = std::exp(-(sigma / q.kappa[d] + alpha) * dt);
+            q.c[d] = 0.0f;
+            float const denominator = q.kappa[d] * (sigma + alpha * q.kappa[d]);
+            if(denominator != 0.0f)
+                q.c[d] = sigma * (q.b[d] - 1.0f) / denominator;
+        }
+        prod = q.b[0] * q.b[1];
+        prod = prod * q.b[2];
+        q.inPml = prod != 1.0f;
+        return q;
+    }
+
+    /** updateE with the PML functor: E += curl B c^2 dt outside the PML, the convolutional update inside */
+    void orc_update_e_pml(OrcParams const* Pp, OrcPml const* Mp, float* E, float const* B, float* psi)
+    {
+        OrcParams const& P = *Pp;
+        OrcPml const& M = *Mp;
+        Dom const D(P);
+        float const c2 = P.c * P.c;
+        float const c2dt = c2 * P.dt;
+        int64_t const sy = D.N[0], sz = int64_t(D.N[0]) * D.N[1];
+        float const *bx = B, *by = B + D.vol, *bz = B + 2 * D.vol;
+        float *ex = E, *ey = E + D.vol, *ez = E + 2 * D.vol;
+        float *pyx = psi, *pzx = psi + D.vol, *pxy = psi + 2 * D.vol, *pzy = psi + 3 * D.vol, *pxz = psi + 4 * D.vol, *pyz = psi + 5 * D.vol;
+#pragma omp parallel for schedule(static) collapse(2)
+        for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
+            for(int y = D.g[1]; y < D.g[1] + D.n[1]; ++y)
+                for(int x = D.g[0]; x < D.g[0] + D.n[0]; ++x)
+                {
+                    int64_t const i = D.idx(x, y, z);
+                    // backward differences (CurlB of the Yee solver), d<comp>d<axis>
+                    float const dBzdy = (bz[i] - bz[i - sy]) / P.cell[1], dBydz = (by[i] - by[i - sz]) / P.cell[2];
+                    float const dBxdz = (bx[i] - bx[i - sz]) / P.cell[2], dBzdx = (bz[i] - bz[i - 1]) / P.cell[0];
+                    float const dBydx = (by[i] - by[i - 1]) / P.cell[0], dBxdy = (bx[i] - bx[i - sy]) / P.cell[1];
+                    float const idx[3] = {float(x), float(y), float(z)};
+                    PmlCoeff const q = pml_coefficients(D, M, idx, P.dt);
+                    if(q.inPml)
+                    {
+                        pyx[i] = q.b[0] * pyx[i] + q.c[0] * dBzdx;
+                        pzx[i] = q.b[0] * pzx[i] + q.c[0] * dBydx;
+                        pxy[i] = q.b[1] * pxy[i] + q.c[1] * dBzdy;
+                        pzy[i] = q.b[1] * pzy[i] + q.c[1] * dBxdy;
+                        pxz[i] = q.b[2] * pxz[i] + q.c[2] * dBydz;
+                        pyz[i] = q.b[2] * pyz[i] + q.c[2] * dBxdz;
+                        ex[i] += c2dt * (dBzdy / q.kappa[1] - dBydz / q.kappa[2] + pxy[i] - pxz[i]);
+                        ey[i] += c2dt * (dBxdz / q.kappa[2] - dBzdx / q.kappa[0] + pyz[i] - pyx[i]);
+                        ez[i] += c2dt * (dBydx / q.kappa[0] - dBxdy / q.kappa[1] + pzx[i] - pzy[i]);
+                    }
+                    else
+                    {
+                        ex[i] += (dBzdy - dBydz) * c2 * P.dt;
+                        ey[i] += (dBxdz - dBzdx) * c2 * P.dt;
+                        ez[i] += (dBydx - dBxdy) * c2 * P.dt;
+                    }
+                }
+    }
+
+    /** updateBHalf with the PML functor; updatePsi: first half update of the step (FDTDBase.hpp:200-211) */
+    void orc_update_b_half_pml(OrcParams const* Pp, OrcPml const* Mp, float const* E, float* B, float* psi, int updatePsi)
+    {
+        OrcParams const& P = *Pp;
+        OrcPml const& M = *Mp;
+        Dom const D(P);
+        float const halfDt = 0.5f * P.dt;
+        int64_t const sy = D.N[0], sz = int64_t(D.N[0]) * D.N[1];
+        float const *ex = E, *ey = E + D.vol, *ez = E + 2 * D.vol;
+        float *bx = B, *by = B + D.vol, *bz = B + 2 * D.vol;
+        float *pyx = psi, *pzx = psi + D.vol, *pxy = psi + 2 * D.vol, *pzy = psi + 3 * D.vol, *pxz = psi + 4 * D.vol, *pyz = psi + 5 * D.vol;
+#pragma omp parallel for schedule(static) collapse(2)
+        for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
+            for(int y = D.g[1]; y < D.g[1] + D.n[1]; ++y)
+                for(int x = D.g[0]; x < D.g[0] + D.n[0]; ++x)
+                {
+                    int64_t const i = D.idx(x, y, z);
+                    // forward differences (CurlE of the Yee solver)
+                    float const dEzdy = (ez[i + sy] - ez[i]) / P.cell[1], dEydz = (ey[i + sz] - ey[i]) / P.cell[2];
+                    float const dExdz = (ex[i + sz] - ex[i]) / P.cell[2], dEzdx = (ez[i + 1] - ez[i]) / P.cell[0];
+                    float const dEydx = (ey[i + 1] - ey[i]) / P.cell[0], dExdy = (ex[i + sy] - ex[i]) / P.cell[1];
+                    float const idx[3] = {0.5f + float(x), 0.5f + float(y), 0.5f + float(z)};
+                    PmlCoeff const q = pml_coefficients(D, M, idx, P.dt);
+                    if(q.inPml)
+                    {
+                        if(updatePsi)
+                        {
+                            pyx[i] = q.b[0] * pyx[i] + q.c[0] * dEzdx;
+                            pzx[i] = q.b[0] * pzx[i] + q.c[0] * dEydx;
+                            pxy[i] = q.b[1] * pxy[i] + q.c[1] * dEzdy;
+                            pzy[i] = q.b[1] * pzy[i] + q.c[1] * dExdy;
+                            pxz[i] = q.b[2] * pxz[i] + q.c[2] * dEydz;
+                            pyz[i] = q.b[2] * pyz[i] + q.c[2] * dExdz;
+                        }
+                        bx[i] += halfDt * (dEydz / q.kappa[2] - dEzdy / q.kappa[1] + pxz[i] - pxy[i]);
+                        by[i] += halfDt * (dEzdx / q.kappa[0] - dExdz / q.kappa[2] + pyx[i] - pyz[i]);
+                        bz[i] += halfDt * (dExdy / q.kappa[1] - dEydx / q.kappa[0] + pzy[i] - pzx[i]);
+                    }
+                    else
+                    {
+                        bx[i] -= (dEzdy - dEydz) * halfDt;
+                        by[i] -= (dExdz - dEzdx) * halfDt;
+                        bz[i] -= (dEydx - dExdy) * halfDt;
+                    }
+                }
+    }
+
+    // ---------------------------------------------------------------------------------------------
     // Incident field (laser) through the YMin Huygens surface: P/fields/incidentField/Solver.hpp:190-395 (updateField),
     // Solver.kernel:101-404 (UpdateFunctor for the Yee solver: margin 1, one derivative coefficient = 1),
     // Functors.hpp (BaseFunctorE::getCurrentTime, BaseSeparableFunctorE::operator(), ApproximateIncidentB),

@@ -78,6 +78,39 @@ def make_laser(cfg):
     return L
 
 
+class OrcPml(C.Structure):
+    """PML absorber parameters (oracle/picoracle.cpp: struct OrcPml)"""
+
+    _fields_ = [
+        ("thickness", (C.c_int * 2) * 3),
+        ("sigmaMax", C.c_float * 3),
+        ("kappaMax", C.c_float * 3),
+        ("alphaMax", C.c_float * 3),
+        ("sigmaKappaGradingOrder", C.c_float),
+        ("alphaGradingOrder", C.c_float),
+    ]
+
+
+def make_pml(cfg):
+    """absorber_kind 2: thickness from absorber_cells at the open faces, parameters from cfg.pml (param.pml_params)"""
+    g = (lambda k: cfg[k]) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k))
+    if not (_has(cfg, "absorber_kind") and int(g("absorber_kind")) == 2):
+        return None
+    M = OrcPml()
+    pm = g("pml")
+    for d in range(3):
+        for sd in range(2):
+            M.thickness[d][sd] = int(g("absorber_cells")[d][sd]) if int(g("open")[d][sd]) else 0
+        M.sigmaMax[d] = float(pm["sigma_max"][d])
+        M.kappaMax[d] = float(pm["kappa_max"][d])
+        M.alphaMax[d] = float(pm["alpha_max"][d])
+    if _has(cfg, "moving_window") and int(g("moving_window")):
+        M.thickness[1][1] = 0
+    M.sigmaKappaGradingOrder = float(pm["sigma_kappa_grading_order"])
+    M.alphaGradingOrder = float(pm["alpha_grading_order"])
+    return M
+
+
 class OrcSpecies(C.Structure):
     _fields_ = [
         ("massRatio", C.c_float),
@@ -143,6 +176,8 @@ def lib():
                                f32p, f32p, f32p, i32p, f32p, f32p, f32p, i32p]
     L.orc_absorb.argtypes = [P, f32p]
     L.orc_incident_update.argtypes = [P, C.POINTER(OrcLaser), f32p, C.c_int, C.c_float]
+    L.orc_update_e_pml.argtypes = [P, C.POINTER(OrcPml), f32p, f32p, f32p]
+    L.orc_update_b_half_pml.argtypes = [P, C.POINTER(OrcPml), f32p, f32p, f32p, C.c_int]
     L.orc_num_threads.restype = C.c_int
     L.orc_set_num_threads.argtypes = [C.c_int]
     _LIB = L
@@ -196,6 +231,10 @@ class Oracle:
         self.g = tuple(self.p.g)
         self.N = tuple(self.p.n[d] + 2 * self.p.g[d] for d in range(3))
         self.laser = make_laser(cfg)
+        self.pml = make_pml(cfg)
+        if self.pml is not None:  # convolutional fields psi_yx, zx, xy, zy, xz, yz of E and B
+            self.psiE = np.zeros((6, self.N[2], self.N[1], self.N[0]), np.float32)
+            self.psiB = np.zeros((6, self.N[2], self.N[1], self.N[0]), np.float32)
         self.step_index = 0  # step_open counts the steps (the incident field is a function of time)
 
     def field(self):
@@ -232,11 +271,18 @@ class Oracle:
     def halo_axis(self, F, axis, lo, up, add=False):
         self.L.orc_halo_axis(C.byref(self.p), F, F.shape[0], axis, lo, up, 1 if add else 0)
 
-    def update_b_half(self, E, B):
-        self.L.orc_update_b_half(C.byref(self.p), E, B)
+    def update_b_half(self, E, B, first_half=False):
+        """first_half: updateBFirstHalf (advances the PML's psiB; FDTDBase.hpp:200-211), else updateBSecondHalf"""
+        if self.pml is not None:
+            self.L.orc_update_b_half_pml(C.byref(self.p), C.byref(self.pml), E, B, self.psiB, 1 if first_half else 0)
+        else:
+            self.L.orc_update_b_half(C.byref(self.p), E, B)
 
     def update_e(self, E, B):
-        self.L.orc_update_e(C.byref(self.p), E, B)
+        if self.pml is not None:
+            self.L.orc_update_e_pml(C.byref(self.p), C.byref(self.pml), E, B, self.psiE)
+        else:
+            self.L.orc_update_e(C.byref(self.p), E, B)
 
     def add_current(self, E, J):
         self.L.orc_add_current(C.byref(self.p), E, J)
@@ -303,7 +349,7 @@ class Oracle:
         self.absorb(E)
         self.incident_update(B, False, self.step_index + 1.0)  # FDTDBase.hpp:161-166
         copy_guards(E)
-        self.update_b_half(E, B)
+        self.update_b_half(E, B, first_half=True)
         self.absorb(B)
         copy_guards(B)
         self.step_index += 1

@@ -107,6 +107,16 @@ namespace picstep
         int updatedIsE;
     };
 
+    // convolutional PML (fields.cu: pmlUpdate*Kernel): local thickness per [axis][negative, positive], graded parameters,
+    // psi = six planes yx, zx, xy, zy, xz, yz over the padded grid
+    struct PmlDev
+    {
+        int thickness[3][2];
+        float sigmaMax[3], kappaMax[3], alphaMax[3];
+        float sigmaKappaGradingOrder, alphaGradingOrder;
+        float* psi;
+    };
+
     struct SpeciesDev
     {
         float* pos[3];

@@ -283,6 +283,154 @@ namespace picstep
         }
     }
 
+    // ---- PML absorber (convolutional PML, Yee curls) ----------------------------------------------------------------
+    // Reference: fields/absorber/pml/Pml.kernel:60-160 (relative depth, graded sigma / kappa / alpha, coefficients b, c),
+    // :420-476 UpdateEFunctor, :520-582 UpdateBHalfFunctor; hook FDTDBase.hpp:244-298.  One thread per cell of the whole
+    // domain (the branch "not in the PML" is the plain Yee update), same float operations as the oracle's restatement.
+    struct PmlCoeff
+    {
+        float kappa[3], b[3], c[3];
+        bool inPml;
+    };
+
+    __device__ __forceinline__ float pmlRelativeDepth(float cellIdx, float nNeg, float nPos, int numLocalDomainCells, int numGuardCells)
+    {
+        float const zeroBasedIdx = cellIdx - float(numGuardCells);
+        if(zeroBasedIdx < nNeg)
+            return (nNeg - zeroBasedIdx) / nNeg;
+        float const zeroBasedRightPMLStart = float(numLocalDomainCells - 2 * numGuardCells) - nPos;
+        if(zeroBasedIdx > zeroBasedRightPMLStart)
+            return (zeroBasedIdx - zeroBasedRightPMLStart) / nPos;
+        return 0.0f;
+    }
+
+    __device__ __forceinline__ PmlCoeff pmlCoefficients(DevParams const& P, PmlDev const& M, float const idx[3])
+    {
+        PmlCoeff q;
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+        {
+            float sigma = 0.0f, alpha = 0.0f;
+            q.kappa[d] = 1.0f;
+            float const depth = pmlRelativeDepth(idx[d], float(M.thickness[d][0]), float(M.thickness[d][1]), P.N[d], P.g[d]);
+            if(depth != 0.0f)
+            {
+                float const sk = powf(depth, M.sigmaKappaGradingOrder);
+                sigma = M.sigmaMax[d] * sk;
+                q.kappa[d] = 1.0f + (M.kappaMax[d] - 1.0f) * sk;
+                float const ag = powf(1.0f - depth, M.alphaGradingOrder);
+                alpha = M.alphaMax[d] * ag;
+            }
+            q.b[d] = expf(-(sigma / q.kappa[d] + alpha) * P.dt);
+            q.c[d] = 0.0f;
+            float const denominator = q.kappa[d] * (sigma + alpha * q.kappa[d]);
+            if(denominator != 0.0f)
+                q.c[d] = sigma * (q.b[d] - 1.0f) / denominator;
+        }
+        float prod = q.b[0] * q.b[1];
+        prod = prod * q.b[2];
+        q.inPml = prod != 1.0f;
+        return q;
+    }
+
+    __global__ void __launch_bounds__(256) pmlUpdateEKernel(DevParams P, PmlDev M, Field3 E, Field3 B)
+    {
+        int const x = blockIdx.x * blockDim.x + threadIdx.x + P.g[0];
+        int const y = blockIdx.y * blockDim.y + threadIdx.y + P.g[1];
+        int const z = blockIdx.z * blockDim.z + threadIdx.z + P.g[2];
+        if(x >= P.g[0] + P.n[0] || y >= P.g[1] + P.n[1] || z >= P.g[2] + P.n[2])
+            return;
+        long long const sy = P.N[0], sz = (long long) P.N[0] * P.N[1];
+        long long const i = fidx(P, x, y, z);
+        float const *bx = B.c[0], *by = B.c[1], *bz = B.c[2];
+        float const dBzdy = (bz[i] - bz[i - sy]) / P.cell[1], dBydz = (by[i] - by[i - sz]) / P.cell[2];
+        float const dBxdz = (bx[i] - bx[i - sz]) / P.cell[2], dBzdx = (bz[i] - bz[i - 1]) / P.cell[0];
+        float const dBydx = (by[i] - by[i - 1]) / P.cell[0], dBxdy = (bx[i] - bx[i - sy]) / P.cell[1];
+        float const c2 = P.c * P.c;
+        float const idx[3] = {float(x), float(y), float(z)};
+        PmlCoeff const q = pmlCoefficients(P, M, idx);
+        if(q.inPml)
+        {
+            float const c2dt = c2 * P.dt;
+            float* const pyx = M.psi + i;
+            float* const pzx = pyx + P.vol;
+            float* const pxy = pzx + P.vol;
+            float* const pzy = pxy + P.vol;
+            float* const pxz = pzy + P.vol;
+            float* const pyz = pxz + P.vol;
+            float const vyx = q.b[0] * *pyx + q.c[0] * dBzdx, vzx = q.b[0] * *pzx + q.c[0] * dBydx;
+            float const vxy = q.b[1] * *pxy + q.c[1] * dBzdy, vzy = q.b[1] * *pzy + q.c[1] * dBxdy;
+            float const vxz = q.b[2] * *pxz + q.c[2] * dBydz, vyz = q.b[2] * *pyz + q.c[2] * dBxdz;
+            *pyx = vyx;
+            *pzx = vzx;
+            *pxy = vxy;
+            *pzy = vzy;
+            *pxz = vxz;
+            *pyz = vyz;
+            E.c[0][i] += c2dt * (dBzdy / q.kappa[1] - dBydz / q.kappa[2] + vxy - vxz);
+            E.c[1][i] += c2dt * (dBxdz / q.kappa[2] - dBzdx / q.kappa[0] + vyz - vyx);
+            E.c[2][i] += c2dt * (dBydx / q.kappa[0] - dBxdy / q.kappa[1] + vzx - vzy);
+        }
+        else
+        {
+            E.c[0][i] += (dBzdy - dBydz) * c2 * P.dt;
+            E.c[1][i] += (dBxdz - dBzdx) * c2 * P.dt;
+            E.c[2][i] += (dBydx - dBxdy) * c2 * P.dt;
+        }
+    }
+
+    __global__ void __launch_bounds__(256) pmlUpdateBHalfKernel(DevParams P, PmlDev M, Field3 E, Field3 B, int updatePsi)
+    {
+        int const x = blockIdx.x * blockDim.x + threadIdx.x + P.g[0];
+        int const y = blockIdx.y * blockDim.y + threadIdx.y + P.g[1];
+        int const z = blockIdx.z * blockDim.z + threadIdx.z + P.g[2];
+        if(x >= P.g[0] + P.n[0] || y >= P.g[1] + P.n[1] || z >= P.g[2] + P.n[2])
+            return;
+        long long const sy = P.N[0], sz = (long long) P.N[0] * P.N[1];
+        long long const i = fidx(P, x, y, z);
+        float const *ex = E.c[0], *ey = E.c[1], *ez = E.c[2];
+        float const dEzdy = (ez[i + sy] - ez[i]) / P.cell[1], dEydz = (ey[i + sz] - ey[i]) / P.cell[2];
+        float const dExdz = (ex[i + sz] - ex[i]) / P.cell[2], dEzdx = (ez[i + 1] - ez[i]) / P.cell[0];
+        float const dEydx = (ey[i + 1] - ey[i]) / P.cell[0], dExdy = (ex[i + sy] - ex[i]) / P.cell[1];
+        float const halfDt = 0.5f * P.dt;
+        float const idx[3] = {0.5f + float(x), 0.5f + float(y), 0.5f + float(z)};
+        PmlCoeff const q = pmlCoefficients(P, M, idx);
+        if(q.inPml)
+        {
+            float* const pyx = M.psi + i;
+            float* const pzx = pyx + P.vol;
+            float* const pxy = pzx + P.vol;
+            float* const pzy = pxy + P.vol;
+            float* const pxz = pzy + P.vol;
+            float* const pyz = pxz + P.vol;
+            float vyx = *pyx, vzx = *pzx, vxy = *pxy, vzy = *pzy, vxz = *pxz, vyz = *pyz;
+            if(updatePsi)
+            {
+                vyx = q.b[0] * vyx + q.c[0] * dEzdx;
+                vzx = q.b[0] * vzx + q.c[0] * dEydx;
+                vxy = q.b[1] * vxy + q.c[1] * dEzdy;
+                vzy = q.b[1] * vzy + q.c[1] * dExdy;
+                vxz = q.b[2] * vxz + q.c[2] * dEydz;
+                vyz = q.b[2] * vyz + q.c[2] * dExdz;
+                *pyx = vyx;
+                *pzx = vzx;
+                *pxy = vxy;
+                *pzy = vzy;
+                *pxz = vxz;
+                *pyz = vyz;
+            }
+            B.c[0][i] += halfDt * (dEydz / q.kappa[2] - dEzdy / q.kappa[1] + vxz - vxy);
+            B.c[1][i] += halfDt * (dEzdx / q.kappa[0] - dExdz / q.kappa[2] + vyx - vyz);
+            B.c[2][i] += halfDt * (dExdy / q.kappa[1] - dEydx / q.kappa[0] + vzy - vzx);
+        }
+        else
+        {
+            B.c[0][i] -= (dEzdy - dEydz) * halfDt;
+            B.c[1][i] -= (dExdz - dEzdx) * halfDt;
+            B.c[2][i] -= (dEydx - dExdy) * halfDt;
+        }
+    }
+
     // ---- incident field (laser): PlaneWave profile through the YMin Huygens surface, Yee solver --------------------
     // Reference: fields/incidentField/Solver.hpp:190-395 (updateField: which plane, in-cell shifts, coefficients),
     // Solver.kernel:101-404 (UpdateFunctor; Yee: margin 1, single derivative coefficient 1), Functors.hpp
@@ -732,6 +880,20 @@ namespace picstep
     static inline dim3 cellGrid(DevParams const& P, dim3 b)
     {
         return dim3((P.n[0] + b.x - 1) / b.x, (P.n[1] + b.y - 1) / b.y, (P.n[2] + b.z - 1) / b.z);
+    }
+
+    cudaError_t launchPmlUpdateE(DevParams const& P, PmlDev const& M, Field3 E, Field3 B, cudaStream_t st)
+    {
+        dim3 const b(32, 4, 2);
+        pmlUpdateEKernel<<<dim3((P.n[0] + b.x - 1) / b.x, (P.n[1] + b.y - 1) / b.y, (P.n[2] + b.z - 1) / b.z), b, 0, st>>>(P, M, E, B);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchPmlUpdateBHalf(DevParams const& P, PmlDev const& M, Field3 E, Field3 B, bool updatePsi, cudaStream_t st)
+    {
+        dim3 const b(32, 4, 2);
+        pmlUpdateBHalfKernel<<<dim3((P.n[0] + b.x - 1) / b.x, (P.n[1] + b.y - 1) / b.y, (P.n[2] + b.z - 1) / b.z), b, 0, st>>>(P, M, E, B, updatePsi ? 1 : 0);
+        return cudaGetLastError();
     }
 
     cudaError_t launchIncident(DevParams const& P, Field3 F, LaserDev const& L, cudaStream_t st)

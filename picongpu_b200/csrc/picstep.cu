@@ -41,6 +41,8 @@ namespace picstep
     void fdtdBox(int*);
     cudaError_t launchFdtdTma(int, bool, DevParams const&, Field3, Field3, CUtensorMap const&, int, cudaStream_t);
     cudaError_t launchIncident(DevParams const&, Field3, LaserDev const&, cudaStream_t);
+    cudaError_t launchPmlUpdateE(DevParams const&, PmlDev const&, Field3, Field3, cudaStream_t);
+    cudaError_t launchPmlUpdateBHalf(DevParams const&, PmlDev const&, Field3, Field3, bool, cudaStream_t);
     cudaError_t launchUpdateBHalf(int, DevParams const&, LeheCoeffs const&, Field3, Field3, cudaStream_t);
     cudaError_t launchUpdateE(DevParams const&, LeheCoeffs const&, Field3, Field3, cudaStream_t);
     cudaError_t launchAddCurrent(DevParams const&, Field3, Field3, bool, cudaStream_t);
@@ -109,6 +111,9 @@ struct picstep_ctx
     TileMaps tileMaps{}; // TMA descriptors of E and B for the supercell tile of this shape
     alignas(64) CUtensorMap fdtdMap[2]; // TMA descriptors of E and B for the brick (+ halo) of the Yee update kernels
     bool fdtdTma = false;
+    bool pmlOn = false; // absorber_kind == PML: the field update runs the PML functors (per-cell kernels)
+    PmlDev pmlE{}, pmlB{}; // the same parameters with the convolutional fields psiE / psiB
+    float* psiMem = nullptr; // 12 * vol floats
     int widthShape = 0; // the widest shape of any species: guard exchange margins follow it
     uint32_t* migPinned = nullptr; // pinned readback of the migration counts of all species (overlapped step)
     cudaEvent_t evBorder = nullptr, evComm = nullptr;
@@ -588,6 +593,11 @@ namespace
                     cells = 0; // the absorber on the +y side is off while the window slides (Exponential.hpp:97-101)
                 c->absorber.cells[d][sd] = cells;
                 c->absorbing = c->absorbing || cells > 1;
+                // PML: local thickness, zero at faces with a neighbour and at +y while the window slides (Pml.hpp:120-150)
+                int pmlCells = (p->absorber_kind == PICSTEP_ABSORBER_PML && !nb[sd]) ? p->absorber_cells[d][sd] : 0;
+                if(p->moving_window && d == 1 && sd == 1)
+                    pmlCells = 0;
+                c->pmlE.thickness[d][sd] = c->pmlB.thickness[d][sd] = pmlCells;
                 for(int f = 0; f < cells; ++f) // math::exp(-absorberStrength * float_X(factor)) (Exponential.kernel:107)
                     damp[size_t(2 * d + sd) * ABS_MAX + f] = std::exp(-p->absorber_strength[d][sd] * float(f));
             }
@@ -755,7 +765,9 @@ extern "C"
             if(p->laser_polarisation < 0 || p->laser_polarisation > 1 || !(p->laser_omega > 0.0f) || !(p->laser_pulse_duration > 0.0f))
                 return fail(nullptr, PICSTEP_ERR_INVALID, "bad incident field parameters");
         }
-        if(p->current_interpolation < 0 || p->current_interpolation > 1 || p->absorber_kind < 0 || p->absorber_kind > 1)
+        if(p->absorber_kind == PICSTEP_ABSORBER_PML && p->field_solver != PICSTEP_SOLVER_YEE)
+            return fail(nullptr, PICSTEP_ERR_INVALID, "the PML is built for the Yee solver");
+        if(p->current_interpolation < 0 || p->current_interpolation > 1 || p->absorber_kind < 0 || p->absorber_kind > 2)
             return fail(nullptr, PICSTEP_ERR_INVALID, "unknown current interpolation / absorber kind");
         for(int d = 0; d < 3; ++d)
             for(int sd = 0; sd < 2; ++sd) // only faces that can absorb (non-periodic axes) are checked
@@ -867,6 +879,32 @@ extern "C"
                 if(makeTileMap(&c->fdtdMap[f], c->fieldAlloc[f], P.N, P.vol, fbox, msg, sizeof(msg)))
                     c->fdtdTma = false;
         }
+        if(p->absorber_kind == PICSTEP_ABSORBER_PML)
+        {
+            for(int d = 0; d < 3; ++d)
+                if(c->pmlE.thickness[d][0] + c->pmlE.thickness[d][1] > P.n[d])
+                {
+                    picstep_destroy(c);
+                    return fail(nullptr, PICSTEP_ERR_INVALID, "requested PML size exceeds the local domain");
+                }
+            c->pmlOn = true;
+            c->fdtdTma = false; // the PML functors are per-cell kernels
+            CUC(cudaMalloc(&c->psiMem, sizeof(float) * 12 * P.vol));
+            CUC(cudaMemsetAsync(c->psiMem, 0, sizeof(float) * 12 * P.vol, c->stream));
+            for(PmlDev* m : {&c->pmlE, &c->pmlB})
+            {
+                for(int d = 0; d < 3; ++d)
+                {
+                    m->sigmaMax[d] = p->pml_sigma_max[d];
+                    m->kappaMax[d] = p->pml_kappa_max[d];
+                    m->alphaMax[d] = p->pml_alpha_max[d];
+                }
+                m->sigmaKappaGradingOrder = p->pml_sigma_kappa_grading_order;
+                m->alphaGradingOrder = p->pml_alpha_grading_order;
+            }
+            c->pmlE.psi = c->psiMem;
+            c->pmlB.psi = c->psiMem + 6 * P.vol;
+        }
         CUC(cudaMalloc(&c->dampDev, sizeof(float) * damp.size()));
         CUC(cudaMemcpy(c->dampDev, damp.data(), sizeof(float) * damp.size(), cudaMemcpyHostToDevice));
         c->absorber.damp = c->dampDev;
@@ -915,6 +953,7 @@ extern "C"
         for(int b = 0; b < 4; ++b)
             cudaFree(c->haloBuf[b]);
         cudaFree(c->redBuf);
+        cudaFree(c->psiMem);
         cudaFree(c->P.stats);
         cudaFree(c->dampDev);
         cudaFree(c->flags);
@@ -1417,10 +1456,12 @@ extern "C"
     }
 
     // B -= curl E * dt/2 (updateBFirstHalf / updateBSecondHalf)
-    static int updateBHalf(picstep_ctx* c)
+    static int updateBHalf(picstep_ctx* c, bool firstHalf)
     {
         Field3 E = fieldOf(c, PICSTEP_FIELD_E), B = fieldOf(c, PICSTEP_FIELD_B);
-        if(c->fdtdTma)
+        if(c->pmlOn) // psiB is advanced once per step, in the first half update (FDTDBase.hpp:200-211)
+            KL(c, 1, launchPmlUpdateBHalf(c->P, c->pmlB, E, B, firstHalf, c->stream));
+        else if(c->fdtdTma)
             KL(c, 1, launchFdtdTma(0, false, c->P, B, B, c->fdtdMap[PICSTEP_FIELD_E], c->tileMaps.lead, c->stream));
         else
             KL(c, 1, launchUpdateBHalf(c->prm.field_solver, c->P, c->lehe, E, B, c->stream));
@@ -1432,7 +1473,7 @@ extern "C"
     {
         StageTimer t(c, 3);
         Field3 E = fieldOf(c, PICSTEP_FIELD_E), B = fieldOf(c, PICSTEP_FIELD_B);
-        int rc = updateBHalf(c); // updateBSecondHalf
+        int rc = updateBHalf(c, false); // updateBSecondHalf
         if(!rc)
             rc = incidentUpdate(c, false, float(step)); // B by half a step with E_inc at t = step
         if(rc)
@@ -1442,7 +1483,9 @@ extern "C"
             rc = incidentUpdate(c, true, float(step) + 0.5f); // E with B_inc at t = step + 1/2, before the E update
         if(rc)
             return rc;
-        if(c->fdtdTma)
+        if(c->pmlOn)
+            KL(c, 1, launchPmlUpdateE(c->P, c->pmlE, E, B, c->stream));
+        else if(c->fdtdTma)
             KL(c, 1, launchFdtdTma(1, addJ, c->P, E, fieldOf(c, PICSTEP_FIELD_J), c->fdtdMap[PICSTEP_FIELD_B], c->tileMaps.lead, c->stream));
         else
             KL(c, 1, launchUpdateE(c->P, c->lehe, E, B, c->stream));
@@ -1580,7 +1623,7 @@ extern "C"
             rc = exchangeField(c, PICSTEP_FIELD_E);
         if(rc)
             return rc;
-        rc = updateBHalf(c); // updateBFirstHalf
+        rc = updateBHalf(c, true); // updateBFirstHalf
         if(rc)
             return rc;
         if(c->absorbing) // exponentialImpl.run(B) (FDTDBase.hpp:175-179)
@@ -1610,6 +1653,8 @@ extern "C"
         {
             for(int f = 0; f < 3; ++f)
                 CU(c, cudaMemsetAsync(c->fieldAlloc[f], 0, sizeof(float) * (3 * c->P.vol + 4), c->stream));
+            if(c->psiMem)
+                CU(c, cudaMemsetAsync(c->psiMem, 0, sizeof(float) * 12 * c->P.vol, c->stream));
             size_t const ncell = size_t(numCells(c));
             for(auto& s : c->species)
             {

@@ -63,10 +63,12 @@ class SimParams:
     # --- --currentInterpolation (0 none, 1 binomial); fieldAbsorber.param (0 none, 1 exponential; NUM_CELLS and
     #     exponential::STRENGTH per [axis][negative, positive], only used at non-periodic outer boundaries) ---
     current_interpolation: int = 0
-    absorber_kind: int = 0
+    absorber_kind: int = 0  # 0 none, 1 exponential, 2 PML
     absorber_cells: tuple = ((12, 12), (12, 12), (12, 12))
     absorber_strength: tuple = ((1.0e-3, 1.0e-3), (1.0e-3, 1.0e-3), (1.0e-3, 1.0e-3))
     moving_window: int = 0  # -m: sliding window along y (needs a non-periodic y axis)
+    # fieldAbsorber.param pml:: values (dict from pml_params(), PIC units); used with absorber_kind = 2
+    pml: dict = None
     # incidentField.param: PlaneWave profile on YMin (dict from plane_wave_laser(), PIC units) or None = profiles::None
     laser: dict = None
     # --- runtime (-d, --periodic) ---
@@ -175,4 +177,21 @@ def plane_wave_laser(p, a0=1.0, wavelength_si=0.8e-6, pulse_duration_si=5.0e-15,
         phase=_f32(phase),
         pol=tuple(_f32(v) for v in pol_dir),
         time_delay=_f32(time_delay_si / p.unit_time),
+    )
+
+
+def pml_params(p, sigma_kappa_grading_order=4.0, sigma_opt_multiplier=1.0, kappa_max=(1.0, 1.0, 1.0), alpha_grading_order=1.0,
+               alpha_max_si=(0.2, 0.2, 0.2)):
+    """include/picongpu/param/fieldAbsorber.param:98-158 (pml:: defaults) converted as in
+    unitless/fieldAbsorber.unitless:72-104: SIGMA_OPT_SI = 0.8 (order + 1) / (Z0 * cell size), normalised by eps0 and
+    the unit of time."""
+    eps0_si = 1.0 / (MUE0_SI * SPEED_OF_LIGHT_SI**2)
+    z0_si = MUE0_SI * SPEED_OF_LIGHT_SI
+    sigma_max_si = [0.8 * (sigma_kappa_grading_order + 1.0) / (z0_si * c) * sigma_opt_multiplier for c in p.cell_si]
+    return dict(
+        sigma_max=tuple(_f32(s / eps0_si * p.unit_time) for s in sigma_max_si),
+        kappa_max=tuple(_f32(k) for k in kappa_max),
+        alpha_max=tuple(_f32(a / eps0_si * p.unit_time) for a in alpha_max_si),
+        sigma_kappa_grading_order=_f32(sigma_kappa_grading_order),
+        alpha_grading_order=_f32(alpha_grading_order),
     )

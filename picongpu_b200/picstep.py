@@ -76,6 +76,11 @@ class Params(C.Structure):
         ("laser_phase", C.c_float),
         ("laser_pol_dir", C.c_float * 3),
         ("laser_time_delay", C.c_float),
+        ("pml_sigma_max", C.c_float * 3),
+        ("pml_kappa_max", C.c_float * 3),
+        ("pml_alpha_max", C.c_float * 3),
+        ("pml_sigma_kappa_grading_order", C.c_float),
+        ("pml_alpha_grading_order", C.c_float),
     ]
 
 
@@ -159,6 +164,12 @@ def to_c_params(p, device=0, flags=0):
     cp.current_interpolation = int(getattr(p, "current_interpolation", 0))
     cp.absorber_kind = int(getattr(p, "absorber_kind", 0))
     cp.moving_window = int(getattr(p, "moving_window", 0))
+    pm = getattr(p, "pml", None)
+    if pm:
+        for d in range(3):
+            cp.pml_sigma_max[d], cp.pml_kappa_max[d], cp.pml_alpha_max[d] = pm["sigma_max"][d], pm["kappa_max"][d], pm["alpha_max"][d]
+        cp.pml_sigma_kappa_grading_order = pm["sigma_kappa_grading_order"]
+        cp.pml_alpha_grading_order = pm["alpha_grading_order"]
     las = getattr(p, "laser", None)
     if las:
         cp.laser_enabled = 1

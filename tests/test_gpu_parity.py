@@ -874,6 +874,59 @@ def test_incident_plane_wave_vs_oracle(orc, exact, polarisation):
     s.close()
 
 
+@pytest.mark.parametrize("exact", [True, False])
+def test_pml_vs_oracle(orc, exact):
+    """PML absorber (fields/absorber/pml/Pml.kernel, hook FDTDBase.hpp:244-298) on all three axes with different
+    thicknesses per face: fields and the coupled step (KHI plasma, absorbing particle boundary) against the oracle's
+    restatement.  pow / exp of the graded coefficients are the device's, hence a tolerance also in the exact build."""
+    p = util.make_params((24, 16, 8), periodic=(0, 0, 0), absorber_kind=2, absorber_cells=((6, 5), (4, 7), (3, 2)))
+    p.pml = prm.pml_params(p)
+    E0, B0 = util.smooth_fields(p, seed=61, amp=0.05)
+    o, e, i = util.khi_ic(orc, p)
+    s = _sim(p, exact)
+    s.upload_field(FE, E0)
+    s.upload_field(FB, B0)
+    for name, sp in (("e", e), ("i", i)):
+        s.upload_particles(name, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+    E, B, J = E0.copy(), B0.copy(), o.field()
+    sps = [e, i]
+    steps = 25
+    for _ in range(steps):
+        o.step_open(E, B, J, sps)
+    s.step(steps)
+    s.sync()
+    Eg, Bg = s.download_field(FE), s.download_field(FB)
+    dE = np.abs(o.interior(Eg) - o.interior(E)).max() / np.abs(o.interior(E)).max()
+    dB = np.abs(o.interior(Bg) - o.interior(B)).max() / np.abs(o.interior(B)).max()
+    print("PML %s: dE %.2e dB %.2e" % ("exact" if exact else "production", dE, dB))
+    assert dE < 5e-5 and dB < 5e-5
+    assert abs(s.particle_count("e") - sps[0]["w"].shape[0]) <= (0 if exact else 3)
+    s.close()
+
+
+def test_pml_absorbs_outgoing_wave():
+    """Physics check: a pulse leaving through PML faces is gone (remaining field energy < 1e-6 of the start; the
+    exponential absorber of the same thickness leaves 20 %, the oracle's PML 2e-13)."""
+    p = util.make_params((64, 8, 4), periodic=(0, 1, 1), absorber_kind=2, absorber_cells=((12, 12), (0, 0), (0, 0)))
+    p.pml = prm.pml_params(p)
+    s = _sim(p, False)
+    N = p.padded
+    x = np.arange(N[0]) - p.guard_cells[0]
+    E = np.zeros((3, N[2], N[1], N[0]), np.float32)
+    B = np.zeros_like(E)
+    E[1] = (np.exp(-((x - 32.0) / 5.0) ** 2) * np.cos(2 * np.pi * (x - 32.0) / 8.0))[None, None, :]
+    xb = x + 0.5
+    B[2] = (np.exp(-((xb - 32.0) / 5.0) ** 2) * np.cos(2 * np.pi * (xb - 32.0) / 8.0) / p.c)[None, None, :]
+    s.upload_field(FE, E)
+    s.upload_field(FB, B)
+    e0 = s.field_energy().sum()
+    s.step(int(3 * 64 * p.cell_size[0] / (p.c * p.dt)))
+    left = s.field_energy().sum() / e0
+    print("PML: field energy left %.2e" % left)
+    assert left < 1e-6
+    s.close()
+
+
 def test_absorber_damps_outgoing_wave():
     """Physics check of the absorber: a pulse leaving through an absorbing face loses energy, the same pulse in a
     periodic box does not."""

@@ -471,3 +471,36 @@ def test_incident_plane_wave_known_answer(orc):
     Ex, Bz = o.interior(E)[0], o.interior(B)[2]
     assert abs(np.abs(Bz).max() * p.c / np.abs(Ex).max() - 1.0) < 0.05
     assert (-(Ex * Bz)).sum() > 0.0
+
+
+def test_pml_known_answer(orc):
+    """Oracle restatement of the PML (fields/absorber/pml/Pml.kernel): a vacuum pulse that leaves through 12 cells of PML
+    with the reference's default parameters (param/fieldAbsorber.param:98-158) is absorbed to round-off, the same pulse
+    through the exponential absorber of the same thickness is not; and the graded coefficients at the interface are those
+    of the plain Yee update (b = 1, c = 0), so nothing changes outside the layer."""
+    from picongpu_b200 import param as prm
+
+    left = {}
+    for kind in (1, 2):
+        p = prm.khi_params(grid=(64, 8, 4), periodic=(0, 1, 1), absorber_kind=kind, absorber_cells=((12, 12), (0, 0), (0, 0)),
+                           absorber_strength=((1e-3, 1e-3), (0, 0), (0, 0)))
+        p.pml = prm.pml_params(p)
+        o = orc.Oracle(p)
+        N, g = p.padded, p.guard_cells
+        x = np.arange(N[0]) - g[0]
+        E, B, J = o.field(), o.field(), o.field()
+        E[1] = (np.exp(-((x - 32.0) / 5.0) ** 2) * np.cos(2 * np.pi * (x - 32.0) / 8.0))[None, None, :]
+        B[2] = (np.exp(-((x + 0.5 - 32.0) / 5.0) ** 2) * np.cos(2 * np.pi * (x + 0.5 - 32.0) / 8.0) / p.c)[None, None, :]
+        e0 = o.field_energy(E, B).sum()
+        if kind == 2:  # one step: cells outside the layer are updated exactly like without an absorber
+            p0 = prm.khi_params(grid=(64, 8, 4), periodic=(0, 1, 1))
+            o0 = orc.Oracle(p0)
+            E1, B1, E2, B2 = E.copy(), B.copy(), E.copy(), B.copy()
+            o.step_open(E1, B1, o.field(), [])
+            o0.step_open(E2, B2, o0.field(), [])
+            sl = (slice(None), slice(g[2], g[2] + 4), slice(g[1], g[1] + 8), slice(g[0] + 13, g[0] + 64 - 13))
+            assert np.array_equal(E1[sl], E2[sl]) and np.array_equal(B1[sl], B2[sl])
+        for _ in range(int(3 * 64 * p.cell_size[0] / (p.c * p.dt))):
+            o.step_open(E, B, J, [])
+        left[kind] = o.field_energy(E, B).sum() / e0
+    assert left[2] < 1e-9 and left[1] > 1e-3

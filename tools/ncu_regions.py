@@ -15,9 +15,14 @@ def find(sub, start=0):
             return i + 1
     return 10**9
 cl = find('for(uint32_t chunk = pBeg')
-marks = [('setup', 1), ('flushCell', find('auto flushCell')), ('chunkloop', cl), ('fused push', find('if constexpr(FUSED)', cl)), ('deposit prep', find('if(deposit)')),
-         ('record build', find('if(narrow)')), ('slow path', find('// wide trajectory')), ('phase2 ctrl', find('uint32_t const validMask')),
-         ('inner loop', find('for(int q = r; q < e; q += 2)')), ('after loop', find('r = e;')), ('final', find('// ---- combine the warp-private'))]
+# regions are source-line ranges of pushdeposit.cu (lambdas are attributed to the lines they are written on)
+marks = [('setup / prologue', 1), ('flushCell (per-cell flush)', find('auto flushCell')), ('record store', find('auto storeRecord')),
+         ('EmZ record', find('auto emzRecord')), ('prefetch', find('auto prefetchIdx')), ('chunk loop head', cl),
+         ('fused push: move + key', find('if constexpr(FUSED)', cl)), ('deposit prep (shapes, offsets)', find('if(deposit)', cl)),
+         ('record build (window placement)', find('if(narrow)', cl)), ('slow path (global atomics)', find('// wide trajectory: reference loop', cl)),
+         ('unused record', find('if(!useRec)', cl)), ('phase 2: masks + stayer ranks', find('uint32_t const validMask')),
+         ('phase 2: passes', find('auto runPasses')), ('phase 2: EmZ second round', find('if constexpr(SOLVER == 1)', find('auto runPasses'))),
+         ('rank store + loop end', find('if(FUSED && valid)')), ('epilogue (tile sum + RED)', find('// ---- combine the warp-private'))]
 agg = {}
 for i in range(min(len(s), len(d))):
     ln = d[i][1]
