@@ -139,7 +139,16 @@ namespace picstep
         int const xa = X0 + 4 * tx; // allocation x of the thread's first cell
         int const xlo = P.g[0] + lead, xhi = xlo + P.n[0];
         bool const yok = Y0 + ty < P.g[1] + P.n[1];
+        // two-point difference divided by the cell size: the exact build divides like the reference
+        // (Forward/BackwardDerivative.hpp:58-63); the production build multiplies with the reciprocal -- 24 IEEE divisions
+        // per four cells were a third of the kernel's instructions
+#ifdef PICSTEP_EXACT
         float const hx = P.cell[0], hy = P.cell[1], hz = P.cell[2];
+#    define FD_DIFF(a, b, h) (((a) - (b)) / (h))
+#else
+        float const hx = 1.0f / P.cell[0], hy = 1.0f / P.cell[1], hz = 1.0f / P.cell[2];
+#    define FD_DIFF(a, b, h) (((a) - (b)) * (h))
+#endif
         float const c2 = P.c * P.c;
         [[maybe_unused]] float const coeff = -(1.0f / P.eps0) * P.dt;
         bool const full = xa >= xlo && xa + 3 < xhi; // all four cells active: 16-byte accesses
@@ -202,21 +211,21 @@ namespace picstep
                 float dzdy, dydz, dxdz, dzdx, dydx, dxdy;
                 if constexpr(KIND == 0)
                 {
-                    dzdy = (fy[2][q] - f[2][q + 1]) / hy;
-                    dydz = (fz[1][q] - f[1][q + 1]) / hz;
-                    dxdz = (fz[0][q] - f[0][q + 1]) / hz;
-                    dzdx = (f[2][q + 2] - f[2][q + 1]) / hx;
-                    dydx = (f[1][q + 2] - f[1][q + 1]) / hx;
-                    dxdy = (fy[0][q] - f[0][q + 1]) / hy;
+                    dzdy = FD_DIFF(fy[2][q], f[2][q + 1], hy);
+                    dydz = FD_DIFF(fz[1][q], f[1][q + 1], hz);
+                    dxdz = FD_DIFF(fz[0][q], f[0][q + 1], hz);
+                    dzdx = FD_DIFF(f[2][q + 2], f[2][q + 1], hx);
+                    dydx = FD_DIFF(f[1][q + 2], f[1][q + 1], hx);
+                    dxdy = FD_DIFF(fy[0][q], f[0][q + 1], hy);
                 }
                 else
                 {
-                    dzdy = (f[2][q + 1] - fy[2][q]) / hy;
-                    dydz = (f[1][q + 1] - fz[1][q]) / hz;
-                    dxdz = (f[0][q + 1] - fz[0][q]) / hz;
-                    dzdx = (f[2][q + 1] - f[2][q]) / hx;
-                    dydx = (f[1][q + 1] - f[1][q]) / hx;
-                    dxdy = (f[0][q + 1] - fy[0][q]) / hy;
+                    dzdy = FD_DIFF(f[2][q + 1], fy[2][q], hy);
+                    dydz = FD_DIFF(f[1][q + 1], fz[1][q], hz);
+                    dxdz = FD_DIFF(f[0][q + 1], fz[0][q], hz);
+                    dzdx = FD_DIFF(f[2][q + 1], f[2][q], hx);
+                    dydx = FD_DIFF(f[1][q + 1], f[1][q], hx);
+                    dxdy = FD_DIFF(f[0][q + 1], fy[0][q], hy);
                 }
                 float const cu[3] = {dzdy - dydz, dxdz - dzdx, dydx - dxdy};
 #pragma unroll

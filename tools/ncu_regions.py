@@ -17,7 +17,7 @@ def find(sub, start=0):
 cl = find('for(uint32_t chunk = pBeg')
 # regions are source-line ranges of pushdeposit.cu (lambdas are attributed to the lines they are written on)
 marks = [('setup / prologue', 1), ('flushCell (per-cell flush)', find('auto flushCell')), ('record store', find('auto storeRecord')),
-         ('EmZ record', find('auto emzRecord')), ('prefetch', find('auto prefetchIdx')), ('chunk loop head', cl),
+         ('EmZ record + prefetch registers', find('auto emzRecord')), ('prefetch', find('auto prefetchIdx')), ('chunk loop head', cl),
          ('fused push: move + key', find('if constexpr(FUSED)', cl)), ('deposit prep (shapes, offsets)', find('if(deposit)', cl)),
          ('record build (window placement)', find('if(narrow)', cl)), ('slow path (global atomics)', find('// wide trajectory: reference loop', cl)),
          ('unused record', find('if(!useRec)', cl)), ('phase 2: masks + stayer ranks', find('uint32_t const validMask')),
