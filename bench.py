@@ -393,6 +393,7 @@ def run_ours(args):
     ms_total = ev0.elapsed_time(ev1)
     sampler.stop_flag = True
     sampler.join()
+    ov = sim.overlap_times() if world > 1 else None
     stage = sim.stage_times(False)
     launches = sim.launch_count() - l0
     if world > 1:
@@ -546,6 +547,8 @@ def run_ours(args):
             "e2e": e2e,
             "gpu_launches": int(launches),
             "slow_path": slow_path,
+            "overlap": None if ov is None else {"exchange_ms_after_border": ov[0], "core_ms_after_border": ov[1], "steps": ov[2], "exchange_hidden": bool(ov[0] < ov[1]),
+                                                "note": "rank 0, device time per step from 'BORDER area pushed' until the migration + J guard exchange is complete (second stream) / until the last CORE kernel is complete (compute stream)"},
             "clocks": sampler.summary(),
             "checks": checks,
         }

@@ -265,6 +265,11 @@ extern "C"
     /* accumulated device time per stage in ms since the last call with reset!=0; names via picstep_stage_name.
      * stages: 0 current_reset 1 push 2 migrate 3 field_before 4 deposit 5 add_current 6 field_after */
     int picstep_stage_times(picstep_ctx* ctx, int32_t enable, float* ms7);
+    /* Overlap evidence of the decomposed step (CORE / BORDER areas): out3[0] = mean device time per step from "BORDER area
+     * pushed" until the exchange of leaving particles and J guard strips is complete (second stream), out3[1] = the same
+     * until the last CORE kernel is complete (compute stream), out3[2] = number of steps measured since the last call.
+     * Recorded while picstep_stage_times is enabled.  The exchange is hidden when out3[0] < out3[1]. */
+    int picstep_overlap_times(picstep_ctx* ctx, float* out3);
     /* the CUDA stream (cudaStream_t) all work of the context is queued on */
     int picstep_stream(picstep_ctx* ctx, void** stream);
 

@@ -117,6 +117,16 @@ struct picstep_ctx
     int widthShape = 0; // the widest shape of any species: guard exchange margins follow it
     uint32_t* migPinned = nullptr; // pinned readback of the migration counts of all species (overlapped step)
     cudaEvent_t evBorder = nullptr, evComm = nullptr;
+    std::vector<cudaEvent_t> evCore; // per species: its CORE launch is through (the re-sort may start on the second stream)
+    // overlap evidence (picstep_overlap_times): per step, device time from "BORDER done" to "exchange done" (second stream)
+    // and to "last CORE kernel done" (compute stream); timing events, resolved lazily
+    struct OverlapSpan
+    {
+        cudaEvent_t border, comm, core;
+    };
+    std::vector<OverlapSpan> overlapSpans;
+    double overlapMs[2] = {0.0, 0.0};
+    int overlapSteps = 0;
     AbsorberDev absorber{}; // exponential absorber: thickness per face (0 = not absorbing) + attenuation table
     float* dampDev = nullptr;
     bool absorbing = false;
@@ -984,6 +994,14 @@ extern "C"
             cudaEventDestroy(c->evFlags);
         for(auto e : c->evMig)
             cudaEventDestroy(e);
+        for(auto e : c->evCore)
+            cudaEventDestroy(e);
+        for(auto& o : c->overlapSpans)
+        {
+            cudaEventDestroy(o.border);
+            cudaEventDestroy(o.comm);
+            cudaEventDestroy(o.core);
+        }
         delete c;
         return PICSTEP_OK;
     }
@@ -1744,6 +1762,8 @@ extern "C"
             cudaEvent_t e;
             CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             c->evMig.push_back(e);
+            CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->evCore.push_back(e);
         }
         std::vector<char> pendingMig(size_t(ns), 0);
         int rc = PICSTEP_OK;
@@ -1756,6 +1776,12 @@ extern "C"
             {
                 int const a = c->P.split_axis;
                 ScArea const border{a, 0, c->P.nsc[a] - 1, 2}, core{a, 1, 1, c->P.nsc[a] - 2};
+                for(int s = 0; s < ns; ++s) // the re-sort of the previous step produced this species' run table
+                    if(pendingMig[s])
+                    {
+                        CU(c, cudaStreamWaitEvent(c->stream, c->evMig[s], 0));
+                        pendingMig[s] = false;
+                    }
                 for(int s = 0; s < ns && !rc; ++s)
                 {
                     if(it == 0)
@@ -1767,30 +1793,62 @@ extern "C"
                     break;
                 CU(c, cudaEventRecord(c->evBorder, c->stream));
                 CU(c, cudaStreamWaitEvent(c->side, c->evBorder, 0));
+                picstep_ctx::OverlapSpan span{};
+                if(c->timing)
+                {
+                    span.border = takeEvent(c);
+                    span.comm = takeEvent(c);
+                    span.core = takeEvent(c);
+                    cudaEventRecord(span.border, c->stream);
+                }
                 for(int s = 0; s < ns && !rc; ++s)
+                {
                     rc = pushDepositFused(c, s, core);
+                    CU(c, cudaEventRecord(c->evCore[s], c->stream));
+                }
                 if(rc)
                     break;
+                if(c->timing)
+                    cudaEventRecord(span.core, c->stream);
                 AxisExchange const xj = axisExchange(c, PICSTEP_FIELD_J, a, -1, -1);
                 rc = exchangeBorderOverlapped(c, c->side, recLo, recHi, xj);
                 if(rc)
                     break;
                 CU(c, cudaEventRecord(c->evComm, c->side));
+                if(c->timing)
+                {
+                    cudaEventRecord(span.comm, c->side);
+                    c->overlapSpans.push_back(span);
+                }
                 CU(c, cudaStreamWaitEvent(c->stream, c->evComm, 0));
                 {
-                    StageTimer t(c, 2);
+                    // The re-sort of a species runs on the second stream as soon as its CORE launch is through: next to the
+                    // CORE kernel of the following species (bound by shared memory, the re-sort by HBM) and to the field
+                    // update.  The next step's kernels of this species wait for evMig.
+                    cudaStream_t const mainStream = c->stream;
                     for(int s = 0; s < ns && !rc; ++s)
                     {
                         SpeciesHost& sp = c->species[s];
                         if(sp.capacity == 0)
                             continue;
-                        if(int64_t(sp.nUpper) + recLo[s] + recHi[s] > sp.capacity)
+                        CU(c, cudaStreamWaitEvent(c->side, c->evCore[s], 0));
+                        c->stream = c->side;
                         {
-                            int64_t const want = int64_t(sp.nUpper) + recLo[s] + recHi[s];
-                            rc = growSpeciesBuffers(c, sp, want + want / 4 + 4096);
+                            StageTimer t(c, 2);
+                            if(int64_t(sp.nUpper) + recLo[s] + recHi[s] > sp.capacity)
+                            {
+                                int64_t const want = int64_t(sp.nUpper) + recLo[s] + recHi[s];
+                                rc = growSpeciesBuffers(c, sp, want + want / 4 + 4096);
+                            }
+                            if(!rc)
+                                rc = resortSpecies(c, sp, recLo[s], recHi[s]);
                         }
+                        c->stream = mainStream;
                         if(!rc)
-                            rc = resortSpecies(c, sp, recLo[s], recHi[s]);
+                        {
+                            CU(c, cudaEventRecord(c->evMig[s], c->side));
+                            pendingMig[s] = true;
+                        }
                     }
                 }
                 if(!rc)
@@ -1943,6 +2001,38 @@ extern "C"
                 return rc;
         }
         return checkFlags(c);
+    }
+
+    /* Overlap evidence of the decomposed step: out[0] = mean device time per step from "BORDER area pushed" to "exchange
+     * of leaving particles and J guard strips complete" (second stream), out[1] = the same to "last CORE kernel complete"
+     * (compute stream), out[2] = steps measured.  Recorded while picstep_stage_times is enabled; the call synchronises. */
+    int picstep_overlap_times(picstep_ctx* c, float* out3)
+    {
+        if(!c || !out3)
+            return PICSTEP_ERR_INVALID;
+        CU(c, cudaSetDevice(c->device));
+        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, cudaStreamSynchronize(c->side));
+        for(auto& o : c->overlapSpans)
+        {
+            float a = 0.0f, b = 0.0f;
+            if(cudaEventElapsedTime(&a, o.border, o.comm) == cudaSuccess && cudaEventElapsedTime(&b, o.border, o.core) == cudaSuccess)
+            {
+                c->overlapMs[0] += a;
+                c->overlapMs[1] += b;
+                c->overlapSteps += 1;
+            }
+            c->evPool.push_back(o.border);
+            c->evPool.push_back(o.comm);
+            c->evPool.push_back(o.core);
+        }
+        c->overlapSpans.clear();
+        out3[0] = c->overlapSteps ? float(c->overlapMs[0] / c->overlapSteps) : 0.0f;
+        out3[1] = c->overlapSteps ? float(c->overlapMs[1] / c->overlapSteps) : 0.0f;
+        out3[2] = float(c->overlapSteps);
+        c->overlapMs[0] = c->overlapMs[1] = 0.0;
+        c->overlapSteps = 0;
+        return PICSTEP_OK;
     }
 
     int picstep_sync(picstep_ctx* c)
@@ -2099,6 +2189,7 @@ extern "C"
         {
             CU(c, cudaSetDevice(c->device));
             CU(c, cudaStreamSynchronize(c->stream));
+            CU(c, cudaStreamSynchronize(c->side)); // the re-sort spans are recorded on the second stream
             for(auto& sp : c->spans)
             {
                 float ms = 0;

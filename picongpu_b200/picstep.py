@@ -27,7 +27,7 @@ SYMBOLS = [
     "picstep_field_update_before_current", "picstep_deposit", "picstep_add_current",
     "picstep_field_update_after_current", "picstep_field_exchange", "picstep_step", "picstep_step_host",
     "picstep_sync", "picstep_reduce", "picstep_debug_gather", "picstep_comm_unique_id", "picstep_comm_init",
-    "picstep_launch_count", "picstep_stage_times", "picstep_stream", "picstep_neighbor_ranks",
+    "picstep_launch_count", "picstep_stage_times", "picstep_overlap_times", "picstep_stream", "picstep_neighbor_ranks",
     "picstep_exchange_widths", "picstep_slide", "picstep_moving_window_info", "picstep_window_neighbors",
 ]
 
@@ -138,6 +138,7 @@ def load(exact=False):
     L.picstep_comm_init.argtypes = [vp, vp, i32, i32]
     L.picstep_launch_count.argtypes = [vp, C.POINTER(i64)]
     L.picstep_stage_times.argtypes = [vp, i32, fp]
+    L.picstep_overlap_times.argtypes = [vp, fp]
     L.picstep_stream.argtypes = [vp, C.POINTER(vp)]
     L.picstep_neighbor_ranks.argtypes = [C.POINTER(i32 * 3), C.POINTER(i32 * 3), i32, i32, C.POINTER(i32), C.POINTER(i32)]
     L.picstep_exchange_widths.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32 * 2)]
@@ -455,6 +456,12 @@ class Simulation:
         ms = (C.c_float * 7)()
         self._chk(self.L.picstep_stage_times(self.ctx, 1 if enable else 0, ms), "stage_times")
         return dict(zip(STAGES, list(ms)))
+
+    def overlap_times(self):
+        """(exchange ms, CORE ms, steps): device time per step from 'BORDER pushed' to 'exchange complete' / 'CORE complete'"""
+        out = (C.c_float * 3)()
+        self._chk(self.L.picstep_overlap_times(self.ctx, out), "overlap_times")
+        return float(out[0]), float(out[1]), int(out[2])
 
     def stream(self):
         s = C.c_void_p()
