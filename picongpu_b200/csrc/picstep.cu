@@ -134,6 +134,10 @@ struct picstep_ctx
     // picstep_step runs the re-sort / migration of a species on a second stream, next to the fused kernel of the next
     // species and the field update (they are bound by different units: HBM vs. shared memory / issue)
     cudaStream_t side = nullptr;
+    // exchange of the decomposed step: highest priority, so that its small kernels (pack, NCCL) are scheduled as soon as a
+    // CTA slot frees up although the CORE kernel's grid is still being dispatched (measured without: the exchange only
+    // completed together with the CORE kernels)
+    cudaStream_t commStream = nullptr;
     cudaEvent_t evFused = nullptr;
     cudaEvent_t evFlags = nullptr; // completion of the asynchronous error-flag readback (peekFlags)
     bool flagsPending = false;
@@ -853,6 +857,11 @@ extern "C"
         CUC(cudaSetDevice(c->device));
         CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CUC(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        {
+            int prLow = 0, prHigh = 0;
+            CUC(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+            CUC(cudaStreamCreateWithPriority(&c->commStream, cudaStreamNonBlocking, prHigh));
+        }
         CUC(cudaEventCreateWithFlags(&c->evFused, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->evFlags, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->evBorder, cudaEventDisableTiming));
@@ -988,6 +997,8 @@ extern "C"
             cudaStreamDestroy(c->stream);
         if(c->side)
             cudaStreamDestroy(c->side);
+        if(c->commStream)
+            cudaStreamDestroy(c->commStream);
         if(c->evFused)
             cudaEventDestroy(c->evFused);
         if(c->evFlags)
@@ -1792,7 +1803,7 @@ extern "C"
                 if(rc)
                     break;
                 CU(c, cudaEventRecord(c->evBorder, c->stream));
-                CU(c, cudaStreamWaitEvent(c->side, c->evBorder, 0));
+                CU(c, cudaStreamWaitEvent(c->commStream, c->evBorder, 0));
                 picstep_ctx::OverlapSpan span{};
                 if(c->timing)
                 {
@@ -1811,16 +1822,17 @@ extern "C"
                 if(c->timing)
                     cudaEventRecord(span.core, c->stream);
                 AxisExchange const xj = axisExchange(c, PICSTEP_FIELD_J, a, -1, -1);
-                rc = exchangeBorderOverlapped(c, c->side, recLo, recHi, xj);
+                rc = exchangeBorderOverlapped(c, c->commStream, recLo, recHi, xj);
                 if(rc)
                     break;
-                CU(c, cudaEventRecord(c->evComm, c->side));
+                CU(c, cudaEventRecord(c->evComm, c->commStream));
                 if(c->timing)
                 {
-                    cudaEventRecord(span.comm, c->side);
+                    cudaEventRecord(span.comm, c->commStream);
                     c->overlapSpans.push_back(span);
                 }
                 CU(c, cudaStreamWaitEvent(c->stream, c->evComm, 0));
+                CU(c, cudaStreamWaitEvent(c->side, c->evComm, 0)); // the re-sort appends the received records
                 {
                     // The re-sort of a species runs on the second stream as soon as its CORE launch is through: next to the
                     // CORE kernel of the following species (bound by shared memory, the re-sort by HBM) and to the field
@@ -2013,6 +2025,7 @@ extern "C"
         CU(c, cudaSetDevice(c->device));
         CU(c, cudaStreamSynchronize(c->stream));
         CU(c, cudaStreamSynchronize(c->side));
+        CU(c, cudaStreamSynchronize(c->commStream));
         for(auto& o : c->overlapSpans)
         {
             float a = 0.0f, b = 0.0f;
