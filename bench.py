@@ -228,7 +228,7 @@ def run_reference(args):
 # -------------------------------------------------------------------------------------------------------------------
 def multi_gpu_parity_check(world, rank, local, dev):
     """N-rank CUDA step against the single-domain oracle, before the timed region (the oracle as CHECKER only):
-    KHI 16 x 16*N x 8 global, slabs in y, 6 steps, particles kicked in y/z so they cross the rank boundaries
+    KHI 16 x 32*N x 8 global, slabs in y, 6 steps, particles kicked in y/z so they cross the rank boundaries
     (pack / NCCL send-recv / append kernels, E/B/J guard exchange).  Returns the dict stored in checks."""
     import torch
     import torch.distributed as dist
@@ -240,7 +240,7 @@ def multi_gpu_parity_check(world, rank, local, dev):
     from oracle import picoracle
     from test_multirank_cpu import _kick
 
-    steps, local_grid = 6, (16, 16, 8)
+    steps, local_grid = 6, (16, 32, 8)  # four supercell layers along y per rank: two BORDER layers and a CORE area
     picoracle.lib().orc_set_num_threads(2 if world > 1 else host_cores())
     p = prm.khi_params(grid=local_grid, devices=(1, world, 1), rank_pos=(0, rank, 0))
     o, e, i = util.khi_ic(picoracle, p)

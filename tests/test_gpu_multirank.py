@@ -22,7 +22,7 @@ import util  # noqa: E402
 from test_multirank_cpu import _kick  # noqa: E402
 
 pytestmark = pytest.mark.gpu
-LOCAL = (16, 16, 8)
+LOCAL = (16, 32, 8)  # four supercell layers along the split axis: BORDER (2) and CORE (2) areas both exist
 
 
 OPEN = dict(periodic=(1, 0, 1), current_interpolation=1, absorber_kind=1, absorber_cells=((0, 0), (6, 6), (0, 0)),
