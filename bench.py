@@ -95,15 +95,18 @@ VARIANT = {"shape": "TSC", "pusher": "Boris", "current": "Esirkepov", "solver": 
 #   lwfa_like C3  LaserWakefield's kernels and boundaries (CIC, open + absorbing y, cell sizes with c dt / dy = 0.94) on the KHI
 #                 plasma -- WITHOUT the laser (incident-field source not built): it measures the step, not wakefield physics
 #   foil_like C4  PQS + Lehe + Binomial current smoothing (the "high-order deposition stress test") on the KHI plasma
+LWFA_MOVE_POINT = 0.14
 CONFIGS = {
     "khi": {},
     "thermal": dict(shape="TSC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
     "lwfa_like": dict(shape="CIC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
     "foil_like": dict(shape="PQS", pusher="Boris", current="Esirkepov", solver="Lehe", interp="binomial"),
-    # C3 with its laser and its moving window: examples/LaserWakefield's grid, boundaries, CIC / Boris / Esirkepov / Yee,
-    # a0 = 8, 0.8 um, 5 fs pulse entering through the YMin Huygens surface (profiles::PlaneWave stands in for the example's
-    # GaussianPulse: the transversal envelope is not built), cold electron + ion plasma, the window slides (here from the
-    # start: --windowMovePoint 0) and the slab that enters is re-initialised; N >= 2 GPUs
+    # C3 with its laser and its moving window: examples/LaserWakefield's grid (2048 cells along y at N = 8), boundaries
+    # (nothing periodic, the default PML of 12 cells on every outer face), CIC / Boris / Esirkepov / Yee and the example's
+    # GaussianPulse (a0 = 8, 0.8 um, 5 fs, W0 = 4.25 um, circular, focus 46.2 um inside, PULSE_INIT 15) through the YMin
+    # Huygens surface; cold electron + ion plasma; the window starts to slide once the pulse is in completely
+    # (--windowMovePoint 0.14 instead of the example's 0.9, so that 900 steps hold two slides: tools/campaign.sh) and the
+    # slab that enters is re-initialised; N >= 2 GPUs
     "lwfa": dict(shape="CIC", pusher="Boris", current="Esirkepov", solver="Yee", interp="none"),
     # the slow-path cliff: relativistic electrons (the Thermal plasma) on LaserWakefield's cells, c dt / dy = 0.94 -- most
     # trajectories are too wide for the four-node window of the fused kernel and are deposited with global atomics
@@ -123,10 +126,10 @@ def workload_name(grid, ppc, n):
             "Thermal3D" if v["config"] == "thermal" else "ThermalOnLaserWakefieldCells3D_cdt_over_dy_0.94",
             grid[0], grid[1], grid[2], ppc, v["shape"], v["pusher"], v["current"], v["solver"], extra, n)
     head = {"khi": "KelvinHelmholtz3D", "lwfa_like": "LaserWakefieldLike3D_noLaser_KHIplasma_open_y", "foil_like": "FoilLCTLike3D_KHIplasma",
-            "lwfa": "LaserWakefield3D_a0_8_PlaneWaveLaser_movingWindow_coldPlasma"}[v["config"]]
+            "lwfa": "LaserWakefield3D_a0_8_GaussianPulse_PML_movingWindow_coldPlasma"}[v["config"]]
     return "%s_%dx%dx%d_per_gpu_%d+%dppc_%s_%s_%s_%s%s_%s_d1x%dx1" % (
         head, grid[0], grid[1], grid[2], ppc, ppc, v["shape"], v["pusher"], v["current"], v["solver"], extra,
-        "periodic" if v["config"] not in ("lwfa_like", "lwfa") else "absorbing_y", n)
+        {"lwfa_like": "absorbing_y", "lwfa": "absorbing_xyz"}.get(v["config"], "periodic"), n)
 
 
 def variant_kwargs():
@@ -138,7 +141,8 @@ def variant_kwargs():
         # 0.4430e-7 m x 0.1772 um (c dt / dy = 0.94); --periodic 1 0 1, exponential absorber on the open axis
         kw.update(periodic=(1, 0, 1), absorber_kind=1, delta_t_si=1.39e-16, cell_si=(0.1772e-6, 0.4430e-7, 0.1772e-6))
     if v["config"] == "lwfa":
-        kw.update(moving_window=1)
+        # etc/picongpu/8.cfg: no --periodic (all axes open), -m; fieldAbsorber default = pml, NUM_CELLS 12 everywhere
+        kw.update(moving_window=1, periodic=(0, 0, 0), absorber_kind=2)
     if v["config"] == "lwfa_hot":
         kw.update(delta_t_si=1.39e-16, cell_si=(0.1772e-6, 0.4430e-7, 0.1772e-6), base_density_si=1.0e25)
     return kw
@@ -149,10 +153,10 @@ def make_params(grid, **kw):
         return prm.thermal_params(grid=grid, **kw)
     p = prm.khi_params(grid=grid, **kw)
     if VARIANT["config"] == "lwfa":
-        # examples/LaserWakefield/include/picongpu/param/incidentField.param: a0 = 8, 0.8 um, 5 fs, circular, RAMP_INIT of
-        # the PlaneWave default (PlaneWave.def:44); surface 16 cells inside (POSITION[1][0], incidentField.param)
-        p.laser = prm.plane_wave_laser(p, a0=8.0, wavelength_si=0.8e-6, pulse_duration_si=5.0e-15, ramp_init=20.6146,
-                                       polarisation="circular", offset_ymin=16)
+        # examples/LaserWakefield/include/picongpu/param/incidentField.param (the defaults of gaussian_pulse_laser) and
+        # param/fieldAbsorber.param (the defaults of pml_params)
+        p.laser = prm.gaussian_pulse_laser(p)
+        p.pml = prm.pml_params(p)
     return p
 
 
@@ -380,7 +384,7 @@ def run_ours(args):
         # local-domain border; the rank that becomes the top of the window starts empty and gets fresh plasma
         for k in range(args.steps):
             step = sim.step_index
-            do_slide, _ = picstep.moving_window_info(p.global_grid[1], p.grid[1], p.cell_size[1], p.c * p.dt, 0.0, step)
+            do_slide, _ = picstep.moving_window_info(p.global_grid[1], p.grid[1], p.cell_size[1], p.c * p.dt, LWFA_MOVE_POINT, step)
             sim.step(1)
             if do_slide:
                 slides += 1

@@ -66,6 +66,12 @@ extern "C"
         PICSTEP_CURRENT_INTERPOLATION_NONE = 0,
         PICSTEP_CURRENT_INTERPOLATION_BINOMIAL = 1
     };
+    /* incidentField.param profile on YMin (include/picongpu/fields/incidentField/profiles/profiles.def) */
+    enum picstep_laser_profile
+    {
+        PICSTEP_LASER_PLANE_WAVE = 0, /* profiles::PlaneWave (profiles/PlaneWave.hpp) */
+        PICSTEP_LASER_GAUSSIAN_PULSE = 1 /* profiles::GaussianPulse / PulseFrontTilt (profiles/GaussianPulse.hpp) */
+    };
     /* fields::absorber::Absorber::Kind (include/picongpu/fields/absorber/Absorber.hpp) */
     enum picstep_absorber
     {
@@ -134,8 +140,8 @@ extern "C"
          * the +y absorber is switched off (Exponential.hpp:97-101) and picstep_slide() may be called */
         int32_t moving_window;
         /* incidentField.param (fields/incidentField/Solver.hpp:547-575, called from FDTDBase.hpp:108-117,161-166): a
-         * `profiles::PlaneWave<>` (profiles/PlaneWave.hpp) entering through the YMin Huygens surface, Yee solver,
-         * x and z periodic (the surface spans them).  All values are the profile's unitless parameters
+         * `profiles::PlaneWave<>` (profiles/PlaneWave.hpp) or GaussianPulse (see laser_profile below) entering through the
+         * YMin Huygens surface, Yee solver.  All values are the profile's unitless parameters
          * (PlaneWaveUnitless / BaseParamUnitless, PIC units).  The source is switched off once the moving window has
          * slid (Solver.hpp: "After the sliding window started moving, does nothing for the y boundaries"). */
         int32_t laser_enabled; /* 0: profiles::None on all boundaries */
@@ -157,6 +163,23 @@ extern "C"
         float pml_alpha_max[3]; /* NORMALIZED_ALPHA_MAX */
         float pml_sigma_kappa_grading_order; /* SIGMA_KAPPA_GRADING_ORDER */
         float pml_alpha_grading_order; /* ALPHA_GRADING_ORDER */
+        /* incidentField.param, continued: profile kind and the values of a `profiles::GaussianPulse<Params,
+         * GaussianPulseEnvelope<Params>>` (profiles/GaussianPulse.hpp:93-346; with a non-zero tilt it is
+         * `profiles::PulseFrontTilt`) entering through YMin.  The Huygens surface of this profile ends at POSITION on the
+         * transversal axes (Solver.hpp:209-258), which may be periodic or not; the PlaneWave profile spans a periodic
+         * transversal axis completely and ends at POSITION on a non-periodic one. */
+        int32_t laser_profile; /* picstep_laser_profile */
+        int32_t laser_position[3][2]; /* POSITION[axis][min, max]; max <= 0 counts from the upper boundary;
+                                         [1][0] == laser_offset_ymin.  All zero: {offset, -offset} on every axis */
+        float laser_w0; /* W0 */
+        float laser_wave_length; /* WAVE_LENGTH */
+        float laser_time_shift; /* GaussianPulseEnvelope::TIME_SHIFT = -0.5 * PULSE_INIT * PULSE_DURATION */
+        float laser_focus_position[3]; /* FOCUS_POSITION_{X,Y,Z} */
+        int32_t laser_focus_origin_center[3]; /* FOCUS_ORIGIN_* == Origin::Center (Functors.hpp:267-291) */
+        float laser_tilt[2]; /* TILT_AXIS_1, TILT_AXIS_2 in radian */
+        int32_t laser_n_modes; /* laguerreModes.size(), 1..8 (0 = one mode of weight 1) */
+        float laser_modes[8]; /* laguerreModes */
+        float laser_mode_phases[8]; /* laguerrePhases */
     } picstep_params;
 
     /* library / build information: returns e.g. "picstep sm_100a fmad=on" */

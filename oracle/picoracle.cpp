@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <random>
 #include <vector>
 #ifdef _OPENMP
@@ -1680,20 +1681,34 @@ extern "C"
 
     // ---------------------------------------------------------------------------------------------
     // Incident field (laser) through the YMin Huygens surface: P/fields/incidentField/Solver.hpp:190-395 (updateField),
-    // Solver.kernel:101-404 (UpdateFunctor for the Yee solver: margin 1, one derivative coefficient = 1),
-    // Functors.hpp (BaseFunctorE::getCurrentTime, BaseSeparableFunctorE::operator(), ApproximateIncidentB),
-    // profiles/PlaneWave.hpp:93-130 (getLongitudinal), calculatePhaseVelocity.hpp + DispersionRelationSolver (Yee,
-    // propagation along y).  Transversal axes are periodic, so the surface spans them completely
-    // (MakePeriodicTransversalHuygensSurfaceContiguous<PlaneWave> = true, PlaneWave.def:71).
+    // Solver.kernel:101-404 (UpdateFunctor for the Yee solver: margin 1, one derivative coefficient = 1; kernel
+    // :418-476 with the "last updated cell" rule), Functors.hpp (BaseFunctorE: getFocus / getOrigin / getCurrentTime /
+    // getInternalCoordinates, BaseSeparableFunctorE::operator(), ApproximateIncidentB), profiles/PlaneWave.hpp:93-130
+    // (getLongitudinal), profiles/GaussianPulse.hpp:186-346 (getValue with Laguerre modes, pulse-front tilt and the
+    // GaussianPulseEnvelope), calculatePhaseVelocity.hpp + DispersionRelationSolver (Yee, propagation along y).
+    // The surface spans a periodic transversal axis completely for the PlaneWave profile only
+    // (MakePeriodicTransversalHuygensSurfaceContiguous, PlaneWave.def:71); otherwise it ends at POSITION.
     // ---------------------------------------------------------------------------------------------
+    constexpr int ORC_LASER_MAX_MODES = 8;
+
     struct OrcLaser
     {
         int polarisation; // PolarisationType: 0 Linear, 1 Circular
         int offset_ymin; // POSITION[1][0]
-        float amplitude, omega, pulse_duration, nofocus_constant, ramp_init, phase; // PlaneWaveUnitless
+        float amplitude, omega, pulse_duration, nofocus_constant, ramp_init, phase; // *Unitless
         float pol[3]; // POLARISATION_DIRECTION (unit, orthogonal to y)
         float time_delay; // TIME_DELAY
         int global_y_offset; // totalCellOffset[1] of this domain
+        int profile; // 0 PlaneWave, 1 GaussianPulse<Params, GaussianPulseEnvelope> (with tilt: PulseFrontTilt)
+        int position[3][2]; // POSITION[axis][min, max] (max <= 0: counted from the upper boundary)
+        int global_size[3]; // global domain cells
+        int periodic[3];
+        float w0, wave_length, time_shift; // W0, WAVE_LENGTH, GaussianPulseEnvelope::TIME_SHIFT
+        float focus_position[3]; // FOCUS_POSITION_{X,Y,Z}
+        int focus_origin_center[3]; // FOCUS_ORIGIN_* == Origin::Center
+        float tilt[2]; // TILT_AXIS_1, TILT_AXIS_2 in radian
+        int n_modes; // laguerreModes.size()
+        float modes[ORC_LASER_MAX_MODES], mode_phases[ORC_LASER_MAX_MODES];
     };
 
     static float orc_laser_phase_velocity(OrcParams const& P, OrcLaser const& L)
@@ -1702,6 +1717,53 @@ extern "C"
         double const w = double(L.omega), dt = double(P.dt), c = double(P.c), dy = double(P.cell[1]);
         double const k = 2.0 / dy * std::asin(dy * std::sin(0.5 * w * dt) / (c * dt));
         return float(w / k / c);
+    }
+
+    // BaseFunctorE::getFocus / getOrigin (Functors.hpp:267-348) for DIR = (0, 1, 0)
+    struct OrcLaserFrame
+    {
+        float focus[3], origin[3], axis1[3], axis2[3];
+        float phaseVelocity;
+    };
+
+    static OrcLaserFrame orc_laser_frame(OrcParams const& P, OrcLaser const& L)
+    {
+        OrcLaserFrame F;
+        float const direction[3] = {0.0f, 1.0f, 0.0f};
+        for(int d = 0; d < 3; ++d)
+        {
+            F.focus[d] = L.focus_position[d];
+            if(L.focus_origin_center[d])
+                F.focus[d] += float(unsigned(L.global_size[d]) / 2u) * P.cell[d];
+        }
+        float originP = -std::numeric_limits<float>::infinity();
+        for(int axis = 0; axis < 3; ++axis)
+            if(std::abs(direction[axis]) > std::numeric_limits<float>::epsilon())
+            {
+                float const minPosition = (float(L.position[axis][0]) + 0.75f) * P.cell[axis];
+                int const maxPositionIdx = (L.position[axis][1] > 0) ? L.position[axis][1] : L.global_size[axis] + L.position[axis][1];
+                float const maxPosition = (float(maxPositionIdx) - 0.75f) * P.cell[axis];
+                float const axisP = std::min((minPosition - F.focus[axis]) / direction[axis], (maxPosition - F.focus[axis]) / direction[axis]);
+                originP = std::max(originP, axisP);
+            }
+        for(int d = 0; d < 3; ++d)
+            F.origin[d] = F.focus[d] + originP * direction[d];
+        for(int d = 0; d < 3; ++d)
+            F.axis1[d] = L.pol[d];
+        // getAxis2(): cross(DIR, POL_DIR)
+        F.axis2[0] = direction[1] * L.pol[2] - direction[2] * L.pol[1];
+        F.axis2[1] = direction[2] * L.pol[0] - direction[0] * L.pol[2];
+        F.axis2[2] = direction[0] * L.pol[1] - direction[1] * L.pol[0];
+        F.phaseVelocity = orc_laser_phase_velocity(P, L);
+        return F;
+    }
+
+    static inline float orc_dot3(float const a[3], float const b[3])
+    {
+        float tmp = a[0] * b[0]; // pmacc Dot: Vector.tpp:87-94
+        tmp += a[1] * b[1];
+        tmp += a[2] * b[2];
+        return tmp;
     }
 
     // PlaneWaveFunctorIncidentE::getLongitudinal (profiles/PlaneWave.hpp:93-130)
@@ -1730,22 +1792,100 @@ extern "C"
         return (std::sin(phase) + std::cos(phase) * integrationCorrectionFactor) * envelope;
     }
 
-    // incident E at a (fractional) total cell index: BaseFunctorE::getCurrentTime + BaseSeparableFunctorE::operator()
-    static void orc_laser_incident_e(OrcParams const& P, OrcLaser const& L, float phaseVelocity, float currentStep, float const idx[3], float out[3])
+    // GaussianPulseFunctorIncidentE::simpleLaguerre (GaussianPulse.hpp:316-336)
+    static float orc_simple_laguerre(unsigned n, float x)
     {
-        float const originY = (float(L.offset_ymin) + 0.75f) * P.cell[1]; // getOrigin(): projection onto the YMin surface
-        float const distance = idx[1] * P.cell[1] - originY; // dot(shiftFromOrigin, (0,1,0))
-        float const timeDelay = distance / phaseVelocity + L.time_delay;
+        if(n == 0)
+            return 1.0f;
+        unsigned currentN = 1;
+        float laguerreNMinus1 = 1.0f;
+        float laguerreN = 1.0f - x;
+        float laguerreNPlus1 = 0.0f;
+        while(currentN < n)
+        {
+            laguerreNPlus1 = ((2.0f * float(currentN) + 1.0f - x) * laguerreN - float(currentN) * laguerreNMinus1) / float(currentN + 1u);
+            laguerreNMinus1 = laguerreN;
+            laguerreN = laguerreNPlus1;
+            currentN++;
+        }
+        return laguerreN;
+    }
+
+    // GaussianPulseFunctorIncidentE::getValue (GaussianPulse.hpp:208-308), `time` = getCurrentTime() >= 0, 3D
+    static float orc_gaussian_pulse_value(OrcParams const& P, OrcLaser const& L, OrcLaserFrame const& F, float posIn[3], float time, float phaseShift)
+    {
+        float const pi = 3.14159265358979323846f;
+        float const rayleighLength = pi * L.w0 * L.w0 / L.wave_length;
+        float pos[3] = {posIn[0], posIn[1], posIn[2]};
+        time += L.time_shift;
+        float const focusRelativeToOrigin[3] = {F.focus[0] - F.origin[0], F.focus[1] - F.origin[1], F.focus[2] - F.origin[2]};
+        float const axis0[3] = {0.0f, 1.0f, 0.0f};
+        float const distanceFocusRelativeToOrigin = orc_dot3(focusRelativeToOrigin, axis0);
+        float const focusPos = distanceFocusRelativeToOrigin - pos[0];
+        float const w = L.w0 * std::sqrt(1.0f + (focusPos / rayleighLength) * (focusPos / rayleighLength));
+        float const phase = L.omega * (time - focusPos / P.c) + L.phase + phaseShift;
+        if(L.tilt[0] != 0.0f || L.tilt[1] != 0.0f)
+        {
+            float const tiltTimeShift = phase / L.omega + focusPos / P.c;
+            float const tiltPositionShift = P.c * tiltTimeShift / orc_dot3(axis0, P.cell);
+            pos[1] += std::tan(L.tilt[0]) * tiltPositionShift;
+            pos[2] += std::tan(L.tilt[1]) * tiltPositionShift;
+        }
+        float const planeNoNormal[3] = {0.0f, 1.0f, 1.0f};
+        float const q[3] = {pos[0] * planeNoNormal[0], pos[1] * planeNoNormal[1], pos[2] * planeNoNormal[2]};
+        float transversalDistanceSquared = q[0] * q[0]; // l2norm2: Vector.tpp:104-110
+        transversalDistanceSquared += q[1] * q[1];
+        transversalDistanceSquared += q[2] * q[2];
+        float const R_inv = -focusPos / (rayleighLength * rayleighLength + focusPos * focusPos);
+        float const xi = std::atan(-focusPos / rayleighLength);
+        float etrans = 0.0f;
+        float const r2OverW2 = transversalDistanceSquared / w / w;
+        float const r = 0.5f * transversalDistanceSquared * R_inv;
+        float const twoPi = 6.28318530717958647692f; // Pi<float_X>::doubleValue
+        for(int m = 0; m < L.n_modes; ++m)
+            etrans += L.modes[m] * orc_simple_laguerre(unsigned(m), 2.0f * r2OverW2) * std::exp(-r2OverW2)
+                * std::cos(twoPi / L.wave_length * focusPos - twoPi / L.wave_length * r + (2.0f * float(m) + 1.0f) * xi + phase + L.mode_phases[m]);
+        float const shiftedTime = time - r / P.c;
+        // GaussianPulseEnvelope::getEnvelope (GaussianPulse.hpp:343-348)
+        float const exponent = shiftedTime / (2.0f * L.pulse_duration);
+        etrans *= std::exp(-exponent * exponent);
+        float etrans_norm = 0.0f;
+        for(int m = 0; m < L.n_modes; ++m)
+            etrans_norm += L.modes[m];
+        float envelope = L.amplitude;
+        envelope *= L.w0 / w;
+        return envelope * etrans / etrans_norm;
+    }
+
+    // incident E at a (fractional) total cell index: BaseFunctorE::getCurrentTime / getInternalCoordinates +
+    // BaseSeparableFunctorE::operator() (PlaneWave) or GaussianPulseFunctorIncidentE::operator()
+    static void orc_laser_incident_e(OrcParams const& P, OrcLaser const& L, OrcLaserFrame const& F, float currentStep, float const idx[3], float out[3])
+    {
+        float const axis0[3] = {0.0f, 1.0f, 0.0f};
+        float const shiftFromOrigin[3] = {idx[0] * P.cell[0] - F.origin[0], idx[1] * P.cell[1] - F.origin[1], idx[2] * P.cell[2] - F.origin[2]};
+        float const distance = orc_dot3(shiftFromOrigin, axis0);
+        float const timeDelay = distance / F.phaseVelocity + L.time_delay;
         float const time = currentStep * P.dt - timeDelay;
         out[0] = out[1] = out[2] = 0.0f;
         if(time < 0.0f)
             return;
-        float const transversal = 1.0f;
+        float a, b; // value with phase shift pi/2 (circular only) and 0
+        if(L.profile == 0)
+        {
+            float const transversal = 1.0f;
+            a = L.polarisation ? orc_laser_longitudinal(L, time, 1.57079632679489661923f) * transversal : 0.0f;
+            b = orc_laser_longitudinal(L, time, 0.0f) * transversal;
+        }
+        else
+        {
+            float pos[3] = {orc_dot3(shiftFromOrigin, axis0), orc_dot3(shiftFromOrigin, F.axis1), orc_dot3(shiftFromOrigin, F.axis2)};
+            a = L.polarisation ? orc_gaussian_pulse_value(P, L, F, pos, time, 1.57079632679489661923f) : 0.0f;
+            b = orc_gaussian_pulse_value(P, L, F, pos, time, 0.0f);
+        }
         if(L.polarisation == 0)
         {
-            float const v = orc_laser_longitudinal(L, time, 0.0f) * transversal;
             for(int d = 0; d < 3; ++d)
-                out[d] = L.pol[d] * v;
+                out[d] = L.pol[d] * b;
         }
         else
         {
@@ -1753,26 +1893,44 @@ extern "C"
             float const p1[3] = {L.pol[0] / rs2, L.pol[1] / rs2, L.pol[2] / rs2};
             // cross(axis0 = (0,1,0), p1)
             float const p2[3] = {1.0f * p1[2] - 0.0f * p1[1], 0.0f * p1[0] - 0.0f * p1[2], 0.0f * p1[1] - 1.0f * p1[0]};
-            float const a = orc_laser_longitudinal(L, time, 1.57079632679489661923f) * transversal;
-            float const b = orc_laser_longitudinal(L, time, 0.0f) * transversal;
             for(int d = 0; d < 3; ++d)
                 out[d] = p1[d] * a + p2[d] * b;
         }
     }
 
     /** incidentField::Solver::updateE (updatedIsE = 1, uses B_inc = cross(dir, E_inc) / c) or ::updateBHalf (0, uses
-     * E_inc) for a PlaneWave profile on YMin.  currentStep is fractional (FDTDBase.hpp:108-117,161-166). */
+     * E_inc) for a profile on YMin.  currentStep is fractional (FDTDBase.hpp:108-117,161-166).  The domain of this
+     * oracle spans x and z completely (it is the last one along both). */
     void orc_incident_update(OrcParams const* Pp, OrcLaser const* Lp, float* F, int updatedIsE, float currentStep)
     {
         OrcParams const& P = *Pp;
         OrcLaser const& L = *Lp;
         Dom const D(P);
         // Solver.hpp:230-236: the updated plane in user (total) coordinates; E sits in the total-field region
-        int const planeTotal = L.offset_ymin + 1 - (updatedIsE ? 0 : 1);
+        int const planeTotal = L.position[1][0] + 1 - (updatedIsE ? 0 : 1);
         int const yl = planeTotal - L.global_y_offset; // local, without guards
         if(yl < 0 || yl >= D.n[1])
             return;
-        float const vph = orc_laser_phase_velocity(P, L);
+        // transversal extent and "last updated cell" flags (Solver.hpp:209-258, Solver.kernel:458-466)
+        int lo[3], hi[3];
+        bool lastDomain[3];
+        for(int d = 0; d < 3; d += 2)
+        {
+            int begin = L.position[d][0] + 1;
+            int end = (L.position[d][1] > 0) ? L.position[d][1] : L.global_size[d] + L.position[d][1];
+            lastDomain[d] = true;
+            if(L.profile == 0 && L.periodic[d])
+            {
+                begin = 0;
+                end = L.global_size[d];
+                lastDomain[d] = false;
+            }
+            lo[d] = std::max(begin, 0);
+            hi[d] = std::min(end, D.n[d]);
+        }
+        if(lo[0] >= hi[0] || lo[2] >= hi[2])
+            return;
+        OrcLaserFrame const frame = orc_laser_frame(P, L);
         float const c2 = P.c * P.c;
         float const curlCoefficient = updatedIsE ? P.dt * c2 : -(0.5f * P.dt);
         float const baseCoefficient = curlCoefficient / P.cell[1] * 1.0f; // direction +1
@@ -1796,16 +1954,20 @@ extern "C"
         float* fz = F + 2 * D.vol;
         int const y = yl + D.g[1];
 #pragma omp parallel for schedule(static)
-        for(int z = D.g[2]; z < D.g[2] + D.n[2]; ++z)
-            for(int x = D.g[0]; x < D.g[0] + D.n[0]; ++x)
+        for(int zl = lo[2]; zl < hi[2]; ++zl)
+            for(int xl = lo[0]; xl < hi[0]; ++xl)
             {
+                bool const lastX = lastDomain[0] && xl == hi[0] - 1, lastZ = lastDomain[2] && zl == hi[2] - 1;
+                // Solver.kernel:318-325 with incidentComponent1 = x, incidentComponent2 = z
+                bool const apply1 = updatedIsE ? !lastZ : !lastX;
+                bool const apply2 = updatedIsE ? !lastX : !lastZ;
                 // total cell index of the Huygens surface cell = the updated cell (margin 1)
-                float const base[3] = {float(x - D.g[0]), float(planeTotal), float(z - D.g[2])};
+                float const base[3] = {float(xl), float(planeTotal), float(zl)};
                 float const i1[3] = {base[0] + shift1[0], base[1] + shift1[1], base[2] + shift1[2]};
                 float const i2[3] = {base[0] + shift2[0], base[1] + shift2[1], base[2] + shift2[2]};
                 float e1[3], e2[3], inc1, inc2;
-                orc_laser_incident_e(P, L, vph, currentStep, i1, e1);
-                orc_laser_incident_e(P, L, vph, currentStep, i2, e2);
+                orc_laser_incident_e(P, L, frame, currentStep, i1, e1);
+                orc_laser_incident_e(P, L, frame, currentStep, i2, e2);
                 if(updatedIsE)
                 {
                     // ApproximateIncidentB: cross((0,1,0), E) / c = (Ez, 0, -Ex) / c
@@ -1819,11 +1981,13 @@ extern "C"
                 }
                 // Solver.kernel:318-337: result[dir1 = z] = +base * inc1, result[dir2 = x] = -base * inc2
                 float rz = 0.0f, rx = 0.0f;
-                rz += 1.0f * inc1;
-                rx += 1.0f * inc2;
+                if(apply1)
+                    rz += 1.0f * inc1;
+                if(apply2)
+                    rx += 1.0f * inc2;
                 rz *= baseCoefficient;
                 rx *= -baseCoefficient;
-                int64_t const i = D.idx(x, y, z);
+                int64_t const i = D.idx(xl + D.g[0], y, zl + D.g[2]);
                 fz[i] += rz;
                 fx[i] += rx;
             }

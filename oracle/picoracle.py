@@ -43,8 +43,11 @@ class OrcParams(C.Structure):
     ]
 
 
+LASER_MAX_MODES = 8
+
+
 class OrcLaser(C.Structure):
-    """PlaneWave incident field on the YMin Huygens surface (oracle/picoracle.cpp: struct OrcLaser)"""
+    """Incident field (PlaneWave or GaussianPulse) on the YMin Huygens surface (oracle/picoracle.cpp: struct OrcLaser)"""
 
     _fields_ = [
         ("polarisation", C.c_int),
@@ -58,23 +61,69 @@ class OrcLaser(C.Structure):
         ("pol", C.c_float * 3),
         ("time_delay", C.c_float),
         ("global_y_offset", C.c_int),
+        ("profile", C.c_int),
+        ("position", (C.c_int * 2) * 3),
+        ("global_size", C.c_int * 3),
+        ("periodic", C.c_int * 3),
+        ("w0", C.c_float),
+        ("wave_length", C.c_float),
+        ("time_shift", C.c_float),
+        ("focus_position", C.c_float * 3),
+        ("focus_origin_center", C.c_int * 3),
+        ("tilt", C.c_float * 2),
+        ("n_modes", C.c_int),
+        ("modes", C.c_float * LASER_MAX_MODES),
+        ("mode_phases", C.c_float * LASER_MAX_MODES),
     ]
 
 
+def laser_position(las):
+    """POSITION[3][2] of a laser dict: 'position' if given, else {offset_ymin, -offset_ymin} on every axis"""
+    if las.get("position") is not None:
+        return tuple((int(a), int(b)) for a, b in las["position"])
+    o = int(las["offset_ymin"])
+    return ((o, -o), (o, -o), (o, -o))
+
+
 def make_laser(cfg):
-    """cfg.laser: dict with the PlaneWave parameters in PIC units (picongpu_b200.param.plane_wave_laser) or None"""
-    las = cfg.get("laser") if isinstance(cfg, dict) else getattr(cfg, "laser", None)
+    """cfg.laser: dict with the profile parameters in PIC units (picongpu_b200.param.plane_wave_laser /
+    gaussian_pulse_laser) or None"""
+    g = (lambda k, dflt=None: cfg.get(k, dflt)) if isinstance(cfg, dict) else (lambda k, dflt=None: getattr(cfg, k, dflt))
+    las = g("laser")
     if not las:
         return None
     L = OrcLaser()
     L.polarisation = int(las["polarisation"])
     L.offset_ymin = int(las["offset_ymin"])
     for k in ("amplitude", "omega", "pulse_duration", "nofocus_constant", "ramp_init", "phase", "time_delay"):
-        setattr(L, k, float(las[k]))
+        setattr(L, k, float(las.get(k, 0.0)))
     for d in range(3):
         L.pol[d] = float(las["pol"][d])
-    go = cfg["global_offset"] if isinstance(cfg, dict) else getattr(cfg, "global_offset", (0, 0, 0))
+    go = g("global_offset", (0, 0, 0))
     L.global_y_offset = int(go[1])
+    L.profile = int(las.get("profile", 0))
+    pos = laser_position(las)
+    gg = g("global_grid") or g("grid")
+    per = g("periodic", (1, 0, 1))
+    for d in range(3):
+        L.position[d][0], L.position[d][1] = pos[d]
+        L.global_size[d] = int(gg[d])
+        L.periodic[d] = int(per[d])
+        L.focus_position[d] = float(las.get("focus_position", (0.0, 0.0, 0.0))[d])
+        L.focus_origin_center[d] = int(las.get("focus_origin_center", (0, 0, 0))[d])
+    if L.position[1][0] != L.offset_ymin:
+        raise ValueError("laser: position[1][0] must equal offset_ymin")
+    L.w0 = float(las.get("w0", 0.0))
+    L.wave_length = float(las.get("wave_length", 0.0))
+    L.time_shift = float(las.get("time_shift", 0.0))
+    L.tilt[0], L.tilt[1] = (float(v) for v in las.get("tilt", (0.0, 0.0)))
+    modes = list(las.get("modes", (1.0,)))
+    phases = list(las.get("mode_phases", (0.0,) * len(modes)))
+    if not 1 <= len(modes) <= LASER_MAX_MODES or len(phases) != len(modes):
+        raise ValueError("laser: 1..8 Laguerre modes with one phase each")
+    L.n_modes = len(modes)
+    for m in range(len(modes)):
+        L.modes[m], L.mode_phases[m] = float(modes[m]), float(phases[m])
     return L
 
 

@@ -94,17 +94,26 @@ namespace picstep
     };
 
     // PlaneWave incident field on the YMin Huygens surface (fields.cu: incidentKernel), unitless profile parameters
+    constexpr int LASER_MAX_MODES = 8;
+
     struct LaserDev
     {
         int polarisation, plane; // plane: padded-grid y index of the updated plane of this call
+        int profile; // 0 PlaneWave, 1 GaussianPulse
         float planeTotal; // its total (global) cell index along y
         float amplitude, omega, pulseDuration, nofocusConstant, rampInit, phase, timeDelay;
-        float pol[3];
-        float originY; // (POSITION[1][0] + 0.75) * cellSize.y
+        float pol[3], axis2[3]; // internal axes 1 and 2 (axis 0 = propagation = +y)
+        float origin[3], focus[3]; // BaseFunctorE::getOrigin / getFocus
         float phaseVelocity; // Yee numerical phase velocity along y, in units of c
         float currentTimeOrigin; // currentStep * dt (fractional step)
         float baseCoefficient; // curl coefficient / cellSize.y (direction +1)
         int updatedIsE;
+        int lo[2], hi[2]; // updated cells along x and z (local = global: neither axis is split), [lo, hi)
+        int lastDomain[2]; // the last cell of the range drops one component (Solver.kernel:318-325,458-466)
+        // GaussianPulse
+        float w0, waveLength, rayleighLength, timeShift, tanTilt[2];
+        int tilted, nModes;
+        float modes[LASER_MAX_MODES], modePhases[LASER_MAX_MODES];
     };
 
     // convolutional PML (fields.cu: pmlUpdate*Kernel): local thickness per [axis][negative, positive], graded parameters,

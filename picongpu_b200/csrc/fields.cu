@@ -443,7 +443,8 @@ namespace picstep
     // ---- incident field (laser): PlaneWave profile through the YMin Huygens surface, Yee solver --------------------
     // Reference: fields/incidentField/Solver.hpp:190-395 (updateField: which plane, in-cell shifts, coefficients),
     // Solver.kernel:101-404 (UpdateFunctor; Yee: margin 1, single derivative coefficient 1), Functors.hpp
-    // (BaseFunctorE::getCurrentTime, BaseSeparableFunctorE::operator(), ApproximateIncidentB), profiles/PlaneWave.hpp:93-130.
+    // (BaseFunctorE::getCurrentTime, BaseSeparableFunctorE::operator(), ApproximateIncidentB), profiles/PlaneWave.hpp:93-130,
+    // profiles/GaussianPulse.hpp:186-346.
     // One thread per cell of the updated plane.  Same float operations in the same order as the oracle's restatement;
     // sin / cos / exp are the device's (1-2 ulp from the host's).
     __device__ __forceinline__ float laserLongitudinal(LaserDev const& L, float time, float phaseShift)
@@ -471,28 +472,110 @@ namespace picstep
         return (sinf(phase) + cosf(phase) * integrationCorrectionFactor) * envelope;
     }
 
-    __device__ __forceinline__ void laserIncidentE(DevParams const& P, LaserDev const& L, float idxY, float out[3])
+    __device__ __forceinline__ float dot3(float const a[3], float const b[3])
     {
-        float const distance = idxY * P.cell[1] - L.originY;
+        float tmp = a[0] * b[0];
+        tmp += a[1] * b[1];
+        tmp += a[2] * b[2];
+        return tmp;
+    }
+
+    // GaussianPulseFunctorIncidentE::simpleLaguerre (profiles/GaussianPulse.hpp:316-336)
+    __device__ __forceinline__ float simpleLaguerre(unsigned n, float x)
+    {
+        if(n == 0)
+            return 1.0f;
+        unsigned currentN = 1;
+        float laguerreNMinus1 = 1.0f;
+        float laguerreN = 1.0f - x;
+        while(currentN < n)
+        {
+            float const laguerreNPlus1 = ((2.0f * float(currentN) + 1.0f - x) * laguerreN - float(currentN) * laguerreNMinus1) / float(currentN + 1u);
+            laguerreNMinus1 = laguerreN;
+            laguerreN = laguerreNPlus1;
+            currentN++;
+        }
+        return laguerreN;
+    }
+
+    // GaussianPulseFunctorIncidentE::getValue (profiles/GaussianPulse.hpp:208-308) + GaussianPulseEnvelope (:343-348)
+    __device__ __forceinline__ float gaussianPulseValue(DevParams const& P, LaserDev const& L, float const posIn[3], float time, float phaseShift)
+    {
+        float pos[3] = {posIn[0], posIn[1], posIn[2]};
+        time += L.timeShift;
+        float const focusRelativeToOrigin[3] = {L.focus[0] - L.origin[0], L.focus[1] - L.origin[1], L.focus[2] - L.origin[2]};
+        float const axis0[3] = {0.0f, 1.0f, 0.0f};
+        float const distanceFocusRelativeToOrigin = dot3(focusRelativeToOrigin, axis0);
+        float const focusPos = distanceFocusRelativeToOrigin - pos[0];
+        float const w = L.w0 * sqrtf(1.0f + (focusPos / L.rayleighLength) * (focusPos / L.rayleighLength));
+        float const phase = L.omega * (time - focusPos / P.c) + L.phase + phaseShift;
+        if(L.tilted)
+        {
+            float const tiltTimeShift = phase / L.omega + focusPos / P.c;
+            float const tiltPositionShift = P.c * tiltTimeShift / dot3(axis0, P.cell);
+            pos[1] += L.tanTilt[0] * tiltPositionShift;
+            pos[2] += L.tanTilt[1] * tiltPositionShift;
+        }
+        float const q[3] = {pos[0] * 0.0f, pos[1] * 1.0f, pos[2] * 1.0f};
+        float transversalDistanceSquared = q[0] * q[0];
+        transversalDistanceSquared += q[1] * q[1];
+        transversalDistanceSquared += q[2] * q[2];
+        float const R_inv = -focusPos / (L.rayleighLength * L.rayleighLength + focusPos * focusPos);
+        float const xi = atanf(-focusPos / L.rayleighLength);
+        float etrans = 0.0f;
+        float const r2OverW2 = transversalDistanceSquared / w / w;
+        float const r = 0.5f * transversalDistanceSquared * R_inv;
+        float const twoPi = 6.28318530717958647692f;
+        for(int m = 0; m < L.nModes; ++m)
+            etrans += L.modes[m] * simpleLaguerre(unsigned(m), 2.0f * r2OverW2) * expf(-r2OverW2)
+                * cosf(twoPi / L.waveLength * focusPos - twoPi / L.waveLength * r + (2.0f * float(m) + 1.0f) * xi + phase + L.modePhases[m]);
+        float const shiftedTime = time - r / P.c;
+        float const exponent = shiftedTime / (2.0f * L.pulseDuration);
+        etrans *= expf(-exponent * exponent);
+        float etrans_norm = 0.0f;
+        for(int m = 0; m < L.nModes; ++m)
+            etrans_norm += L.modes[m];
+        float envelope = L.amplitude;
+        envelope *= L.w0 / w;
+        return envelope * etrans / etrans_norm;
+    }
+
+    // incident E at a fractional total cell index (Functors.hpp: BaseFunctorE::getCurrentTime / getInternalCoordinates)
+    __device__ __forceinline__ void laserIncidentE(DevParams const& P, LaserDev const& L, float const idx[3], float out[3])
+    {
+        float const axis0[3] = {0.0f, 1.0f, 0.0f};
+        float const shiftFromOrigin[3] = {idx[0] * P.cell[0] - L.origin[0], idx[1] * P.cell[1] - L.origin[1], idx[2] * P.cell[2] - L.origin[2]};
+        float const distance = dot3(shiftFromOrigin, axis0);
         float const timeDelay = distance / L.phaseVelocity + L.timeDelay;
         float const time = L.currentTimeOrigin - timeDelay;
         out[0] = out[1] = out[2] = 0.0f;
         if(time < 0.0f)
             return;
+        float a = 0.0f, b;
+        if(L.profile == 0)
+        {
+            if(L.polarisation)
+                a = laserLongitudinal(L, time, 1.57079632679489661923f) * 1.0f;
+            b = laserLongitudinal(L, time, 0.0f) * 1.0f;
+        }
+        else
+        {
+            float const pos[3] = {dot3(shiftFromOrigin, axis0), dot3(shiftFromOrigin, L.pol), dot3(shiftFromOrigin, L.axis2)};
+            if(L.polarisation)
+                a = gaussianPulseValue(P, L, pos, time, 1.57079632679489661923f);
+            b = gaussianPulseValue(P, L, pos, time, 0.0f);
+        }
         if(L.polarisation == 0)
         {
-            float const v = laserLongitudinal(L, time, 0.0f) * 1.0f;
 #pragma unroll
             for(int d = 0; d < 3; ++d)
-                out[d] = L.pol[d] * v;
+                out[d] = L.pol[d] * b;
         }
         else
         {
             float const rs2 = sqrtf(2.0f);
             float const p1[3] = {L.pol[0] / rs2, L.pol[1] / rs2, L.pol[2] / rs2};
             float const p2[3] = {1.0f * p1[2] - 0.0f * p1[1], 0.0f * p1[0] - 0.0f * p1[2], 0.0f * p1[1] - 1.0f * p1[0]};
-            float const a = laserLongitudinal(L, time, 1.57079632679489661923f) * 1.0f;
-            float const b = laserLongitudinal(L, time, 0.0f) * 1.0f;
 #pragma unroll
             for(int d = 0; d < 3; ++d)
                 out[d] = p1[d] * a + p2[d] * b;
@@ -501,29 +584,54 @@ namespace picstep
 
     __global__ void __launch_bounds__(256) incidentKernel(DevParams P, Field3 F, LaserDev L)
     {
-        int const x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
-        if(x >= P.n[0] || z >= P.n[2])
+        int const x = L.lo[0] + blockIdx.x * blockDim.x + threadIdx.x, z = L.lo[1] + blockIdx.y;
+        if(x >= L.hi[0] || z >= L.hi[1])
             return;
-        // the plane-wave profile depends on y only: the in-cell shifts along x and z drop out, the one along y is
-        // -1 + 0.5 for the E update (B_inc on its Yee position) and +1 + 0 for the B update (Solver.hpp:360-372)
-        float const shiftY = L.updatedIsE ? (-1.0f + 0.5f) : (1.0f + 0.0f);
-        float e[3];
-        laserIncidentE(P, L, L.planeTotal + shiftY, e);
+        bool const lastX = L.lastDomain[0] && x == L.hi[0] - 1, lastZ = L.lastDomain[1] && z == L.hi[1] - 1;
+        // Solver.kernel:318-325 with incidentComponent1 = x, incidentComponent2 = z
+        bool const apply1 = L.updatedIsE ? !lastZ : !lastX;
+        bool const apply2 = L.updatedIsE ? !lastX : !lastZ;
+        // in-cell shifts (Solver.hpp:360-372): -1 (E updated) / +1 (B updated) along y plus the Yee position of the
+        // incident component: B_inc,x at (0, .5, .5), B_inc,z at (.5, .5, 0); E_inc,x at (.5, 0, 0), E_inc,z at (0, 0, .5)
+        float const baseShift = L.updatedIsE ? -1.0f : 1.0f;
+        float const base[3] = {float(x), L.planeTotal, float(z)};
+        float i1[3], i2[3];
+        if(L.updatedIsE)
+        {
+            i1[0] = base[0] + 0.0f, i1[1] = base[1] + (baseShift + 0.5f), i1[2] = base[2] + 0.5f;
+            i2[0] = base[0] + 0.5f, i2[1] = base[1] + (baseShift + 0.5f), i2[2] = base[2] + 0.0f;
+        }
+        else
+        {
+            i1[0] = base[0] + 0.5f, i1[1] = base[1] + (baseShift + 0.0f), i1[2] = base[2] + 0.0f;
+            i2[0] = base[0] + 0.0f, i2[1] = base[1] + (baseShift + 0.0f), i2[2] = base[2] + 0.5f;
+        }
+        float e1[3], e2[3];
+        laserIncidentE(P, L, i1, e1);
+        if(L.profile == 0)
+        {
+            // the plane wave depends on y only: both evaluations see the same point
+            e2[0] = e1[0], e2[1] = e1[1], e2[2] = e1[2];
+        }
+        else
+            laserIncidentE(P, L, i2, e2);
         float inc1, inc2; // incident components x and z
         if(L.updatedIsE)
         {
             // ApproximateIncidentB: cross((0,1,0), E) / c
-            inc1 = (1.0f * e[2] - 0.0f * e[1]) / P.c;
-            inc2 = (0.0f * e[1] - 1.0f * e[0]) / P.c;
+            inc1 = (1.0f * e1[2] - 0.0f * e1[1]) / P.c;
+            inc2 = (0.0f * e2[1] - 1.0f * e2[0]) / P.c;
         }
         else
         {
-            inc1 = e[0];
-            inc2 = e[2];
+            inc1 = e1[0];
+            inc2 = e2[2];
         }
         float rz = 0.0f, rx = 0.0f;
-        rz += 1.0f * inc1;
-        rx += 1.0f * inc2;
+        if(apply1)
+            rz += 1.0f * inc1;
+        if(apply2)
+            rx += 1.0f * inc2;
         rz *= L.baseCoefficient;
         rx *= -L.baseCoefficient;
         long long const i = fidx(P, x + P.g[0], L.plane, z + P.g[2]);
@@ -907,7 +1015,7 @@ namespace picstep
 
     cudaError_t launchIncident(DevParams const& P, Field3 F, LaserDev const& L, cudaStream_t st)
     {
-        dim3 const grid((P.n[0] + 255) / 256, P.n[2]);
+        dim3 const grid((L.hi[0] - L.lo[0] + 255) / 256, L.hi[1] - L.lo[1]);
         incidentKernel<<<grid, 256, 0, st>>>(P, F, L);
         return cudaGetLastError();
     }

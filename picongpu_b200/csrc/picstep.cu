@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -770,8 +771,26 @@ extern "C"
             return fail(nullptr, PICSTEP_ERR_INVALID, "EmZ needs at least CIC");
         if(p->laser_enabled)
         {
-            if(p->field_solver != PICSTEP_SOLVER_YEE || p->periodic[1] || !p->periodic[0] || !p->periodic[2])
-                return fail(nullptr, PICSTEP_ERR_INVALID, "the incident field source is built for the Yee solver, a non-periodic y axis and periodic x, z");
+            if(p->field_solver != PICSTEP_SOLVER_YEE || p->periodic[1])
+                return fail(nullptr, PICSTEP_ERR_INVALID, "the incident field source is built for the Yee solver and a non-periodic y axis");
+            if(p->laser_profile < 0 || p->laser_profile > PICSTEP_LASER_GAUSSIAN_PULSE)
+                return fail(nullptr, PICSTEP_ERR_INVALID, "unknown incident field profile");
+            bool anyPos = false;
+            for(int d = 0; d < 3; ++d)
+                anyPos = anyPos || p->laser_position[d][0] || p->laser_position[d][1];
+            if(anyPos && p->laser_position[1][0] != p->laser_offset_ymin)
+                return fail(nullptr, PICSTEP_ERR_INVALID, "laser_position[1][0] must equal laser_offset_ymin");
+            if(p->laser_profile == PICSTEP_LASER_GAUSSIAN_PULSE)
+            {
+                if(!(p->laser_w0 > 0.0f) || !(p->laser_wave_length > 0.0f) || p->laser_n_modes < 0 || p->laser_n_modes > LASER_MAX_MODES)
+                    return fail(nullptr, PICSTEP_ERR_INVALID, "bad GaussianPulse parameters (W0, WAVE_LENGTH, number of Laguerre modes)");
+                // GaussianPulseFunctorIncidentE constructor: "Sum of laguerreModes can not be 0."
+                float norm = 0.0f;
+                for(int m = 0; m < p->laser_n_modes; ++m)
+                    norm += p->laser_modes[m];
+                if(p->laser_n_modes > 0 && !(std::abs(norm) > std::numeric_limits<float>::epsilon()))
+                    return fail(nullptr, PICSTEP_ERR_INVALID, "Sum of laguerreModes can not be 0.");
+            }
             // Solver.hpp:133-159 (checkRequirements): the surface keeps clear of the absorber and of the local domain border
             int const minOffset = p->absorber_kind ? p->absorber_cells[1][0] : 0;
             if(p->laser_offset_ymin < minOffset || p->laser_offset_ymin + 2 > p->grid[1])
@@ -1455,8 +1474,38 @@ extern "C"
         int const yl = planeTotal - p.grid[1] * p.rank_pos[1];
         if(yl < 0 || yl >= P.n[1])
             return PICSTEP_OK;
+        // POSITION (all zero: {offset, -offset} on every axis), global size, transversal extent of the surface
+        int position[3][2], globalSize[3];
+        bool anyPos = false;
+        for(int d = 0; d < 3; ++d)
+            anyPos = anyPos || p.laser_position[d][0] || p.laser_position[d][1];
+        for(int d = 0; d < 3; ++d)
+        {
+            position[d][0] = anyPos ? p.laser_position[d][0] : p.laser_offset_ymin;
+            position[d][1] = anyPos ? p.laser_position[d][1] : -p.laser_offset_ymin;
+            globalSize[d] = p.grid[d] * p.devices[d];
+        }
         LaserDev L{};
+        for(int t = 0; t < 2; ++t)
+        {
+            // Solver.hpp:209-258: contiguous over a periodic transversal axis for the PlaneWave profile only
+            int const d = 2 * t;
+            int begin = position[d][0] + 1;
+            int end = position[d][1] > 0 ? position[d][1] : globalSize[d] + position[d][1];
+            L.lastDomain[t] = 1; // x and z are never split: this rank is the last one along both
+            if(p.laser_profile == PICSTEP_LASER_PLANE_WAVE && p.periodic[d])
+            {
+                begin = 0;
+                end = globalSize[d];
+                L.lastDomain[t] = 0;
+            }
+            L.lo[t] = std::max(begin, 0);
+            L.hi[t] = std::min(end, P.n[d]);
+        }
+        if(L.lo[0] >= L.hi[0] || L.lo[1] >= L.hi[1])
+            return PICSTEP_OK;
         L.polarisation = p.laser_polarisation;
+        L.profile = p.laser_profile;
         L.plane = yl + P.g[1];
         L.planeTotal = float(planeTotal);
         L.amplitude = p.laser_amplitude;
@@ -1468,7 +1517,48 @@ extern "C"
         L.timeDelay = p.laser_time_delay;
         for(int d = 0; d < 3; ++d)
             L.pol[d] = p.laser_pol_dir[d];
-        L.originY = (float(p.laser_offset_ymin) + 0.75f) * P.cell[1];
+        {
+            // BaseFunctorE::getFocus / getOrigin / getAxis2 (Functors.hpp:267-380) for DIR = (0, 1, 0), in float_X
+            float const direction[3] = {0.0f, 1.0f, 0.0f};
+            for(int d = 0; d < 3; ++d)
+            {
+                L.focus[d] = p.laser_focus_position[d];
+                if(p.laser_focus_origin_center[d])
+                    L.focus[d] += float(unsigned(globalSize[d]) / 2u) * P.cell[d];
+            }
+            float originP = -std::numeric_limits<float>::infinity();
+            for(int axis = 0; axis < 3; ++axis)
+                if(std::abs(direction[axis]) > std::numeric_limits<float>::epsilon())
+                {
+                    float const minPosition = (float(position[axis][0]) + 0.75f) * P.cell[axis];
+                    int const maxPositionIdx = position[axis][1] > 0 ? position[axis][1] : globalSize[axis] + position[axis][1];
+                    float const maxPosition = (float(maxPositionIdx) - 0.75f) * P.cell[axis];
+                    float const axisP = std::min((minPosition - L.focus[axis]) / direction[axis], (maxPosition - L.focus[axis]) / direction[axis]);
+                    originP = std::max(originP, axisP);
+                }
+            for(int d = 0; d < 3; ++d)
+                L.origin[d] = L.focus[d] + originP * direction[d];
+            L.axis2[0] = direction[1] * L.pol[2] - direction[2] * L.pol[1];
+            L.axis2[1] = direction[2] * L.pol[0] - direction[0] * L.pol[2];
+            L.axis2[2] = direction[0] * L.pol[1] - direction[1] * L.pol[0];
+        }
+        if(p.laser_profile == PICSTEP_LASER_GAUSSIAN_PULSE)
+        {
+            // GaussianPulseUnitless (profiles/GaussianPulse.hpp:93-110)
+            L.w0 = p.laser_w0;
+            L.waveLength = p.laser_wave_length;
+            L.rayleighLength = 3.14159265358979323846f * L.w0 * L.w0 / L.waveLength;
+            L.timeShift = p.laser_time_shift;
+            L.tilted = (p.laser_tilt[0] != 0.0f || p.laser_tilt[1] != 0.0f) ? 1 : 0;
+            L.tanTilt[0] = std::tan(p.laser_tilt[0]);
+            L.tanTilt[1] = std::tan(p.laser_tilt[1]);
+            L.nModes = p.laser_n_modes > 0 ? p.laser_n_modes : 1;
+            for(int m = 0; m < L.nModes; ++m)
+            {
+                L.modes[m] = p.laser_n_modes > 0 ? p.laser_modes[m] : 1.0f;
+                L.modePhases[m] = p.laser_n_modes > 0 ? p.laser_mode_phases[m] : 0.0f;
+            }
+        }
         {
             // Yee dispersion relation along y (calculatePhaseVelocity.hpp, DispersionRelationSolver), fp64
             double const w = double(p.laser_omega), dt = double(P.dt), cc = double(P.c), dy = double(P.cell[1]);

@@ -69,7 +69,8 @@ class SimParams:
     moving_window: int = 0  # -m: sliding window along y (needs a non-periodic y axis)
     # fieldAbsorber.param pml:: values (dict from pml_params(), PIC units); used with absorber_kind = 2
     pml: dict = None
-    # incidentField.param: PlaneWave profile on YMin (dict from plane_wave_laser(), PIC units) or None = profiles::None
+    # incidentField.param: PlaneWave / GaussianPulse profile on YMin (dict from plane_wave_laser() / gaussian_pulse_laser(),
+    # PIC units) or None = profiles::None
     laser: dict = None
     # --- runtime (-d, --periodic) ---
     periodic: tuple = (1, 1, 1)
@@ -174,6 +175,46 @@ def plane_wave_laser(p, a0=1.0, wavelength_si=0.8e-6, pulse_duration_si=5.0e-15,
         pulse_duration=_f32(pulse_duration_si / p.unit_time),
         nofocus_constant=_f32(nofocus_constant_si / p.unit_time),
         ramp_init=_f32(ramp_init),
+        phase=_f32(phase),
+        pol=tuple(_f32(v) for v in pol_dir),
+        time_delay=_f32(time_delay_si / p.unit_time),
+    )
+
+
+def gaussian_pulse_laser(p, a0=8.0, wavelength_si=0.8e-6, pulse_duration_si=5.0e-15, w0_si=5.0e-6 / 1.17741, pulse_init=15.0,
+                         focus_position_si=(0.0, 4.62e-5, 0.0), focus_origin_center=(1, 0, 1), phase=0.0, polarisation="circular",
+                         pol_dir=(1.0, 0.0, 0.0), position=((16, -16), (16, -16), (16, -16)), time_delay_si=0.0,
+                         tilt_deg=(0.0, 0.0), modes=(1.0,), mode_phases=None):
+    """incidentField.param for a `profiles::GaussianPulse<Params, GaussianPulseEnvelope<Params>>` (with a tilt:
+    `PulseFrontTilt`) entering through YMin: the SI parameters converted as in GaussianPulseUnitless / BaseParamUnitless
+    (profiles/GaussianPulse.hpp:93-110, BaseParam.hpp:43-180).  The defaults are the values of
+    examples/LaserWakefield/include/picongpu/param/incidentField.param (a0 = 8, circular, focus 46.2 um behind the
+    y boundary on the transversal centre of the box)."""
+    amplitude_si = a0 * (-2.0 * math.pi / wavelength_si * ELECTRON_MASS_SI * SPEED_OF_LIGHT_SI**2 / ELECTRON_CHARGE_SI)
+    wave_length = _f32(wavelength_si / p.unit_length)
+    f = _f32(np.float32(p.c) / np.float32(wave_length))
+    pulse_duration = _f32(pulse_duration_si / p.unit_time)
+    pi_f = float(np.float32(math.pi))
+    modes = tuple(_f32(m) for m in modes)
+    return dict(
+        profile=1,
+        polarisation=0 if polarisation == "linear" else 1,
+        offset_ymin=int(position[1][0]),
+        position=tuple((int(a), int(b)) for a, b in position),
+        amplitude=_f32(amplitude_si / p.unit_efield),
+        omega=_f32(np.float32(2.0 * math.pi) * np.float32(f)),
+        wave_length=wave_length,
+        pulse_duration=pulse_duration,
+        # GaussianPulseEnvelope::TIME_SHIFT = -0.5_X * PULSE_INIT (float_64) * PULSE_DURATION (float_X)
+        time_shift=_f32(-0.5 * float(pulse_init) * pulse_duration),
+        w0=_f32(w0_si / p.unit_length),
+        focus_position=tuple(_f32(v / p.unit_length) for v in focus_position_si),
+        focus_origin_center=tuple(int(v) for v in focus_origin_center),
+        tilt=tuple(_f32(t * pi_f / 180.0) for t in tilt_deg),
+        modes=modes,
+        mode_phases=tuple(_f32(v) for v in (mode_phases if mode_phases is not None else (0.0,) * len(modes))),
+        nofocus_constant=0.0,
+        ramp_init=0.0,
         phase=_f32(phase),
         pol=tuple(_f32(v) for v in pol_dir),
         time_delay=_f32(time_delay_si / p.unit_time),

@@ -81,6 +81,17 @@ class Params(C.Structure):
         ("pml_alpha_max", C.c_float * 3),
         ("pml_sigma_kappa_grading_order", C.c_float),
         ("pml_alpha_grading_order", C.c_float),
+        ("laser_profile", C.c_int32),
+        ("laser_position", (C.c_int32 * 2) * 3),
+        ("laser_w0", C.c_float),
+        ("laser_wave_length", C.c_float),
+        ("laser_time_shift", C.c_float),
+        ("laser_focus_position", C.c_float * 3),
+        ("laser_focus_origin_center", C.c_int32 * 3),
+        ("laser_tilt", C.c_float * 2),
+        ("laser_n_modes", C.c_int32),
+        ("laser_modes", C.c_float * 8),
+        ("laser_mode_phases", C.c_float * 8),
     ]
 
 
@@ -181,6 +192,23 @@ def to_c_params(p, device=0, flags=0):
         cp.laser_ramp_init, cp.laser_phase, cp.laser_time_delay = las["ramp_init"], las["phase"], las["time_delay"]
         for d in range(3):
             cp.laser_pol_dir[d] = las["pol"][d]
+        cp.laser_profile = int(las.get("profile", 0))
+        if las.get("position") is not None:
+            for d in range(3):
+                cp.laser_position[d][0], cp.laser_position[d][1] = (int(v) for v in las["position"][d])
+        cp.laser_w0, cp.laser_wave_length = las.get("w0", 0.0), las.get("wave_length", 0.0)
+        cp.laser_time_shift = las.get("time_shift", 0.0)
+        for d in range(3):
+            cp.laser_focus_position[d] = las.get("focus_position", (0.0, 0.0, 0.0))[d]
+            cp.laser_focus_origin_center[d] = int(las.get("focus_origin_center", (0, 0, 0))[d])
+        cp.laser_tilt[0], cp.laser_tilt[1] = las.get("tilt", (0.0, 0.0))
+        modes = las.get("modes", (1.0,))
+        phases = las.get("mode_phases", (0.0,) * len(modes))
+        if len(modes) > 8 or len(phases) != len(modes):
+            raise ValueError("laser: at most 8 Laguerre modes, one phase each")
+        cp.laser_n_modes = len(modes)
+        for m in range(len(modes)):
+            cp.laser_modes[m], cp.laser_mode_phases[m] = modes[m], phases[m]
     for d in range(3):
         for sd in range(2):
             cp.absorber_cells[d][sd] = int(getattr(p, "absorber_cells", ((0, 0),) * 3)[d][sd])

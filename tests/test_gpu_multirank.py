@@ -29,6 +29,14 @@ OPEN = dict(periodic=(1, 0, 1), current_interpolation=1, absorber_kind=1, absorb
             absorber_strength=((0, 0), (0.05, 0.05), (0, 0)))  # LWFA-like boundaries: open + absorbing along the split axis
 
 
+# examples/LaserWakefield's boundaries and source: nothing periodic, PML on every outer face, a GaussianPulse (three
+# Laguerre modes) entering through a Huygens surface five cells below the rank boundary, so that the pulse crosses it
+_P0 = prm.khi_params(grid=LOCAL)
+LWFA = dict(periodic=(0, 0, 0), absorber_kind=2, absorber_cells=((4, 4), (6, 6), (2, 2)), pml=prm.pml_params(_P0),
+            laser=prm.gaussian_pulse_laser(_P0, a0=0.5, pulse_duration_si=3e-15, w0_si=0.4e-6, pulse_init=1.0, focus_position_si=(0.0, 3.5e-6, 0.0),
+                                           polarisation="circular", position=((5, -5), (26, -8), (2, -2)), modes=(0.7, 0.2, 0.1)))
+
+
 def _worker(rank, world, port, steps, fused, outdir, kw):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -65,13 +73,13 @@ def _worker(rank, world, port, steps, fused, outdir, kw):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fused,variant", [(True, "periodic"), (False, "periodic"), (True, "open")])
+@pytest.mark.parametrize("fused,variant", [(True, "periodic"), (False, "periodic"), (True, "open"), (True, "lwfa")])
 def test_two_gpu_slab_decomposition_equals_single_domain(orc, tmp_path, fused, variant):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    world, steps = 2, 6
-    kw = OPEN if variant == "open" else {}
-    port = 29500 + (os.getpid() % 2000) + (7 if fused else 0) + (13 if kw else 0)
+    world, steps = 2, (16 if variant == "lwfa" else 6)
+    kw = {"open": OPEN, "lwfa": LWFA}.get(variant, {})
+    port = 29500 + (os.getpid() % 2000) + (7 if fused else 0) + (13 if kw else 0) + (17 if variant == "lwfa" else 0)
     mp.spawn(_worker, args=(world, port, steps, fused, str(tmp_path), kw), nprocs=world, join=True)
     p = prm.khi_params(grid=(LOCAL[0], LOCAL[1] * world, LOCAL[2]), **kw)
     o, e, i = util.khi_ic(orc, p)
@@ -87,6 +95,11 @@ def test_two_gpu_slab_decomposition_equals_single_domain(orc, tmp_path, fused, v
     Eg = np.concatenate([r[0]["E"], r[1]["E"]], axis=2)
     Bg = np.concatenate([r[0]["B"], r[1]["B"]], axis=2)
     _, escale = util.khi_scales(p, 1)
+    if variant == "lwfa":
+        amp = abs(p.laser["amplitude"])
+        escale = max(escale, amp)
+        # the pulse has crossed from rank 0 (which holds the Huygens surface) into rank 1
+        assert np.abs(r[1]["E"]).max() > 0.03 * amp
     # production build vs oracle, tolerance as in test_khi_100_steps_vs_oracle (2e-5 of the per-species drive scale)
     assert np.abs(Eg - o.interior(E)).max() / escale < 2e-5
     assert np.abs(Bg - o.interior(B)).max() / escale < 2e-5

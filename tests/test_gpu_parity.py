@@ -875,6 +875,73 @@ def test_incident_plane_wave_vs_oracle(orc, exact, polarisation):
 
 
 @pytest.mark.parametrize("exact", [True, False])
+def test_incident_gaussian_pulse_vs_oracle(orc, exact):
+    """GaussianPulse profile of examples/LaserWakefield (profiles/GaussianPulse.hpp; bounded Huygens surface,
+    Solver.hpp:209-258) through YMin: (a) on vacuum with absorbing x, y, z the fields equal the oracle's restatement and
+    the pulse focuses where and as tightly as requested; (b) --periodic 0 0 1 with a plasma in the box, three Laguerre
+    modes, a tilted pulse front and circular polarisation: the coupled step against the oracle."""
+    kw = dict(periodic=(0, 0, 0), absorber_kind=1, absorber_cells=((8, 8),) * 3, absorber_strength=((1e-3, 1e-3),) * 3)
+    p = util.make_params((64, 64, 64), **kw)
+    las = p.laser = prm.gaussian_pulse_laser(p, a0=0.5, pulse_duration_si=3e-15, w0_si=1.0e-6, pulse_init=6.0, focus_position_si=(0.0, 4.0e-6, 0.0),
+                                             polarisation="linear", pol_dir=(1.0, 0.0, 0.0), position=((10, -10),) * 3)
+    amp = abs(las["amplitude"])
+    fy = int(round(las["focus_position"][1] / p.cell_size[1]))
+    s = _sim(p, exact)
+    o = orc.Oracle(p)
+    E, B, J = o.field(), o.field(), o.field()
+    peak_map = np.zeros((64, 64))
+    worst = 0.0
+    for chunk in range(13):
+        s.step(10)
+        s.sync()
+        Eg = s.download_field(FE)
+        for _ in range(10):
+            o.step_open(E, B, J, [])
+        worst = max(worst, float(np.abs(o.interior(Eg) - o.interior(E)).max()) / amp)
+        peak_map = np.maximum(peak_map, np.abs(o.interior(Eg)[0][:, fy, :]))
+    Bg = s.download_field(FB)
+    dB = np.abs(o.interior(Bg) - o.interior(B)).max() / (amp / p.c)
+    behind = np.abs(o.interior(Eg)[:, :, :10, :]).max() / amp
+    w0_cells = las["w0"] / p.cell_size[0]
+    row = peak_map[32, :] / peak_map.max()
+    x = np.arange(64) + 0.5 - 32.0
+    sel = (row > 0.3) & (row < 0.9)
+    w_fit = np.sqrt(-(x[sel] ** 2) / np.log(row[sel]))
+    print("gaussian pulse %s: dE %.2e dB %.2e of the amplitude; snapshot peak in the focal plane %.3f of the amplitude, waist %.2f..%.2f cells (W0 = %.2f), behind the surface %.1e"
+          % ("exact" if exact else "production", worst, dB, peak_map.max() / amp, w_fit.min(), w_fit.max(), w0_cells, behind))
+    assert worst < 2e-5 and dB < 2e-5
+    assert abs(peak_map.max() / amp - 1.0) < 0.12 and np.abs(w_fit / w0_cells - 1.0).max() < 0.1 and behind < 0.02
+    s.close()
+    # (b) with plasma
+    kw = dict(periodic=(0, 0, 1), absorber_kind=1, absorber_cells=((4, 4), (8, 8), (0, 0)), absorber_strength=((1e-3, 1e-3), (1e-3, 1e-3), (0, 0)))
+    p = util.make_params((32, 64, 16), **kw)
+    p.laser = prm.gaussian_pulse_laser(p, a0=0.5, pulse_duration_si=3e-15, w0_si=0.7e-6, pulse_init=5.0, focus_position_si=(0.1e-6, 3.0e-6, 0.0),
+                                       polarisation="circular", pol_dir=(0.0, 0.0, 1.0), position=((6, -6), (10, -10), (3, -3)),
+                                       modes=(0.8, 0.2), mode_phases=(0.0, 0.4), tilt_deg=(5.0, 0.0))
+    amp = abs(p.laser["amplitude"])
+    o2, e, i = util.khi_ic(orc, p, ppc_dim=(2, 2, 1))
+    s = _sim(p, exact)
+    for name, sp in (("e", e), ("i", i)):
+        s.upload_particles(name, sp["pos"], sp["mom"], sp["w"], sp["cell"])
+    steps = 100
+    s.step(steps)
+    s.sync()
+    E, B, J = o2.field(), o2.field(), o2.field()
+    sps = [e, i]
+    for _ in range(steps):
+        o2.step_open(E, B, J, sps)
+    Eg, Bg = s.download_field(FE), s.download_field(FB)
+    dE = np.abs(o2.interior(Eg) - o2.interior(E)).max() / amp
+    dB = np.abs(o2.interior(Bg) - o2.interior(B)).max() / (amp / p.c)
+    print("gaussian pulse + plasma: dE %.2e dB %.2e of the amplitude, |E| max %.3f of the amplitude" % (dE, dB, np.abs(o2.interior(E)).max() / amp))
+    assert np.abs(o2.interior(E)).max() > 0.2 * amp
+    assert dE < 1e-4 and dB < 1e-4
+    ne = s.particle_count("e")
+    assert abs(ne - sps[0]["w"].shape[0]) <= (0 if exact else 2)
+    s.close()
+
+
+@pytest.mark.parametrize("exact", [True, False])
 def test_pml_vs_oracle(orc, exact):
     """PML absorber (fields/absorber/pml/Pml.kernel, hook FDTDBase.hpp:244-298) on all three axes with different
     thicknesses per face: fields and the coupled step (KHI plasma, absorbing particle boundary) against the oracle's

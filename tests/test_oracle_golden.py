@@ -473,6 +473,140 @@ def test_incident_plane_wave_known_answer(orc):
     assert (-(Ex * Bz)).sum() > 0.0
 
 
+def gaussian_beam_f64(p, las, X, Y, Z, step, shift):
+    """Textbook Gaussian beam in float64 with the complex beam parameter, u = 1/(1 + i zeta) exp(-rho^2 / (w0^2 (1 + i zeta)))
+    (Pampaloni & Enderlein 2004, eq. 18; the reference cites it in profiles/GaussianPulse.hpp:169-175), times the
+    GaussianPulseEnvelope, on total cell indices X, Y, Z at the fractional step `step`.  Written independently of the
+    oracle's real-valued restatement (w, R_inv, Gouy phase as separate terms)."""
+    c, dt, cell, gg = p.c, p.dt, p.cell_size, p.global_grid
+    focus = [las["focus_position"][d] + (gg[d] // 2) * cell[d] * las["focus_origin_center"][d] for d in range(3)]
+    y_surf = (las["position"][1][0] + 0.75) * cell[1]
+    w, lam, w0 = las["omega"], las["wave_length"], las["w0"]
+    k_num = 2.0 / cell[1] * np.arcsin(cell[1] * np.sin(0.5 * w * dt) / (c * dt))  # Yee dispersion along y
+    vph = w / k_num / c
+    zR = np.pi * w0 * w0 / lam
+    pol = np.array(las["pol"], dtype=np.float64)
+    ax2 = np.cross([0.0, 1.0, 0.0], pol)
+    sx, sy, sz = X * cell[0] - focus[0], Y * cell[1] - y_surf, Z * cell[2] - focus[2]
+    t = step * dt - (sy / vph + las["time_delay"])
+    on = t >= 0
+    t = t + las["time_shift"]
+    zf = sy - (focus[1] - y_surf)  # position relative to the focus along the propagation direction
+    zeta = zf / zR
+    p1, p2 = sx * pol[0] + sz * pol[2], sx * ax2[0] + sz * ax2[2]
+    if any(las["tilt"]):
+        # pulse-front tilt (GaussianPulse.hpp:244-254): transversal shift proportional to the local time in the pulse
+        tilt_shift = c * (t + (las["phase"] + shift) / w) / cell[1]
+        p1, p2 = p1 + np.tan(las["tilt"][0]) * tilt_shift, p2 + np.tan(las["tilt"][1]) * tilt_shift
+    rho2 = p1**2 + p2**2
+    from scipy.special import eval_laguerre
+
+    wz2 = w0 * w0 * (1.0 + zeta * zeta)
+    ph = w * (t + zf / c) - 2 * np.pi / lam * zf + las["phase"] + shift
+    total = 0.0
+    for m, (am, pm) in enumerate(zip(las["modes"], las["mode_phases"])):
+        # Gauss-Laguerre mode (radial index m, no azimuthal index): Gouy phase (2 m + 1) atan(zeta)
+        u = 1.0 / (1.0 + 1j * zeta) * ((1.0 - 1j * zeta) / (1.0 + 1j * zeta)) ** m * eval_laguerre(m, 2.0 * rho2 / wz2) * np.exp(-rho2 / (w0 * w0 * (1.0 + 1j * zeta)))
+        total = total + am * np.real(np.conj(u) * np.exp(1j * (ph + pm)))
+    r = 0.5 * rho2 * zf / (zR * zR + zf * zf)  # the curved wavefront delays the envelope by r / c
+    env = np.exp(-(((t - r / c) / (2.0 * las["pulse_duration"])) ** 2))
+    return on * las["amplitude"] * env * total / sum(las["modes"])
+
+
+def test_incident_gaussian_pulse_known_answer(orc):
+    """Oracle restatement of profiles/GaussianPulse.hpp (+ the bounded Huygens surface of Solver.hpp:209-258 and the
+    last-updated-cell rule of Solver.kernel:318-325,458-466): one E and one B source update on zero fields equals the
+    float64 complex-beam formula evaluated on the Yee positions of the incident components, inside POSITION only, with
+    one component dropped in the last cell along x and along z.  Linear (oblique polarisation direction, off-centre
+    focus) and circular polarisation, a superposition of three Laguerre modes, and a tilted pulse front."""
+    from picongpu_b200 import param as prm
+
+    nx, nz = 64, 48
+    cases = (("linear", (0.6, 0.0, 0.8), {}), ("circular", (1.0, 0.0, 0.0), {}),
+             ("linear", (1.0, 0.0, 0.0), dict(modes=(0.7, 0.2, 0.1), mode_phases=(0.0, 0.5, -0.3))),
+             ("circular", (0.0, 0.0, 1.0), dict(tilt_deg=(12.0, -7.0))))
+    for polarisation, pol, extra in cases:
+        p = prm.khi_params(grid=(nx, 32, nz), periodic=(0, 0, 1))
+        las = p.laser = prm.gaussian_pulse_laser(p, a0=0.5, pulse_duration_si=3e-15, w0_si=1.0e-6, pulse_init=6.0, polarisation=polarisation,
+                                                 focus_position_si=(0.3e-6, 4.0e-6, -0.2e-6), pol_dir=pol, position=((10, -10), (10, -10), (6, -6)), **extra)
+        o = orc.Oracle(p)
+        amp = abs(las["amplitude"])
+        Z, X = np.meshgrid(np.arange(float(nz)), np.arange(float(nx)), indexing="ij")
+        inside = np.zeros((nz, nx), dtype=bool)
+        inside[7 : nz - 6, 11 : nx - 10] = True
+        not_last_x, not_last_z = inside.copy(), inside.copy()
+        not_last_x[:, nx - 10 - 1] = False
+        not_last_z[nz - 6 - 1, :] = False
+
+        def einc(X, Y, Z, step):
+            b = gaussian_beam_f64(p, las, X, Y, Z, step, 0.0)
+            if las["polarisation"] == 0:
+                return [las["pol"][d] * b for d in range(3)]
+            a = gaussian_beam_f64(p, las, X, Y, Z, step, np.pi / 2)
+            p1 = np.array(las["pol"]) / np.sqrt(2.0)
+            p2 = np.cross([0.0, 1.0, 0.0], p1)
+            return [p1[d] * a + p2[d] * b for d in range(3)]
+
+        for step in (20.0, 50.5, 61.0):
+            # E (total field) on plane POSITION + 1: E_z += coef B_inc,x(x, y - .5, z + .5), E_x -= coef B_inc,z(x + .5, y - .5, z)
+            # with B_inc = cross(e_y, E_inc) / c = (E_inc,z, 0, -E_inc,x) / c
+            E = o.field()
+            o.incident_update(E, True, step)
+            Ei = o.interior(E)
+            plane = las["position"][1][0] + 1
+            assert not Ei[:, :, :plane].any() and not Ei[:, :, plane + 1 :].any() and not Ei[1].any()
+            coef = p.dt * p.c * p.c / p.cell_size[1]
+            want_z = coef * einc(X, plane - 0.5, Z + 0.5, step)[2] / p.c * not_last_z
+            want_x = coef * einc(X + 0.5, plane - 0.5, Z, step)[0] / p.c * not_last_x
+            scale = coef * amp / p.c
+            assert np.abs(Ei[0][:, plane, :] - want_x).max() < 3e-6 * scale and np.abs(Ei[2][:, plane, :] - want_z).max() < 3e-6 * scale
+            assert np.abs(Ei[[0, 2]][:, :, plane, :]).max() > 0.15 * scale
+            # B (scattered field) on plane POSITION: B_z += coef E_inc,x(x + .5, y + 1, z), B_x -= coef E_inc,z(x, y + 1, z + .5)
+            B = o.field()
+            o.incident_update(B, False, step)
+            Bi = o.interior(B)
+            plane = las["position"][1][0]
+            assert not Bi[:, :, :plane].any() and not Bi[:, :, plane + 1 :].any() and not Bi[1].any()
+            coef = -0.5 * p.dt / p.cell_size[1]
+            want_z = coef * einc(X + 0.5, plane + 1.0, Z, step)[0] * not_last_x
+            want_x = -coef * einc(X, plane + 1.0, Z + 0.5, step)[2] * not_last_z
+            scale = abs(coef) * amp
+            assert np.abs(Bi[2][:, plane, :] - want_z).max() < 3e-6 * scale and np.abs(Bi[0][:, plane, :] - want_x).max() < 3e-6 * scale
+
+
+def test_incident_gaussian_pulse_focuses_in_vacuum(orc):
+    """The same source over 130 steps of the oracle's vacuum Yee solver: the pulse reaches the requested peak amplitude at
+    the requested focus, with the requested waist there, and the region behind the Huygens surface stays at the level
+    set by the truncation of the beam at POSITION."""
+    from picongpu_b200 import param as prm
+
+    p = prm.khi_params(grid=(64, 64, 64), periodic=(0, 0, 0), absorber_kind=1, absorber_cells=((8, 8),) * 3, absorber_strength=((1e-3, 1e-3),) * 3)
+    las = p.laser = prm.gaussian_pulse_laser(p, a0=0.5, pulse_duration_si=3e-15, w0_si=1.0e-6, pulse_init=6.0, focus_position_si=(0.0, 4.0e-6, 0.0),
+                                             polarisation="linear", pol_dir=(1.0, 0.0, 0.0), position=((10, -10),) * 3)
+    o = orc.Oracle(p)
+    E, B, J = o.field(), o.field(), o.field()
+    amp = abs(las["amplitude"])
+    fy = int(round(las["focus_position"][1] / p.cell_size[1]))
+    peak_map, peak_y = np.zeros((64, 64)), np.zeros(64)
+    for _ in range(130):
+        o.step_open(E, B, J, [])
+        Ex = np.abs(o.interior(E)[0])
+        peak_map = np.maximum(peak_map, Ex[:, fy, :])
+        peak_y = np.maximum(peak_y, Ex[32, :, 32])
+    assert abs(peak_map.max() / amp - 1.0) < 0.04
+    assert np.unravel_index(peak_map.argmax(), peak_map.shape) in ((32, 31), (32, 32), (31, 32), (31, 31))
+    assert abs(int(peak_y[12:].argmax()) + 12 - fy) <= 6  # on-axis maximum within half a Rayleigh length (3.9 um = 42 cells) of the focus
+    # 1/e radius of the field amplitude in the focal plane, along x (E_x sits at x + .5) and along z
+    w0_cells = las["w0"] / p.cell_size[0]
+    row, col = peak_map[32, :] / peak_map.max(), peak_map[:, 32] / peak_map.max()
+    x, z = np.arange(64) + 0.5 - 32.0, np.arange(64) - 32.0
+    for prof, q in ((row, x), (col, z)):
+        sel = (prof > 0.3) & (prof < 0.9)
+        w_fit = np.sqrt(-(q[sel] ** 2) / np.log(prof[sel]))
+        assert np.abs(w_fit / w0_cells - 1.0).max() < 0.1
+    assert np.abs(o.interior(E)[:, :, :10, :]).max() / amp < 0.02
+
+
 def test_pml_known_answer(orc):
     """Oracle restatement of the PML (fields/absorber/pml/Pml.kernel): a vacuum pulse that leaves through 12 cells of PML
     with the reference's default parameters (param/fieldAbsorber.param:98-158) is absorbed to round-off, the same pulse

@@ -28,7 +28,7 @@ for w in $WHAT; do
     thermalB) [ "$N" != "1" ] && run thermalB --config thermal --scaling strong --grid 1024 1024 1024 --ppc 2 --steps 8 --warmup 3 --no-e2e ;;
     c3) run c3 --config lwfa_like --steps 10 --warmup 3 --no-e2e ;;
     c4) run c4 --config foil_like --steps 6 --warmup 3 --no-e2e ;;
-    lwfa) [ "$N" != "1" ] && run lwfa --config lwfa --ppc 8 --steps 600 --warmup 3 --no-e2e ;;
+    lwfa) [ "$N" != "1" ] && run lwfa --config lwfa --ppc 8 --steps 900 --warmup 3 --no-e2e ;;
     hot) run hot --config lwfa_hot --shape TSC --grid 256 256 256 --ppc 8 --steps 6 --warmup 3 --no-e2e ;;
     hotcic) run hotcic --config lwfa_hot --grid 256 256 256 --ppc 8 --steps 6 --warmup 3 --no-e2e ;;
   esac
