@@ -356,12 +356,12 @@ class Oracle:
         if self.laser is not None:
             self.L.orc_incident_update(C.byref(self.p), C.byref(self.laser), F, 1 if updated_is_e else 0, float(step))
 
-    def step_open(self, E, B, J, species):
+    def step_open(self, E, B, J, species, background_j=None):
         """One PIC step for a single domain with any mix of periodic and open (absorbing) axes, composed of the stage
         calls in the order of Simulation::runOneStep (Simulation.hpp:526-541).  Particles that leave through an open
         face are deleted before the current deposition (Particles.tpp:322-368: push, shift, applyBoundary).
         species dicts are updated (arrays are REPLACED when particles were absorbed).  Exchange passes are done
-        axis by axis over the periodic axes only (orc_halo_axis)."""
+        axis by axis over the periodic axes only (orc_halo_axis).  `background_j(J, step)`: optional FieldBackgroundJ."""
         periodic = [bool(self.p.wrap[d]) for d in range(3)]
         g = self.g
         J[...] = 0
@@ -386,6 +386,8 @@ class Oracle:
         copy_guards(B)
         self.incident_update(E, True, self.step_index + 0.5)
         self.update_e(E, B)
+        if background_j is not None:  # stage::CurrentBackground (Simulation.hpp:538): J += FieldBackgroundJ(cell, step)
+            background_j(J, self.step_index)
         for s in species:
             if s["w"].shape[0]:
                 self.deposit(s["massRatio"], s["chargeRatio"], J, s["pos"], s["mom"], s["w"], s["cell"])
