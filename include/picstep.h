@@ -70,7 +70,10 @@ extern "C"
     enum picstep_laser_profile
     {
         PICSTEP_LASER_PLANE_WAVE = 0, /* profiles::PlaneWave (profiles/PlaneWave.hpp) */
-        PICSTEP_LASER_GAUSSIAN_PULSE = 1 /* profiles::GaussianPulse / PulseFrontTilt (profiles/GaussianPulse.hpp) */
+        PICSTEP_LASER_GAUSSIAN_PULSE = 1, /* profiles::GaussianPulse / PulseFrontTilt (profiles/GaussianPulse.hpp) */
+        PICSTEP_LASER_WAVEPACKET = 2, /* profiles::Wavepacket (profiles/Wavepacket.hpp) */
+        PICSTEP_LASER_POLYNOM = 3, /* profiles::Polynom (profiles/Polynom.hpp) */
+        PICSTEP_LASER_EXP_RAMP_WITH_PREPULSE = 4 /* profiles::ExpRampWithPrepulse (profiles/ExpRampWithPrepulse.hpp) */
     };
     /* fields::absorber::Absorber::Kind (include/picongpu/fields/absorber/Absorber.hpp) */
     enum picstep_absorber
@@ -180,6 +183,12 @@ extern "C"
         int32_t laser_n_modes; /* laguerreModes.size(), 1..8 (0 = one mode of weight 1) */
         float laser_modes[8]; /* laguerreModes */
         float laser_mode_phases[8]; /* laguerrePhases */
+        /* separable profiles with a Gaussian transversal envelope (Wavepacket, Polynom, ExpRampWithPrepulse:
+         * BaseTransversalGaussianParamUnitless, profiles/BaseParam.hpp:186-203; Functors.hpp:481-533) */
+        float laser_w0_axis[2]; /* W0_AXIS_1, W0_AXIS_2 */
+        /* Wavepacket: [0] INIT_TIME.  ExpRampWithPrepulse: [0] time_start_init, [1] TIME_PREPULSE, [2] TIME_PEAKPULSE,
+         * [3..5] TIME_1..3, [6] PREPULSE_DURATION, [7] INT_RATIO_PREPULSE, [8..10] INT_RATIO_POINT_1..3 */
+        float laser_profile_params[16];
     } picstep_params;
 
     /* library / build information: returns e.g. "picstep sm_100a fmad=on" */

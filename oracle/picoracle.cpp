@@ -1699,7 +1699,7 @@ extern "C"
         float pol[3]; // POLARISATION_DIRECTION (unit, orthogonal to y)
         float time_delay; // TIME_DELAY
         int global_y_offset; // totalCellOffset[1] of this domain
-        int profile; // 0 PlaneWave, 1 GaussianPulse<Params, GaussianPulseEnvelope> (with tilt: PulseFrontTilt)
+        int profile; // 0 PlaneWave, 1 GaussianPulse<Params, GaussianPulseEnvelope> (with tilt: PulseFrontTilt), 2 Wavepacket, 3 Polynom, 4 ExpRampWithPrepulse
         int position[3][2]; // POSITION[axis][min, max] (max <= 0: counted from the upper boundary)
         int global_size[3]; // global domain cells
         int periodic[3];
@@ -1709,6 +1709,12 @@ extern "C"
         float tilt[2]; // TILT_AXIS_1, TILT_AXIS_2 in radian
         int n_modes; // laguerreModes.size()
         float modes[ORC_LASER_MAX_MODES], mode_phases[ORC_LASER_MAX_MODES];
+        // separable profiles with a Gaussian transversal envelope (BaseTransversalGaussianParamUnitless): profile 2
+        // Wavepacket, 3 Polynom, 4 ExpRampWithPrepulse
+        float w0_axis[2]; // W0_AXIS_1, W0_AXIS_2
+        // Wavepacket: [0] INIT_TIME.  ExpRampWithPrepulse: [0] time_start_init, [1] TIME_PREPULSE, [2] TIME_PEAKPULSE,
+        // [3..5] TIME_1..3, [6] PREPULSE_DURATION, [7] INT_RATIO_PREPULSE, [8..10] INT_RATIO_POINT_1..3
+        float profile_params[16];
     };
 
     static float orc_laser_phase_velocity(OrcParams const& P, OrcLaser const& L)
@@ -1792,6 +1798,108 @@ extern "C"
         return (std::sin(phase) + std::cos(phase) * integrationCorrectionFactor) * envelope;
     }
 
+    // WavepacketFunctorIncidentE::getLongitudinal (profiles/Wavepacket.hpp:122-151)
+    static float orc_wavepacket_longitudinal(OrcLaser const& L, float time, float phaseShift)
+    {
+        float const endUpramp = -0.5f * L.nofocus_constant, startDownramp = 0.5f * L.nofocus_constant;
+        float const mue = 0.5f * L.profile_params[0];
+        float const runTime = time - mue;
+        float const tau = L.pulse_duration * std::sqrt(2.0f);
+        float envelope = L.amplitude;
+        float correctionFactor = 0.0f;
+        if(runTime > startDownramp)
+        {
+            float const exponent = ((runTime - startDownramp) / L.pulse_duration / std::sqrt(2.0f));
+            envelope *= std::exp(-0.5f * exponent * exponent);
+            correctionFactor = (runTime - startDownramp) / (tau * tau * L.omega);
+        }
+        else if(runTime < endUpramp)
+        {
+            float const exponent = ((runTime - endUpramp) / L.pulse_duration / std::sqrt(2.0f));
+            envelope *= std::exp(-0.5f * exponent * exponent);
+            correctionFactor = (runTime - endUpramp) / (tau * tau * L.omega);
+        }
+        float const phase = L.omega * runTime + L.phase + phaseShift;
+        return (std::sin(phase) + correctionFactor * std::cos(phase)) * envelope;
+    }
+
+    // PolynomFunctorIncidentE::getLongitudinal / polynomial (profiles/Polynom.hpp:112-136)
+    static float orc_polynom_longitudinal(OrcLaser const& L, float time, float phaseShift)
+    {
+        float const riseTime = 0.5f * L.pulse_duration;
+        float const tau = time / riseTime;
+        float const phase = L.omega * (time - riseTime) + L.phase + phaseShift;
+        float result = 0.0f;
+        if(tau >= 0.0f && tau <= 1.0f)
+            result = tau * tau * tau * (10.0f - 15.0f * tau + 6.0f * tau * tau);
+        else if(tau > 1.0f && tau <= 2.0f)
+            result = (2.0f - tau) * (2.0f - tau) * (2.0f - tau) * (4.0f - 9.0f * tau + 6.0f * tau * tau);
+        float const amplitude = L.amplitude * result;
+        return std::sin(phase) * amplitude;
+    }
+
+    // ExpRampWithPrepulseLongitudinal::getEnvelope + ExpRampWithPrepulseFunctorIncidentE::getLongitudinal
+    // (profiles/ExpRampWithPrepulse.hpp:157-290)
+    static float orc_exp_ramp_longitudinal(OrcLaser const& L, float time, float phaseShift)
+    {
+        float const* q = L.profile_params;
+        float const time_start_init = q[0], TIME_PREPULSE = q[1], TIME_PEAKPULSE = q[2], TIME_1 = q[3], TIME_2 = q[4], TIME_3 = q[5];
+        float const PREPULSE_DURATION = q[6];
+        float const endUpramp = TIME_PEAKPULSE - 0.5f * L.nofocus_constant, startDownramp = TIME_PEAKPULSE + 0.5f * L.nofocus_constant;
+        auto gauss = [](float t, float pulseDuration) {
+            float const exponent = t / pulseDuration;
+            return std::exp(-0.25f * exponent * exponent);
+        };
+        auto extrapolateExpo = [](float t1, float a1, float t2, float a2, float t) {
+            float const log1 = (t2 - t) * std::log(a1);
+            float const log2 = (t - t1) * std::log(a2);
+            return std::exp((log1 + log2) / (t2 - t1));
+        };
+        float const runTime = time + time_start_init;
+        float const phase = L.omega * runTime + L.phase + phaseShift;
+        float const AMP_PREPULSE = std::sqrt(q[7]), AMP_1 = std::sqrt(q[8]), AMP_2 = std::sqrt(q[9]), AMP_3 = std::sqrt(q[10]);
+        float env = 0.0f;
+        bool const before_preupramp = runTime < time_start_init;
+        bool const before_start = runTime < TIME_1;
+        bool const before_peakpulse = runTime < endUpramp;
+        bool const during_first_exp = (TIME_1 < runTime) && (runTime < TIME_2);
+        bool const after_peakpulse = startDownramp <= runTime;
+        if(before_preupramp)
+            env = 0.0f;
+        else if(before_start)
+            env = AMP_1 * gauss(runTime - TIME_1, L.pulse_duration);
+        else if(before_peakpulse)
+        {
+            float const ramp_when_peakpulse = extrapolateExpo(TIME_2, AMP_2, TIME_3, AMP_3, endUpramp);
+            env += (1.0f - ramp_when_peakpulse) * gauss(runTime - endUpramp, L.pulse_duration);
+            env += AMP_PREPULSE * gauss(runTime - TIME_PREPULSE, PREPULSE_DURATION);
+            if(during_first_exp)
+                env += extrapolateExpo(TIME_1, AMP_1, TIME_2, AMP_2, runTime);
+            else
+                env += extrapolateExpo(TIME_2, AMP_2, TIME_3, AMP_3, runTime);
+        }
+        else if(!after_peakpulse)
+            env = 1.0f;
+        else
+            env = gauss(runTime - startDownramp, L.pulse_duration);
+        return std::cos(phase) * L.amplitude * env;
+    }
+
+    static float orc_separable_longitudinal(OrcLaser const& L, float time, float phaseShift)
+    {
+        switch(L.profile)
+        {
+        case 2:
+            return orc_wavepacket_longitudinal(L, time, phaseShift);
+        case 3:
+            return orc_polynom_longitudinal(L, time, phaseShift);
+        case 4:
+            return orc_exp_ramp_longitudinal(L, time, phaseShift);
+        default:
+            return orc_laser_longitudinal(L, time, phaseShift);
+        }
+    }
+
     // GaussianPulseFunctorIncidentE::simpleLaguerre (GaussianPulse.hpp:316-336)
     static float orc_simple_laguerre(unsigned n, float x)
     {
@@ -1870,11 +1978,23 @@ extern "C"
         if(time < 0.0f)
             return;
         float a, b; // value with phase shift pi/2 (circular only) and 0
-        if(L.profile == 0)
+        if(L.profile != 1)
         {
-            float const transversal = 1.0f;
-            a = L.polarisation ? orc_laser_longitudinal(L, time, 1.57079632679489661923f) * transversal : 0.0f;
-            b = orc_laser_longitudinal(L, time, 0.0f) * transversal;
+            // BaseSeparableFunctorE::operator() (Functors.hpp:452-470); PlaneWave: transversal 1,
+            // BaseSeparableTransversalGaussianFunctorE::getTransversal (:525-532) otherwise
+            float transversal = 1.0f;
+            if(L.profile != 0)
+            {
+                float const internalPosition[3] = {0.0f, orc_dot3(shiftFromOrigin, F.axis1), orc_dot3(shiftFromOrigin, F.axis2)};
+                float const w0[3] = {1.0f, L.w0_axis[0], L.w0_axis[1]};
+                float const r[3] = {internalPosition[0] / w0[0], internalPosition[1] / w0[1], internalPosition[2] / w0[2]};
+                float r2 = r[0] * r[0];
+                r2 += r[1] * r[1];
+                r2 += r[2] * r[2];
+                transversal = std::exp(-r2);
+            }
+            a = L.polarisation ? orc_separable_longitudinal(L, time, 1.57079632679489661923f) * transversal : 0.0f;
+            b = orc_separable_longitudinal(L, time, 0.0f) * transversal;
         }
         else
         {

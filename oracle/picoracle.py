@@ -74,6 +74,8 @@ class OrcLaser(C.Structure):
         ("n_modes", C.c_int),
         ("modes", C.c_float * LASER_MAX_MODES),
         ("mode_phases", C.c_float * LASER_MAX_MODES),
+        ("w0_axis", C.c_float * 2),
+        ("profile_params", C.c_float * 16),
     ]
 
 
@@ -124,6 +126,9 @@ def make_laser(cfg):
     L.n_modes = len(modes)
     for m in range(len(modes)):
         L.modes[m], L.mode_phases[m] = float(modes[m]), float(phases[m])
+    L.w0_axis[0], L.w0_axis[1] = (float(v) for v in las.get("w0_axis", (0.0, 0.0)))
+    for k, v in enumerate(las.get("profile_params", ())):
+        L.profile_params[k] = float(v)
     return L
 
 

@@ -99,7 +99,7 @@ namespace picstep
     struct LaserDev
     {
         int polarisation, plane; // plane: padded-grid y index of the updated plane of this call
-        int profile; // 0 PlaneWave, 1 GaussianPulse
+        int profile; // picstep_laser_profile
         float planeTotal; // its total (global) cell index along y
         float amplitude, omega, pulseDuration, nofocusConstant, rampInit, phase, timeDelay;
         float pol[3], axis2[3]; // internal axes 1 and 2 (axis 0 = propagation = +y)
@@ -114,6 +114,8 @@ namespace picstep
         float w0, waveLength, rayleighLength, timeShift, tanTilt[2];
         int tilted, nModes;
         float modes[LASER_MAX_MODES], modePhases[LASER_MAX_MODES];
+        // Wavepacket / Polynom / ExpRampWithPrepulse (picstep.h: laser_w0_axis, laser_profile_params)
+        float w0Axis[2], prm[16];
     };
 
     // convolutional PML (fields.cu: pmlUpdate*Kernel): local thickness per [axis][negative, positive], graded parameters,

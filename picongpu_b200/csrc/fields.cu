@@ -472,6 +472,112 @@ namespace picstep
         return (sinf(phase) + cosf(phase) * integrationCorrectionFactor) * envelope;
     }
 
+    // WavepacketFunctorIncidentE::getLongitudinal (profiles/Wavepacket.hpp:122-151)
+    __device__ __forceinline__ float wavepacketLongitudinal(LaserDev const& L, float time, float phaseShift)
+    {
+        float const endUpramp = -0.5f * L.nofocusConstant, startDownramp = 0.5f * L.nofocusConstant;
+        float const mue = 0.5f * L.prm[0];
+        float const runTime = time - mue;
+        float const tau = L.pulseDuration * sqrtf(2.0f);
+        float envelope = L.amplitude;
+        float correctionFactor = 0.0f;
+        if(runTime > startDownramp)
+        {
+            float const exponent = ((runTime - startDownramp) / L.pulseDuration / sqrtf(2.0f));
+            envelope *= expf(-0.5f * exponent * exponent);
+            correctionFactor = (runTime - startDownramp) / (tau * tau * L.omega);
+        }
+        else if(runTime < endUpramp)
+        {
+            float const exponent = ((runTime - endUpramp) / L.pulseDuration / sqrtf(2.0f));
+            envelope *= expf(-0.5f * exponent * exponent);
+            correctionFactor = (runTime - endUpramp) / (tau * tau * L.omega);
+        }
+        float const phase = L.omega * runTime + L.phase + phaseShift;
+        return (sinf(phase) + correctionFactor * cosf(phase)) * envelope;
+    }
+
+    // PolynomFunctorIncidentE::getLongitudinal / polynomial (profiles/Polynom.hpp:112-136)
+    __device__ __forceinline__ float polynomLongitudinal(LaserDev const& L, float time, float phaseShift)
+    {
+        float const riseTime = 0.5f * L.pulseDuration;
+        float const tau = time / riseTime;
+        float const phase = L.omega * (time - riseTime) + L.phase + phaseShift;
+        float result = 0.0f;
+        if(tau >= 0.0f && tau <= 1.0f)
+            result = tau * tau * tau * (10.0f - 15.0f * tau + 6.0f * tau * tau);
+        else if(tau > 1.0f && tau <= 2.0f)
+            result = (2.0f - tau) * (2.0f - tau) * (2.0f - tau) * (4.0f - 9.0f * tau + 6.0f * tau * tau);
+        float const amplitude = L.amplitude * result;
+        return sinf(phase) * amplitude;
+    }
+
+    // ExpRampWithPrepulseLongitudinal::getEnvelope + ExpRampWithPrepulseFunctorIncidentE::getLongitudinal
+    // (profiles/ExpRampWithPrepulse.hpp:157-290)
+    __device__ __forceinline__ float expRampGauss(float t, float pulseDuration)
+    {
+        float const exponent = t / pulseDuration;
+        return expf(-0.25f * exponent * exponent);
+    }
+
+    __device__ __forceinline__ float expRampExtrapolate(float t1, float a1, float t2, float a2, float t)
+    {
+        float const log1 = (t2 - t) * logf(a1);
+        float const log2 = (t - t1) * logf(a2);
+        return expf((log1 + log2) / (t2 - t1));
+    }
+
+    __device__ __forceinline__ float expRampLongitudinal(LaserDev const& L, float time, float phaseShift)
+    {
+        float const* q = L.prm;
+        float const time_start_init = q[0], TIME_PREPULSE = q[1], TIME_PEAKPULSE = q[2], TIME_1 = q[3], TIME_2 = q[4], TIME_3 = q[5];
+        float const PREPULSE_DURATION = q[6];
+        float const endUpramp = TIME_PEAKPULSE - 0.5f * L.nofocusConstant, startDownramp = TIME_PEAKPULSE + 0.5f * L.nofocusConstant;
+        float const runTime = time + time_start_init;
+        float const phase = L.omega * runTime + L.phase + phaseShift;
+        float const AMP_PREPULSE = sqrtf(q[7]), AMP_1 = sqrtf(q[8]), AMP_2 = sqrtf(q[9]), AMP_3 = sqrtf(q[10]);
+        float env = 0.0f;
+        bool const before_preupramp = runTime < time_start_init;
+        bool const before_start = runTime < TIME_1;
+        bool const before_peakpulse = runTime < endUpramp;
+        bool const during_first_exp = (TIME_1 < runTime) && (runTime < TIME_2);
+        bool const after_peakpulse = startDownramp <= runTime;
+        if(before_preupramp)
+            env = 0.0f;
+        else if(before_start)
+            env = AMP_1 * expRampGauss(runTime - TIME_1, L.pulseDuration);
+        else if(before_peakpulse)
+        {
+            float const ramp_when_peakpulse = expRampExtrapolate(TIME_2, AMP_2, TIME_3, AMP_3, endUpramp);
+            env += (1.0f - ramp_when_peakpulse) * expRampGauss(runTime - endUpramp, L.pulseDuration);
+            env += AMP_PREPULSE * expRampGauss(runTime - TIME_PREPULSE, PREPULSE_DURATION);
+            if(during_first_exp)
+                env += expRampExtrapolate(TIME_1, AMP_1, TIME_2, AMP_2, runTime);
+            else
+                env += expRampExtrapolate(TIME_2, AMP_2, TIME_3, AMP_3, runTime);
+        }
+        else if(!after_peakpulse)
+            env = 1.0f;
+        else
+            env = expRampGauss(runTime - startDownramp, L.pulseDuration);
+        return cosf(phase) * L.amplitude * env;
+    }
+
+    __device__ __forceinline__ float separableLongitudinal(LaserDev const& L, float time, float phaseShift)
+    {
+        switch(L.profile)
+        {
+        case 2:
+            return wavepacketLongitudinal(L, time, phaseShift);
+        case 3:
+            return polynomLongitudinal(L, time, phaseShift);
+        case 4:
+            return expRampLongitudinal(L, time, phaseShift);
+        default:
+            return laserLongitudinal(L, time, phaseShift);
+        }
+    }
+
     __device__ __forceinline__ float dot3(float const a[3], float const b[3])
     {
         float tmp = a[0] * b[0];
@@ -552,11 +658,22 @@ namespace picstep
         if(time < 0.0f)
             return;
         float a = 0.0f, b;
-        if(L.profile == 0)
+        if(L.profile != 1)
         {
+            // BaseSeparableFunctorE::operator(); transversal: 1 (PlaneWave) or the Gaussian of
+            // BaseSeparableTransversalGaussianFunctorE::getTransversal (Functors.hpp:525-532)
+            float transversal = 1.0f;
+            if(L.profile != 0)
+            {
+                float const r[3] = {0.0f / 1.0f, dot3(shiftFromOrigin, L.pol) / L.w0Axis[0], dot3(shiftFromOrigin, L.axis2) / L.w0Axis[1]};
+                float r2 = r[0] * r[0];
+                r2 += r[1] * r[1];
+                r2 += r[2] * r[2];
+                transversal = expf(-r2);
+            }
             if(L.polarisation)
-                a = laserLongitudinal(L, time, 1.57079632679489661923f) * 1.0f;
-            b = laserLongitudinal(L, time, 0.0f) * 1.0f;
+                a = separableLongitudinal(L, time, 1.57079632679489661923f) * transversal;
+            b = separableLongitudinal(L, time, 0.0f) * transversal;
         }
         else
         {

@@ -773,8 +773,18 @@ extern "C"
         {
             if(p->field_solver != PICSTEP_SOLVER_YEE || p->periodic[1])
                 return fail(nullptr, PICSTEP_ERR_INVALID, "the incident field source is built for the Yee solver and a non-periodic y axis");
-            if(p->laser_profile < 0 || p->laser_profile > PICSTEP_LASER_GAUSSIAN_PULSE)
+            if(p->laser_profile < 0 || p->laser_profile > PICSTEP_LASER_EXP_RAMP_WITH_PREPULSE)
                 return fail(nullptr, PICSTEP_ERR_INVALID, "unknown incident field profile");
+            if(p->laser_profile >= PICSTEP_LASER_WAVEPACKET && (!(p->laser_w0_axis[0] > 0.0f) || !(p->laser_w0_axis[1] > 0.0f)))
+                return fail(nullptr, PICSTEP_ERR_INVALID, "bad incident field parameters (W0_AXIS_1, W0_AXIS_2)");
+            if(p->laser_profile == PICSTEP_LASER_EXP_RAMP_WITH_PREPULSE)
+            {
+                // static_assert of ExpRampWithPrepulsesLongitudinalUnitless (ExpRampWithPrepulse.hpp:84-88)
+                float const* q = p->laser_profile_params;
+                float const endUpramp = q[2] - 0.5f * p->laser_nofocus_constant;
+                if(!((q[3] < q[4]) && (q[4] < q[5]) && (q[5] < endUpramp)))
+                    return fail(nullptr, PICSTEP_ERR_INVALID, "The times in the parameters TIME_POINT_1/2/3 and the beginning of the plateau should be in ascending order");
+            }
             bool anyPos = false;
             for(int d = 0; d < 3; ++d)
                 anyPos = anyPos || p->laser_position[d][0] || p->laser_position[d][1];
@@ -1542,6 +1552,10 @@ extern "C"
             L.axis2[1] = direction[2] * L.pol[0] - direction[0] * L.pol[2];
             L.axis2[2] = direction[0] * L.pol[1] - direction[1] * L.pol[0];
         }
+        L.w0Axis[0] = p.laser_w0_axis[0];
+        L.w0Axis[1] = p.laser_w0_axis[1];
+        for(int k = 0; k < 16; ++k)
+            L.prm[k] = p.laser_profile_params[k];
         if(p.laser_profile == PICSTEP_LASER_GAUSSIAN_PULSE)
         {
             // GaussianPulseUnitless (profiles/GaussianPulse.hpp:93-110)

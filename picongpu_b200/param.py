@@ -221,6 +221,64 @@ def gaussian_pulse_laser(p, a0=8.0, wavelength_si=0.8e-6, pulse_duration_si=5.0e
     )
 
 
+def _separable_base(p, profile, a0, amplitude_si, wavelength_si, pulse_duration_si, w0_axis_si, focus_position_si, focus_origin_center, phase,
+                    polarisation, pol_dir, position, time_delay_si, nofocus_constant_si):
+    """BaseTransversalGaussianParamUnitless (profiles/BaseParam.hpp:43-203) of the separable profiles"""
+    if amplitude_si is None:
+        amplitude_si = a0 * (-2.0 * math.pi / wavelength_si * ELECTRON_MASS_SI * SPEED_OF_LIGHT_SI**2 / ELECTRON_CHARGE_SI)
+    wave_length = _f32(wavelength_si / p.unit_length)
+    f = _f32(np.float32(p.c) / np.float32(wave_length))
+    return dict(
+        profile=profile, polarisation=0 if polarisation == "linear" else 1, offset_ymin=int(position[1][0]),
+        position=tuple((int(a), int(b)) for a, b in position), amplitude=_f32(amplitude_si / p.unit_efield),
+        omega=_f32(np.float32(2.0 * math.pi) * np.float32(f)), wave_length=wave_length, pulse_duration=_f32(pulse_duration_si / p.unit_time),
+        w0_axis=tuple(_f32(w / p.unit_length) for w in w0_axis_si), focus_position=tuple(_f32(v / p.unit_length) for v in focus_position_si),
+        focus_origin_center=tuple(int(v) for v in focus_origin_center), nofocus_constant=_f32(nofocus_constant_si / p.unit_time), ramp_init=0.0,
+        phase=_f32(phase), pol=tuple(_f32(v) for v in pol_dir), time_delay=_f32(time_delay_si / p.unit_time), profile_params=())
+
+
+_SEPARABLE_DEFAULTS = dict(a0=1.0, amplitude_si=None, wavelength_si=0.8e-6, pulse_duration_si=5.0e-15, w0_axis_si=(4.246e-6, 4.246e-6),
+                           focus_position_si=(0.0, 0.0, 0.0), focus_origin_center=(1, 0, 1), phase=0.0, polarisation="linear", pol_dir=(1.0, 0.0, 0.0),
+                           position=((16, -16), (16, -16), (16, -16)), time_delay_si=0.0, nofocus_constant_si=0.0)
+
+
+def wavepacket_laser(p, pulse_init=20.0, **kw):
+    """`profiles::Wavepacket<>` on YMin (profiles/Wavepacket.def:36-72, Wavepacket.hpp:52-73): Gaussian in time with an
+    optional plateau and Gaussian transversally.  INIT_TIME = PULSE_INIT (float_64) * PULSE_DURATION + LASER_NOFOCUS_CONSTANT."""
+    a = dict(_SEPARABLE_DEFAULTS, nofocus_constant_si=7.0 * 5.0e-15)
+    a.update(kw)
+    las = _separable_base(p, 2, **a)
+    las["profile_params"] = (_f32(float(pulse_init) * las["pulse_duration"] + las["nofocus_constant"]),)
+    return las
+
+
+def polynom_laser(p, **kw):
+    """`profiles::Polynom<>` on YMin (profiles/Polynom.def:36-52, Polynom.hpp:112-136): the amplitude rises for half of
+    PULSE_DURATION with a polynomial of fifth order and falls symmetrically."""
+    a = dict(_SEPARABLE_DEFAULTS)
+    a.update(kw)
+    return _separable_base(p, 3, **a)
+
+
+def exp_ramp_with_prepulse_laser(p, int_ratio_prepulse=0.0, int_ratio_points=(1.0e-8, 1.0e-4, 1.0e-4), time_prepulse_si=-950.0e-15,
+                                 time_peakpulse_si=0.0, time_points_si=(-1000.0e-15, -300.0e-15, -100.0e-15), prepulse_duration_si=None,
+                                 ramp_init=16.0, **kw):
+    """`profiles::ExpRampWithPrepulse<>` on YMin (profiles/ExpRampWithPrepulse.def:36-110, ExpRampWithPrepulse.hpp:52-124):
+    Gaussian main pulse with plateau, preceded by two exponential ramps through three (time, intensity ratio) points and
+    an optional Gaussian prepulse.  time_start_init = TIME_POINT_1 - 0.5 * RAMP_INIT (float_64) * PULSE_DURATION."""
+    a = dict(_SEPARABLE_DEFAULTS, amplitude_si=1.0e6 if "a0" not in kw else None)
+    a.update(kw)
+    las = _separable_base(p, 4, **a)
+    t = [_f32(v / p.unit_time) for v in time_points_si]
+    pre = _f32((prepulse_duration_si if prepulse_duration_si is not None else a["pulse_duration_si"]) / p.unit_time)
+    end_upramp = float(np.float32(_f32(time_peakpulse_si / p.unit_time)) - np.float32(0.5) * np.float32(las["nofocus_constant"]))
+    if not (t[0] < t[1] < t[2] < end_upramp):
+        raise ValueError("TIME_POINT_1/2/3 and the beginning of the plateau should be in ascending order")
+    las["profile_params"] = (_f32(t[0] - 0.5 * float(ramp_init) * las["pulse_duration"]), _f32(time_prepulse_si / p.unit_time),
+                             _f32(time_peakpulse_si / p.unit_time), t[0], t[1], t[2], pre, _f32(int_ratio_prepulse)) + tuple(_f32(v) for v in int_ratio_points)
+    return las
+
+
 def pml_params(p, sigma_kappa_grading_order=4.0, sigma_opt_multiplier=1.0, kappa_max=(1.0, 1.0, 1.0), alpha_grading_order=1.0,
                alpha_max_si=(0.2, 0.2, 0.2)):
     """include/picongpu/param/fieldAbsorber.param:98-158 (pml:: defaults) converted as in

@@ -92,6 +92,8 @@ class Params(C.Structure):
         ("laser_n_modes", C.c_int32),
         ("laser_modes", C.c_float * 8),
         ("laser_mode_phases", C.c_float * 8),
+        ("laser_w0_axis", C.c_float * 2),
+        ("laser_profile_params", C.c_float * 16),
     ]
 
 
@@ -209,6 +211,9 @@ def to_c_params(p, device=0, flags=0):
         cp.laser_n_modes = len(modes)
         for m in range(len(modes)):
             cp.laser_modes[m], cp.laser_mode_phases[m] = modes[m], phases[m]
+        cp.laser_w0_axis[0], cp.laser_w0_axis[1] = las.get("w0_axis", (0.0, 0.0))
+        for k, v in enumerate(las.get("profile_params", ())):
+            cp.laser_profile_params[k] = v
     for d in range(3):
         for sd in range(2):
             cp.absorber_cells[d][sd] = int(getattr(p, "absorber_cells", ((0, 0),) * 3)[d][sd])

@@ -942,6 +942,42 @@ def test_incident_gaussian_pulse_vs_oracle(orc, exact):
 
 
 @pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("profile", ["wavepacket", "polynom", "exp_ramp"])
+def test_incident_separable_profiles_vs_oracle(orc, exact, profile):
+    """Wavepacket, Polynom and ExpRampWithPrepulse profiles (profiles/{Wavepacket,Polynom,ExpRampWithPrepulse}.hpp,
+    Gaussian transversal envelope of Functors.hpp:481-533) through YMin into vacuum, --periodic 0 0 1: E and B against the
+    oracle after every block of 20 steps, long enough for every branch of the longitudinal functions."""
+    fs = 1.0e-15
+    common = dict(pulse_duration_si=2.5e-15, w0_axis_si=(0.9e-6, 1.4e-6), focus_position_si=(0.2e-6, 0.0, -0.1e-6), position=((6, -6), (10, -10), (3, -3)))
+    kw = dict(periodic=(0, 0, 1), absorber_kind=1, absorber_cells=((4, 4), (8, 8), (0, 0)), absorber_strength=((1e-3, 1e-3), (1e-3, 1e-3), (0, 0)))
+    p = util.make_params((48, 64, 16), **kw)
+    if profile == "wavepacket":
+        p.laser, blocks = prm.wavepacket_laser(p, a0=0.5, pulse_init=6.0, nofocus_constant_si=4 * fs, polarisation="circular", **common), 6
+    elif profile == "polynom":
+        p.laser, blocks = prm.polynom_laser(p, a0=0.5, polarisation="linear", pol_dir=(0.6, 0.0, 0.8), **common), 3
+    else:
+        p.laser, blocks = prm.exp_ramp_with_prepulse_laser(p, a0=0.5, int_ratio_prepulse=0.01, int_ratio_points=(1e-4, 1e-2, 4e-2), time_prepulse_si=-14 * fs,
+                                                           time_points_si=(-20 * fs, -10 * fs, -5 * fs), prepulse_duration_si=1.0 * fs, ramp_init=6.0,
+                                                           nofocus_constant_si=3 * fs, polarisation="linear", **common), 10
+    amp = abs(p.laser["amplitude"])
+    s = _sim(p, exact)
+    o = orc.Oracle(p)
+    E, B, J = o.field(), o.field(), o.field()
+    worst, peak = 0.0, 0.0
+    for _ in range(blocks):
+        s.step(20)
+        s.sync()
+        Eg, Bg = s.download_field(FE), s.download_field(FB)
+        for _ in range(20):
+            o.step_open(E, B, J, [])
+        worst = max(worst, float(np.abs(o.interior(Eg) - o.interior(E)).max()) / amp, float(np.abs(o.interior(Bg) - o.interior(B)).max()) / (amp / p.c))
+        peak = max(peak, float(np.abs(o.interior(Eg)).max()) / amp)
+    print("%s %s: max deviation %.2e of the amplitude, peak |E| %.3f of the amplitude" % (profile, "exact" if exact else "production", worst, peak))
+    assert peak > 0.4 and worst < 2e-5
+    s.close()
+
+
+@pytest.mark.parametrize("exact", [True, False])
 def test_pml_vs_oracle(orc, exact):
     """PML absorber (fields/absorber/pml/Pml.kernel, hook FDTDBase.hpp:244-298) on all three axes with different
     thicknesses per face: fields and the coupled step (KHI plasma, absorbing particle boundary) against the oracle's

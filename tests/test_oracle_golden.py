@@ -607,6 +607,106 @@ def test_incident_gaussian_pulse_focuses_in_vacuum(orc):
     assert np.abs(o.interior(E)[:, :, :10, :]).max() / amp < 0.02
 
 
+def _separable_f64(p, las, X, Y, Z, step, shift):
+    """float64 restatement of the separable profiles (longitudinal(t) x Gaussian transversal), written from the
+    profiles' documentation rather than from the oracle: Wavepacket (Gaussian flanks around a plateau, carrier sin),
+    Polynom (fifth-order smooth rise and fall), ExpRampWithPrepulse (two exponential ramps through three
+    (time, intensity) points, prepulse, Gaussian main pulse, carrier cos)"""
+    c, dt, cell, gg = p.c, p.dt, p.cell_size, p.global_grid
+    focus = [las["focus_position"][d] + (gg[d] // 2) * cell[d] * las["focus_origin_center"][d] for d in range(3)]
+    y_surf = (las["position"][1][0] + 0.75) * cell[1]
+    w, T, A, phi = las["omega"], las["pulse_duration"], las["amplitude"], las["phase"] + shift
+    k_num = 2.0 / cell[1] * np.arcsin(cell[1] * np.sin(0.5 * w * dt) / (c * dt))
+    vph = w / k_num / c
+    pol = np.array(las["pol"], dtype=np.float64)
+    ax2 = np.cross([0.0, 1.0, 0.0], pol)
+    sx, sy, sz = X * cell[0] - focus[0], Y * cell[1] - y_surf, Z * cell[2] - focus[2]
+    t = step * dt - (sy / vph + las["time_delay"])
+    on = t >= 0
+    trans = np.exp(-(((sx * pol[0] + sz * pol[2]) / las["w0_axis"][0]) ** 2) - (((sx * ax2[0] + sz * ax2[2]) / las["w0_axis"][1]) ** 2))
+    plateau = las["nofocus_constant"]
+    if las["profile"] == 2:
+        rt = t - 0.5 * las["profile_params"][0]
+        d = np.where(rt > 0.5 * plateau, rt - 0.5 * plateau, np.where(rt < -0.5 * plateau, rt + 0.5 * plateau, 0.0))  # distance to the plateau
+        env = A * np.exp(-(d**2) / (4.0 * T * T))
+        lon = env * (np.sin(w * rt + phi) + d / (2.0 * T * T * w) * np.cos(w * rt + phi))
+    elif las["profile"] == 3:
+        tau = t / (0.5 * T)
+        rise = tau**3 * (10.0 - 15.0 * tau + 6.0 * tau**2)
+        u = 2.0 - tau
+        fall = u**3 * (4.0 - 9.0 * tau + 6.0 * tau**2)
+        poly = np.where((tau >= 0) & (tau <= 1), rise, np.where((tau > 1) & (tau <= 2), fall, 0.0))
+        lon = A * poly * np.sin(w * (t - 0.5 * T) + phi)
+    else:
+        q = las["profile_params"]
+        t0, t_pre, t_peak, t1, t2, t3, T_pre = q[0:7]
+        a_pre, a1, a2, a3 = np.sqrt(q[7:11])
+        rt = t + t0
+        up, down = t_peak - 0.5 * plateau, t_peak + 0.5 * plateau
+        gauss = lambda x, TT: np.exp(-0.25 * (x / TT) ** 2)  # noqa: E731
+        expo = lambda ta, aa, tb, ab, x: np.exp(((tb - x) * np.log(aa) + (x - ta) * np.log(ab)) / (tb - ta))  # noqa: E731
+        ramp = (1.0 - expo(t2, a2, t3, a3, up)) * gauss(rt - up, T) + a_pre * gauss(rt - t_pre, T_pre) + np.where(
+            (t1 < rt) & (rt < t2), expo(t1, a1, t2, a2, rt), expo(t2, a2, t3, a3, rt))
+        env = np.where(rt < t0, 0.0, np.where(rt < t1, a1 * gauss(rt - t1, T), np.where(rt < up, ramp, np.where(rt < down, 1.0, gauss(rt - down, T)))))
+        lon = A * env * np.cos(w * rt + phi)
+    return on * lon * trans
+
+
+def test_incident_separable_profiles_known_answer(orc):
+    """Wavepacket, Polynom and ExpRampWithPrepulse (profiles/{Wavepacket,Polynom,ExpRampWithPrepulse}.hpp with the Gaussian
+    transversal envelope of Functors.hpp:481-533): one source update of E on zero fields against the float64 formulas,
+    at times that hit every branch of the longitudinal functions; elliptic focus (W0_AXIS_1 != W0_AXIS_2), circular and
+    oblique linear polarisation."""
+    from picongpu_b200 import param as prm
+
+    nx, nz = 48, 40
+    common = dict(pulse_duration_si=2.5e-15, w0_axis_si=(0.9e-6, 1.4e-6), focus_position_si=(0.2e-6, 0.0, -0.1e-6), position=((6, -6), (10, -10), (5, -5)))
+    p0 = prm.khi_params(grid=(nx, 32, nz), periodic=(0, 0, 1))
+    fs = 1.0e-15
+    cases = [
+        (prm.wavepacket_laser(p0, a0=0.5, pulse_init=6.0, nofocus_constant_si=4 * fs, polarisation="circular", **common), (5.0, 30.5, 52.0, 75.0, 95.0)),
+        (prm.polynom_laser(p0, a0=0.5, polarisation="linear", pol_dir=(0.6, 0.0, 0.8), **common), (1.0, 5.5, 9.0, 13.0, 20.0)),
+        (prm.exp_ramp_with_prepulse_laser(p0, a0=0.5, int_ratio_prepulse=0.01, int_ratio_points=(1e-4, 1e-2, 4e-2), time_prepulse_si=-14 * fs,
+                                          time_points_si=(-20 * fs, -10 * fs, -5 * fs), prepulse_duration_si=1.0 * fs, ramp_init=6.0,
+                                          nofocus_constant_si=3 * fs, polarisation="linear", **common), (3.0, 30.0, 60.0, 95.0, 110.0, 125.0, 140.0, 160.0, 175.0, 200.0)),
+    ]
+    for las, steps in cases:
+        p = prm.khi_params(grid=(nx, 32, nz), periodic=(0, 0, 1))
+        p.laser = las
+        o = orc.Oracle(p)
+        amp = abs(las["amplitude"])
+        Z, X = np.meshgrid(np.arange(float(nz)), np.arange(float(nx)), indexing="ij")
+        inside = np.zeros((nz, nx), dtype=bool)
+        inside[6 : nz - 5, 7 : nx - 6] = True
+        not_last_x, not_last_z = inside.copy(), inside.copy()
+        not_last_x[:, nx - 6 - 1] = False
+        not_last_z[nz - 5 - 1, :] = False
+
+        def einc(X, Y, Z, step):
+            b = _separable_f64(p, las, X, Y, Z, step, 0.0)
+            if las["polarisation"] == 0:
+                return [las["pol"][d] * b for d in range(3)]
+            a = _separable_f64(p, las, X, Y, Z, step, np.pi / 2)
+            p1 = np.array(las["pol"]) / np.sqrt(2.0)
+            p2 = np.cross([0.0, 1.0, 0.0], p1)
+            return [p1[d] * a + p2[d] * b for d in range(3)]
+
+        seen = 0.0
+        for step in steps:
+            E = o.field()
+            o.incident_update(E, True, step)
+            Ei = o.interior(E)
+            plane = las["position"][1][0] + 1
+            coef = p.dt * p.c * p.c / p.cell_size[1]
+            want_z = coef * einc(X, plane - 0.5, Z + 0.5, step)[2] / p.c * not_last_z
+            want_x = coef * einc(X + 0.5, plane - 0.5, Z, step)[0] / p.c * not_last_x
+            scale = coef * amp / p.c
+            err = max(np.abs(Ei[0][:, plane, :] - want_x).max(), np.abs(Ei[2][:, plane, :] - want_z).max()) / scale
+            assert err < 5e-6, (las["profile"], step, err)
+            seen = max(seen, np.abs(Ei[[0, 2]][:, :, plane, :]).max() / scale)
+        assert seen > 0.5, (las["profile"], seen)  # the sampled times include the main pulse
+
+
 def test_pml_known_answer(orc):
     """Oracle restatement of the PML (fields/absorber/pml/Pml.kernel): a vacuum pulse that leaves through 12 cells of PML
     with the reference's default parameters (param/fieldAbsorber.param:98-158) is absorbed to round-off, the same pulse
