@@ -13,10 +13,18 @@
 //     tree to generate tests/golden/current_deposition.npz)
 //   * share/picongpu/tests/Pusher/README.rst        (gyro radius / phase drift bounds)
 //   * share/picongpu/tests/PusherScaling/README.rst (phase lag ~ dt^2: exponent 2 +- 0.1, std <= 0.05)
+//   * share/picongpu/tests/FieldAbsorber (the PML acceptance test: radiating wire, small box against a reflection-free
+//     box, lib/python/test/FieldAbsorber/validate.py bound 1e-4; tests/test_field_absorber_acceptance.py)
 // Restated without a golden vector in the reference (checked by their own known answers in
 // tests/test_oracle_golden.py and by construction against the cited source): the Higuera-Cary pusher
 // (gyration test of share/picongpu/tests/Pusher applies), the Binomial current interpolation (delta
 // response = 1-2-1 tensor weights / 64), the exponential absorber (attenuation profile), the open-boundary step.
+// PARITY UNPINNED against reference outputs: the incident-field source (Huygens surface, PlaneWave / GaussianPulse /
+// Wavepacket / Polynom / ExpRampWithPrepulse profiles) -- the reference tests it by compiling only
+// (share/picongpu/tests/compileLaser), there is no fixture to pin against.  What the tests hold instead: independent
+// float64 formulas on the Yee positions (textbook complex Gaussian beam with scipy's Laguerre polynomials, the
+// documented envelopes), and the defining properties in vacuum (requested amplitude, focus position and waist, nothing
+// behind the total-field / scattered-field surface beyond the truncation of the beam).
 // The coupled step as a whole is additionally pinned on the GPU by the reference's acceptance test
 // share/picongpu/tests/KHI_growthRate (tests/test_gpu_parity.py::test_khi_growth_rate_reference_acceptance).
 // The reference binary itself cannot be built in this image (needs Boost + MPI), see DESIGN.md.
