@@ -247,6 +247,19 @@ def write(p, parts, directory):
     return name
 
 
+def write_distributed(p, part, directory, rank, world):
+    """One process per rank (torch.distributed is initialised): the parts are gathered on rank 0, which writes the
+    file; every rank returns the file name after a barrier."""
+    import torch.distributed as dist
+
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(part, parts, dst=0)
+    if rank == 0:
+        write(p, parts, directory)
+    dist.barrier()
+    return file_name(directory, part["step"])
+
+
 def read(name):
     with open(name) as f:
         return _from_json(json.load(f))

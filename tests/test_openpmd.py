@@ -120,6 +120,36 @@ def test_checkpoint_round_trip_is_bit_exact(tmp_path, slides):
         openpmd.check_restart_compatibility(bad)
 
 
+def _gloo_worker(rank, world, port, outdir):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = _params(rank, world, periodic=(1, 0, 1), moving_window=1)
+    part = _synthetic_part(p, seed=20 + rank, slides=1, step=40)
+    name = openpmd.write_distributed(p, part, outdir, rank, world)
+    back = openpmd.rank_part(openpmd.read(name), p)
+    ok = np.array_equal(back["E"], part["E"]) and np.array_equal(back["B"], part["B"])
+    for a, b in zip(back["species"], part["species"]):
+        ok = ok and all(np.array_equal(a[k], b[k]) for k in ("position", "momentum", "weighting", "cell"))
+    open(os.path.join(outdir, "ok%d" % rank), "w").write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_checkpoint_two_ranks_gloo(tmp_path):
+    """One process per rank: parts gathered on rank 0, one file, every rank finds its own patch again."""
+    import torch.multiprocessing as mp
+
+    world = 2
+    port = 29500 + (os.getpid() % 2000) + 41
+    mp.spawn(_gloo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert [open(os.path.join(str(tmp_path), "ok%d" % r)).read() for r in range(world)] == ["1", "1"]
+    tree = openpmd.read(openpmd.file_name(str(tmp_path), 40))
+    assert tree["data"]["40"]["particles"]["e"]["particlePatches"]["offset"]["y"]["data"].tolist() == [LOCAL[1], 2 * LOCAL[1]]  # one slide
+
+
 @pytest.mark.gpu
 def test_restart_continues_the_run(orc, tmp_path):
     """KHI plasma with a laser entering (the source depends on the restored step counter): 12 steps in one go against
