@@ -302,6 +302,10 @@ namespace picstep
             bool useRec = false; // this lane wrote a record phase 2 has to add
             bool stays = false;
             uint32_t myRank = 0;
+            // An arrival's rank is the return value of a global atomic.  Nothing may touch that register before the
+            // store at the end of the chunk: an OR right behind the atomic made every warp with an arrival wait for the
+            // L2 round trip there (ncu: 8.5 % of all stall samples on that one LOP3, long scoreboard).
+            [[maybe_unused]] bool arrives = false;
             // EmZ: a trajectory that changes its assignment cell is split at the relay point; the second segment is
             // kept here while phase 2 adds the first one
             [[maybe_unused]] F2 tSeg2[3][Sh::SUPP];
@@ -356,7 +360,14 @@ namespace picstep
                         if((dir[0] | dir[1] | dir[2]) == 0)
                             stays = true; // ranked per run of equal cells in phase 2
                         else
+                        {
+#ifdef PICSTEP_RANK_EAGER
                             myRank = 0x80000000u | atomicAdd(&cellCnt[k], 1u);
+#else
+                            myRank = atomicAdd(&cellCnt[k], 1u);
+                            arrives = true;
+#endif
+                        }
                     }
                     else
                     {
@@ -393,7 +404,14 @@ namespace picstep
                             if(flag)
                                 k |= flag;
                             else
+                            {
+#ifdef PICSTEP_RANK_EAGER
                                 myRank = 0x80000000u | atomicAdd(&cellCnt[k], 1u);
+#else
+                                myRank = atomicAdd(&cellCnt[k], 1u);
+                                arrives = true;
+#endif
+                            }
                         }
                     }
                     key[i] = k;
@@ -753,7 +771,13 @@ namespace picstep
                 }
             }
             if(FUSED && valid)
-                rank[i] = myRank; // last: the rank of an arrival is the return value of a global atomic
+            {
+#ifdef PICSTEP_RANK_EAGER
+                rank[i] = myRank;
+#else
+                rank[i] = arrives ? (0x80000000u | myRank) : myRank; // bit 31: arrival, ranked behind the stayers
+#endif
+            }
         }
         if(curCell >= 0)
         {
