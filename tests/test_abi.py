@@ -84,6 +84,47 @@ def test_unit_system_khi():
     assert abs(wpe_pic - wpe * 1.79e-16) / (wpe * 1.79e-16) < 1e-4
 
 
+def test_laser_and_pml_unit_conversions():
+    """Unitless incident-field and PML parameters of examples/LaserWakefield (incidentField.param, simulation.param;
+    BaseParam.hpp:43-180, GaussianPulse.hpp:93-110, fieldAbsorber.unitless:72-104) against their SI definitions computed
+    independently: a0 = e E0 / (m_e c omega), omega dt, Rayleigh length, TIME_SHIFT, focus on the transversal centre,
+    sigma_opt = 0.8 (m + 1) / (Z0 dx)."""
+    import math
+
+    dt, cell = 1.39e-16, (0.1772e-6, 0.4430e-7, 0.1772e-6)
+    p = prm.khi_params(grid=(192, 2048, 192), delta_t_si=dt, cell_si=cell, periodic=(0, 0, 0))
+    las = prm.gaussian_pulse_laser(p)
+    lam, c = 0.8e-6, prm.SPEED_OF_LIGHT_SI
+    omega_si = 2.0 * math.pi * c / lam
+    e0_si = abs(las["amplitude"]) * p.unit_efield
+    a0 = abs(prm.ELECTRON_CHARGE_SI) * e0_si / (prm.ELECTRON_MASS_SI * c * omega_si)
+    assert abs(a0 - 8.0) < 1e-5 and las["amplitude"] > 0  # UNITCONV_A0_to_Amplitude_SI = -2 pi / lambda * m_e c^2 / q_e, q_e < 0
+    assert abs(las["omega"] - omega_si * dt) < 1e-6 * omega_si * dt
+    assert abs(las["wave_length"] * p.unit_length - lam) < 1e-6 * lam
+    w0_si = 5.0e-6 / 1.17741
+    assert abs(las["w0"] * p.unit_length - w0_si) < 1e-6 * w0_si
+    z_r = math.pi * las["w0"] ** 2 / las["wave_length"] * p.unit_length
+    assert abs(z_r - math.pi * w0_si**2 / lam) < 1e-5 * z_r  # 70.8 um
+    assert abs(las["pulse_duration"] - 5.0e-15 / dt) < 1e-5 * (5.0e-15 / dt)
+    assert abs(las["time_shift"] + 0.5 * 15.0 * 5.0e-15 / dt) < 1e-4 * (37.5e-15 / dt)  # the pulse peak enters after 37.5 fs
+    assert abs(las["focus_position"][1] * p.unit_length - 4.62e-5) < 1e-10 and las["focus_origin_center"] == (1, 0, 1)
+    assert las["polarisation"] == 1 and las["position"] == ((16, -16),) * 3 and las["modes"] == (1.0,)
+    # plane wave of the same example family: RAMP_INIT, plateau
+    pw = prm.plane_wave_laser(p, a0=1.5, pulse_duration_si=10.615e-15 / 4.0, nofocus_constant_si=13.34e-15, ramp_init=20.6146)
+    assert abs(pw["nofocus_constant"] - 13.34e-15 / dt) < 1e-5 * (13.34e-15 / dt) and abs(pw["ramp_init"] - 20.6146) < 1e-5
+    # PML: SIGMA_OPT_SI = 0.8 (order + 1) / (Z0 cell), normalised by eps0 and the unit of time; alpha 0.2 S/m
+    pm = prm.pml_params(p)
+    z0 = prm.MUE0_SI * c
+    eps0 = 1.0 / (prm.MUE0_SI * c * c)
+    for d in range(3):
+        assert abs(pm["sigma_max"][d] - 0.8 * 5.0 / (z0 * cell[d]) / eps0 * dt) < 1e-5 * pm["sigma_max"][d]
+        assert abs(pm["alpha_max"][d] - 0.2 / eps0 * dt) < 1e-5 * pm["alpha_max"][d]
+    assert pm["kappa_max"] == (1.0, 1.0, 1.0) and pm["sigma_kappa_grading_order"] == 4.0 and pm["alpha_grading_order"] == 1.0
+    # ExpRampWithPrepulse: ordering check of the reference's static_assert
+    with pytest.raises(ValueError):
+        prm.exp_ramp_with_prepulse_laser(p, time_points_si=(-100e-15, -300e-15, -50e-15))
+
+
 def test_moving_window_schedule():
     """MovingWindow::getCurrentSlideInfo (MovingWindow.hpp:44-170): hand-computed answers for 4 GPUs x 16 cells,
     dy = 1, c*dt = 0.5, movePoint 0.5 (window starts to move in step 47, slides in steps 79, 111, 143, ...), and a
