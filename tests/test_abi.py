@@ -173,3 +173,51 @@ def test_params_struct_layout_matches_the_header(tmp_path):
     assert out[0] == C.sizeof(picstep.Params)
     for f, off in zip(fields, out[1:]):
         assert getattr(picstep.Params, f).offset == off, f
+
+
+def test_plain_c_caller(tmp_path):
+    """A C99 program (no C++, no Python) includes include/picstep.h, loads libpicstep.so and calls through the ABI: the
+    version string comes back, and without a CUDA device picstep_create refuses with PICSTEP_ERR_NOGPU and says why."""
+    import subprocess
+
+    src = tmp_path / "caller.c"
+    src.write_text(r"""
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include "picstep.h"
+typedef const char* (*version_fn)(void);
+typedef int (*create_fn)(const picstep_params*, picstep_ctx**);
+typedef const char* (*error_fn)(const picstep_ctx*);
+int main(int argc, char** argv)
+{
+    void* h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
+    if(!h) { printf("dlopen: %s\n", dlerror()); return 2; }
+    version_fn version = (version_fn) dlsym(h, "picstep_version");
+    create_fn create = (create_fn) dlsym(h, "picstep_create");
+    error_fn last_error = (error_fn) dlsym(h, "picstep_last_error");
+    if(!version || !create || !last_error) return 3;
+    picstep_params p;
+    memset(&p, 0, sizeof p);
+    p.grid[0] = p.grid[1] = 16; p.grid[2] = 8;
+    p.supercell[0] = p.supercell[1] = 8; p.supercell[2] = 4;
+    p.guard_supercells[0] = p.guard_supercells[1] = p.guard_supercells[2] = 1;
+    p.devices[0] = p.devices[1] = p.devices[2] = 1;
+    p.periodic[0] = p.periodic[1] = p.periodic[2] = 1;
+    p.shape = PICSTEP_SHAPE_TSC; p.pusher = PICSTEP_PUSHER_BORIS;
+    p.current_solver = PICSTEP_CURRENT_ESIRKEPOV; p.field_solver = PICSTEP_SOLVER_YEE;
+    picstep_ctx* ctx = NULL;
+    int rc = create(&p, &ctx);
+    printf("%s|%d|%s\n", version(), rc, rc ? last_error(NULL) : "created");
+    return 0;
+}
+""")
+    exe = tmp_path / "caller"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-ldl"], check=True)
+    out = subprocess.run([str(exe), picstep.lib_path(False)], capture_output=True, text=True, check=True).stdout.strip()
+    version, rc, msg = out.split("|")
+    assert version.startswith("picstep") and "sm_100a" in version
+    import torch
+
+    if not torch.cuda.is_available():
+        assert int(rc) == 5 and "no CPU fallback" in msg  # PICSTEP_ERR_NOGPU
